@@ -1,0 +1,639 @@
+/* smolscale-cuda-kernels.cu -- the device side of the B200 (sm_100a) smolscale pipeline.
+ *
+ * One fused kernel does what the reference does in four row passes (reference call stack,
+ * smolscale.c:491-546 -> smolscale-generic.c:1613-1642, :1648-2318): unpack the packed 24/32bpp
+ * source pixels into the intermediate representation (with premultiply / unpremultiply through
+ * the inverse-division tables and optional sRGB linearisation), filter horizontally, filter
+ * vertically, and repack -- intermediate rows live in registers / shared memory only and never
+ * round-trip HBM.
+ *
+ * Arithmetic contract.  The reference computes on uint64_t words that hold four 16-bit lanes
+ * ("64bpp") or two 32-bit lanes ("128bpp").  We keep the same word layout idea (so box sums use
+ * the same 64-bit adds) but write every weighted tap in its non-negative form
+ *     lerp (p, q, F) = ((p * F + q * (256 - F)) >> 8) & mask
+ * which is algebraically identical, lane by lane, to the reference's
+ *     ((((p - q) * F) >> 8) + q) & mask            (smolscale-generic.c:1317, :1704, ...)
+ * because p*F + q*(256-F) = (p-q)*F + 256*q, and never borrows across lanes: every lane product
+ * stays below the lane width for the value ranges the unpackers can produce (8-bit payload in
+ * 16-bit lanes, <= 19-bit payload in 32-bit lanes).  tests/ check all of this bit-for-bit
+ * against the compiled reference and the plain-C oracle.
+ *
+ * No tensor cores: every output is a 2-tap (bilinear) or variable-span (box) integer stencil
+ * with a floor after each tap, i.e. bandwidth-bound byte work, not a dense contraction. */
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "smolscale-cuda-private.h"
+
+#define SMOL_BLOCK 256
+
+/* ------------------------------------------------------------------------------------------ *
+ * Intermediate pixel: 1 (64bpp) or 2 (128bpp) 64-bit words.                                  *
+ *   64bpp : w[0] = alpha | c0 << 16 | c1 << 32 | c2 << 48       (8-bit payloads)             *
+ *   128bpp: w[0] = alpha | c0 << 32,  w[1] = c1 | c2 << 32      (up to 19-bit payloads)      *
+ * c0..c2 are the colour channels in INPUT memory order.  The reference orders lanes per pixel *
+ * type (smolscale.c:647-719); since all lanes are filtered alike, lane order is free.        *
+ * ------------------------------------------------------------------------------------------ */
+
+template <bool S128> struct Px { uint64_t w[S128 ? 2 : 1]; };
+
+template <bool S128> struct PxTraits;
+template <> struct PxTraits<false> { static constexpr uint64_t MASK = 0x00ff00ff00ff00ffULL; static constexpr int N = 1; };
+template <> struct PxTraits<true>  { static constexpr uint64_t MASK = 0x00ffffff00ffffffULL; static constexpr int N = 2; };
+
+template <bool S128> __device__ __forceinline__ Px<S128> px_zero ()
+{
+    Px<S128> r;
+#pragma unroll
+    for (int i = 0; i < PxTraits<S128>::N; i++) r.w[i] = 0;
+    return r;
+}
+
+template <bool S128> __device__ __forceinline__ void px_add (Px<S128> &a, const Px<S128> &b)
+{
+#pragma unroll
+    for (int i = 0; i < PxTraits<S128>::N; i++) a.w[i] += b.w[i];
+}
+
+/* ((p * w) >> 8) & mask -- reference weight_pixel_64bpp / _128bpp (generic:1177-1192); also the
+ * "(255 - F) * r" left-over of a box edge (generic:1462, :1524, :2065) since
+ * ((r << 8) - r - r * F) == r * (255 - F). */
+template <bool S128> __device__ __forceinline__ Px<S128> px_weight (const Px<S128> &p, uint32_t w)
+{
+    Px<S128> r;
+#pragma unroll
+    for (int i = 0; i < PxTraits<S128>::N; i++) r.w[i] = ((p.w[i] * w) >> 8) & PxTraits<S128>::MASK;
+    return r;
+}
+
+template <bool S128> __device__ __forceinline__ Px<S128> px_lerp (const Px<S128> &p, const Px<S128> &q, uint32_t F)
+{
+    Px<S128> r;
+#pragma unroll
+    for (int i = 0; i < PxTraits<S128>::N; i++)
+        r.w[i] = ((p.w[i] * F + q.w[i] * (256u - F)) >> 8) & PxTraits<S128>::MASK;
+    return r;
+}
+
+/* (acc >> n) & mask -- the halving step (generic:1319, :1357-1358, :1806, :1834) */
+template <bool S128> __device__ __forceinline__ Px<S128> px_halve (const Px<S128> &a, uint32_t n)
+{
+    Px<S128> r;
+#pragma unroll
+    for (int i = 0; i < PxTraits<S128>::N; i++) r.w[i] = (a.w[i] >> n) & PxTraits<S128>::MASK;
+    return r;
+}
+
+/* Box normalisation: scale_64bpp (generic:1231-1245) / scale_128bpp_half (generic:1247-1261). */
+template <bool S128> __device__ __forceinline__ Px<S128> px_box_scale (const Px<S128> &acc, uint32_t mul)
+{
+    Px<S128> r;
+    const uint64_t half = 1ull << 23;
+    if constexpr (!S128)
+    {
+        uint64_t a = ((acc.w[0] & 0x0000ffff0000ffffULL) * mul + half + (half << 32)) >> 24;
+        uint64_t b = (((acc.w[0] & 0xffff0000ffff0000ULL) >> 16) * mul + half + (half << 32)) >> 24;
+        r.w[0] = (a & 0x000000ff000000ffULL) | ((b & 0x000000ff000000ffULL) << 16);
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+        {
+            uint64_t a = ((acc.w[i] & 0xffffffffULL) * mul + half) >> 24;
+            uint64_t b = ((acc.w[i] >> 32) * mul + half) >> 24;
+            r.w[i] = (a & 0xffffULL) | ((b & 0xffffULL) << 32);
+        }
+    }
+    return r;
+}
+
+template <bool S128> __device__ __forceinline__ Px<S128> px_shfl_xor_add (Px<S128> a, uint32_t m)
+{
+#pragma unroll
+    for (int i = 0; i < PxTraits<S128>::N; i++)
+        a.w[i] += __shfl_xor_sync (0xffffffffu, a.w[i], m);
+    return a;
+}
+
+/* ------------------------------------------------------------------------------------------ *
+ * Unpack / pack (reference smolscale-generic.c:349-1164 with helpers :185-318)               *
+ * ------------------------------------------------------------------------------------------ */
+
+/* raw = the pixel's bytes in memory order, byte 0 in bits 0..7 (for 24bpp the top byte is ignored) */
+template <bool S128>
+__device__ __forceinline__ Px<S128> unpack_px (uint32_t raw, const SmolJobDesc &d, const SmolDeviceLuts *__restrict__ lut)
+{
+    uint32_t a = (d.in_alpha_idx == 0xff) ? 255u : ((raw >> (8 * d.in_alpha_idx)) & 0xff);
+    uint32_t alane = a;
+    uint32_t c[3];
+
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        c[i] = (raw >> (8 * (d.in_col0 + i))) & 0xff;
+
+    if (d.mid == SMOL_MID_P8)
+    {
+        if (d.in_unassoc)
+        {
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                c[i] = (((c[i] + 1) * (a + 1) - 1) >> 8) & 0xff;                 /* generic:238-244 */
+        }
+    }
+    else if (d.mid == SMOL_MID_P8L)
+    {
+        const uint32_t inv = d.in_unassoc ? 0 : lut->inv_div_p8[a];
+        const uint32_t am = (a << 3) + 1;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            uint32_t v = c[i];
+            if (!d.in_unassoc)
+                v = ((v * inv) >> 13) & 0xff;                                    /* generic:227-236 */
+            v = lut->from_srgb[v];                                               /* generic:185-199 */
+            c[i] = (((v + 1) * am - 1) >> 11) & 0x7ff;                           /* generic:261-269 */
+        }
+    }
+    else
+    {
+        /* P16 / P16L: value * alpha, alpha lane carries 8 fraction bits (generic:616-660, :708-752) */
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            uint32_t v = c[i];
+            if (d.mid == SMOL_MID_P16L)
+                v = lut->from_srgb[v];
+            c[i] = v * a;
+        }
+        alane = (a << 8) | 0x80;
+    }
+
+    Px<S128> r;
+    if constexpr (S128)
+    {
+        r.w[0] = (uint64_t) alane | ((uint64_t) c[0] << 32);
+        r.w[1] = (uint64_t) c[1] | ((uint64_t) c[2] << 32);
+    }
+    else
+    {
+        r.w[0] = (uint64_t) alane | ((uint64_t) c[0] << 16) | ((uint64_t) c[1] << 32) | ((uint64_t) c[2] << 48);
+    }
+    return r;
+}
+
+/* Returns the output pixel's bytes in memory order (byte 0 in bits 0..7). */
+template <bool S128>
+__device__ __forceinline__ uint32_t pack_px (const Px<S128> &p, const SmolJobDesc &d, const SmolDeviceLuts *__restrict__ lut)
+{
+    uint64_t lane[4];   /* alpha lane, c0, c1, c2 */
+
+    if constexpr (S128)
+    {
+        lane[0] = p.w[0] & 0xffffffffULL; lane[1] = p.w[0] >> 32;
+        lane[2] = p.w[1] & 0xffffffffULL; lane[3] = p.w[1] >> 32;
+    }
+    else
+    {
+        lane[0] = p.w[0] & 0xffff; lane[1] = (p.w[0] >> 16) & 0xffff;
+        lane[2] = (p.w[0] >> 32) & 0xffff; lane[3] = p.w[0] >> 48;
+    }
+
+    uint32_t a;
+    uint32_t c[3];
+
+    if (d.mid == SMOL_MID_P16 || d.mid == SMOL_MID_P16L)
+        a = (uint32_t) (lane[0] >> 8) & 0xff;                                    /* generic:1140, :1152 */
+    else
+        a = (uint32_t) lane[0] & 0xff;                                           /* generic:876, :1101 */
+
+    if (d.mid == SMOL_MID_P8)
+    {
+        const uint32_t inv = lut->inv_div_p8[a];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            uint64_t v = lane[i + 1];
+            if (d.out_unassoc)
+                v = ((v & 0xff) * inv) >> 13;                                    /* generic:246-259 */
+            c[i] = (uint32_t) v & 0xff;
+        }
+    }
+    else if (d.mid == SMOL_MID_P8L)
+    {
+        const uint32_t inv = lut->inv_div_p8l[a];
+        const bool unpremul = !(d.bpp_out == 3 && d.pack24_direct);              /* generic:922-935 vs :1010-1023 */
+        const bool repremul = (d.bpp_out == 4 && !d.out_unassoc);                /* generic:1096-1109 */
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            uint64_t v = lane[i + 1];
+            if (unpremul)
+                v = (v * inv) >> 10;                                             /* generic:271-280 */
+            v = lut->to_srgb[v & 0x7ff];                                         /* generic:201-211 */
+            if (repremul)
+                v = (((v + 1) * (a + 1) - 1) >> 8) & 0xff;                       /* generic:217-225 */
+            c[i] = (uint32_t) v & 0xff;
+        }
+    }
+    else if (d.mid == SMOL_MID_P16)
+    {
+        const uint32_t inv = lut->inv_div_p16[a];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            c[i] = (uint32_t) ((lane[i + 1] * inv) >> 16) & 0xff;                /* generic:290-299 */
+    }
+    else
+    {
+        const uint32_t inv = lut->inv_div_p16l[a];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            c[i] = lut->to_srgb[(uint32_t) ((lane[i + 1] * inv) >> 19) & 0x7ff]; /* generic:309-318 */
+    }
+
+    if (d.swap_rb)
+    {
+        uint32_t t = c[0]; c[0] = c[2]; c[2] = t;
+    }
+
+    uint32_t out = (c[0] << (8 * d.out_col0)) | (c[1] << (8 * (d.out_col0 + 1))) | (c[2] << (8 * (d.out_col0 + 2)));
+    if (d.out_alpha_idx != 0xff)
+        out |= a << (8 * d.out_alpha_idx);
+    return out;
+}
+
+__device__ __forceinline__ uint32_t load_raw_px (const uint8_t *s, uint32_t bpp)
+{
+    if (bpp == 4 && (((uintptr_t) s) & 3) == 0)
+        return *reinterpret_cast<const uint32_t *> (s);
+    uint32_t v = (uint32_t) s[0] | ((uint32_t) s[1] << 8) | ((uint32_t) s[2] << 16);
+    if (bpp == 4)
+        v |= (uint32_t) s[3] << 24;
+    return v;
+}
+
+__device__ __forceinline__ void store_raw_px (uint8_t *o, uint32_t v, uint32_t bpp)
+{
+    if (bpp == 4 && (((uintptr_t) o) & 3) == 0)
+    {
+        *reinterpret_cast<uint32_t *> (o) = v;
+        return;
+    }
+    o[0] = (uint8_t) v; o[1] = (uint8_t) (v >> 8); o[2] = (uint8_t) (v >> 16);
+    if (bpp == 4)
+        o[3] = (uint8_t) (v >> 24);
+}
+
+__device__ __forceinline__ uint4 ldg_nc_v4 (const void *p)
+{
+    uint4 r;
+    asm volatile ("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+/* Cooperative copy of global bytes [gbeg, gend) into shared memory such that the byte at global
+ * address A lands at sm[A - (gbeg & ~15)]: alignment (mod 16) is preserved, whole 16-byte
+ * chunks move as one 128-bit load, and no byte outside [gbeg, gend) is touched. */
+__device__ __forceinline__ void stage_bytes (uint8_t *sm, const uint8_t *gbeg, const uint8_t *gend)
+{
+    const uint8_t *abase = reinterpret_cast<const uint8_t *> (reinterpret_cast<uintptr_t> (gbeg) & ~(uintptr_t) 15);
+    const uint32_t n_chunks = (uint32_t) ((gend - abase + 15) >> 4);
+
+    for (uint32_t k = threadIdx.x; k < n_chunks; k += blockDim.x)
+    {
+        const uint8_t *ca = abase + 16 * (size_t) k;
+        if (ca >= gbeg && ca + 16 <= gend)
+        {
+            *reinterpret_cast<uint4 *> (sm + 16 * (size_t) k) = ldg_nc_v4 (ca);
+        }
+        else
+        {
+            for (int b = 0; b < 16; b++)
+                if (ca + b >= gbeg && ca + b < gend)
+                    sm[16 * (size_t) k + b] = ca[b];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ *
+ * General kernel: any filter pair, any format.                                               *
+ *                                                                                            *
+ * A CTA owns TW output columns x rows_per_cta output rows.  `lanes_per_col` (G) threads       *
+ * cooperate on one output column (G > 1 only for wide box spans; the G partial sums are       *
+ * combined with warp shuffles).  The CTA walks its output rows top to bottom; for every       *
+ * source row it needs it stages the row segment [sx0, sx1] into shared memory with coalesced  *
+ * 128-bit loads, every thread horizontally filters its own column from there, and the result  *
+ * goes straight into the thread's vertical accumulator (box) or its two-row register cache    *
+ * (taps -- the device analogue of the reference's SmolVerticalCtx, generic:1648-1682).        *
+ * ------------------------------------------------------------------------------------------ */
+
+template <bool S128, bool HBOX>
+struct HState
+{
+    uint32_t x;            /* output column (clamped) */
+    uint32_t g, G;         /* lane within the column group */
+    uint32_t sx0, sx1;     /* CTA source column range, inclusive */
+    /* box */
+    uint32_t hL, hR, wl, wr;
+};
+
+template <bool S128, bool HBOX>
+__device__ __forceinline__ Px<S128>
+hfilter_row (const SmolLaunch &L, const uint8_t *__restrict__ src_row, uint8_t *sm_raw,
+             const HState<S128, HBOX> &hs)
+{
+    const SmolJobDesc &d = L.d;
+    const uint32_t bpp = d.bpp_in;
+    Px<S128> acc = px_zero<S128> ();
+
+    for (uint32_t c0 = hs.sx0; c0 <= hs.sx1; c0 += L.chunk_px)
+    {
+        const uint32_t c1 = min (c0 + L.chunk_px, hs.sx1 + 1);                 /* exclusive */
+        const uint32_t c1s = HBOX ? c1 : min (c1 + 1, hs.sx1 + 1);             /* taps read one pixel past */
+        const uint8_t *gbeg = src_row + (size_t) c0 * bpp;
+        const uint8_t *gend = src_row + (size_t) c1s * bpp;
+
+        __syncthreads ();
+        stage_bytes (sm_raw, gbeg, gend);
+        __syncthreads ();
+
+        const uint32_t sm_ofs = (uint32_t) (reinterpret_cast<uintptr_t> (gbeg) & 15);
+
+        if constexpr (HBOX)
+        {
+            const uint32_t lo = max (hs.hL, c0), hi = min (hs.hR, c1 - 1);
+            uint32_t j = hs.hL + hs.g;
+            if (j < lo)
+                j += ((lo - j + hs.G - 1) / hs.G) * hs.G;
+            for (; j <= hi; j += hs.G)
+            {
+                Px<S128> p = unpack_px<S128> (load_raw_px (sm_raw + sm_ofs + (size_t) (j - c0) * bpp, bpp), d, L.luts);
+                if (j == hs.hL)
+                    p = px_weight<S128> (p, hs.wl);
+                else if (j == hs.hR)
+                    p = px_weight<S128> (p, hs.wr);
+                px_add<S128> (acc, p);
+            }
+        }
+        else
+        {
+            const uint32_t n = 1u << d.h_halvings;
+            for (uint32_t k = 0; k < n; k++)
+            {
+                const uint32_t e = __ldg (&L.tab_x[(hs.x << d.h_halvings) + k]);
+                const uint32_t ofs = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e);
+                if (ofs >= c0 && ofs < c1)
+                {
+                    const uint32_t ofs2 = min (ofs + 1, d.w_in - 1);
+                    Px<S128> p = unpack_px<S128> (load_raw_px (sm_raw + sm_ofs + (size_t) (ofs - c0) * bpp, bpp), d, L.luts);
+                    Px<S128> q = unpack_px<S128> (load_raw_px (sm_raw + sm_ofs + (size_t) (ofs2 - c0) * bpp, bpp), d, L.luts);
+                    px_add<S128> (acc, px_lerp<S128> (p, q, F));
+                }
+            }
+        }
+    }
+
+    if constexpr (HBOX)
+    {
+        for (uint32_t m = hs.G >> 1; m; m >>= 1)
+            acc = px_shfl_xor_add<S128> (acc, m);
+        return px_box_scale<S128> (acc, d.span_mul_x);
+    }
+    else
+    {
+        return px_halve<S128> (acc, d.h_halvings);
+    }
+}
+
+template <bool S128, bool HBOX, bool VBOX>
+__global__ void __launch_bounds__ (SMOL_BLOCK)
+smol_general_kernel (const SmolLaunch L)
+{
+    extern __shared__ __align__ (16) uint8_t sm_raw[];
+
+    const SmolJobDesc &d = L.d;
+    const uint32_t G = L.lanes_per_col;
+    const uint32_t TW = blockDim.x / G;
+    const uint32_t x0 = blockIdx.x * TW;
+    const uint32_t xlast = min (x0 + TW, d.w_out) - 1;
+    const uint8_t *src = L.src + (size_t) blockIdx.z * L.src_image_stride;
+    uint8_t *dst = L.dst + (size_t) blockIdx.z * L.dst_image_stride;
+
+    HState<S128, HBOX> hs;
+    hs.G = G;
+    hs.g = threadIdx.x & (G - 1);
+    hs.x = x0 + threadIdx.x / G;
+    const bool active = hs.x < d.w_out && hs.g == 0;
+    if (hs.x >= d.w_out)
+        hs.x = d.w_out - 1;
+
+    if constexpr (HBOX)
+    {
+        const uint32_t e0 = __ldg (&L.tab_x[hs.x]), e1 = __ldg (&L.tab_x[hs.x + 1]);
+        hs.hL = SMOL_TAB_OFS (e0);
+        hs.hR = SMOL_TAB_OFS (e1);
+        hs.wr = SMOL_TAB_F (e0);
+        hs.wl = (hs.x == 0) ? 256u : 255u - SMOL_TAB_F (__ldg (&L.tab_x[hs.x - 1]));
+        hs.sx0 = SMOL_TAB_OFS (__ldg (&L.tab_x[x0]));
+        hs.sx1 = SMOL_TAB_OFS (__ldg (&L.tab_x[xlast + 1]));
+    }
+    else
+    {
+        hs.hL = hs.hR = hs.wl = hs.wr = 0;
+        hs.sx0 = SMOL_TAB_OFS (__ldg (&L.tab_x[x0 << d.h_halvings]));
+        hs.sx1 = min (SMOL_TAB_OFS (__ldg (&L.tab_x[((xlast + 1) << d.h_halvings) - 1])) + 1, d.w_in - 1);
+    }
+
+    const uint32_t y_begin = L.first_row + blockIdx.y * L.rows_per_cta;
+    const uint32_t y_end = min (y_begin + L.rows_per_cta, L.first_row + L.n_rows);
+
+    /* two-row cache for the vertical taps */
+    uint32_t idx0 = 0xffffffffu, idx1 = 0xffffffffu;
+    Px<S128> row0 = px_zero<S128> (), row1 = px_zero<S128> ();
+
+    for (uint32_t y = y_begin; y < y_end; y++)
+    {
+        Px<S128> out;
+
+        if constexpr (VBOX)
+        {
+            /* generic:2112-2161 (64bpp) and :2198-2260 (128bpp) */
+            const uint32_t e0 = __ldg (&L.tab_y[y]), e1 = __ldg (&L.tab_y[y + 1]);
+            const uint32_t T = SMOL_TAB_OFS (e0), B = SMOL_TAB_OFS (e1), Fy = SMOL_TAB_F (e0);
+            const uint32_t w1 = (y == 0) ? 256u : 255u - SMOL_TAB_F (__ldg (&L.tab_y[y - 1]));
+
+            Px<S128> acc = px_weight<S128> (hfilter_row<S128, HBOX> (L, src + (size_t) T * L.src_pitch, sm_raw, hs), w1);
+            for (uint32_t r = T + 1; r < B; r++)
+                px_add<S128> (acc, hfilter_row<S128, HBOX> (L, src + (size_t) r * L.src_pitch, sm_raw, hs));
+            if (Fy > 0)
+            {
+                /* 128bpp weighs the trailing row by F - 1, 64bpp by F (generic:2247-2249 vs :2129-2137) */
+                const uint32_t w2 = S128 ? Fy - 1 : Fy;
+                px_add<S128> (acc, px_weight<S128> (hfilter_row<S128, HBOX> (L, src + (size_t) B * L.src_pitch, sm_raw, hs), w2));
+            }
+            out = px_box_scale<S128> (acc, d.span_mul_y);
+        }
+        else
+        {
+            const uint32_t n = 1u << d.v_halvings;
+            Px<S128> acc = px_zero<S128> ();
+
+            for (uint32_t k = 0; k < n; k++)
+            {
+                const uint32_t e = __ldg (&L.tab_y[(y << d.v_halvings) + k]);
+                const uint32_t r0 = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e);
+                const uint32_t r1 = min (r0 + 1, d.h_in - 1);
+
+                /* F == 256 needs only the top row, F == 0 only the bottom one */
+                if (F != 0)
+                {
+                    if (r0 == idx1)
+                    {
+                        Px<S128> t = row0; row0 = row1; row1 = t;
+                        uint32_t ti = idx0; idx0 = idx1; idx1 = ti;
+                    }
+                    else if (r0 != idx0)
+                    {
+                        row0 = hfilter_row<S128, HBOX> (L, src + (size_t) r0 * L.src_pitch, sm_raw, hs);
+                        idx0 = r0;
+                    }
+                }
+                if (F != 256)
+                {
+                    if (r1 != idx1)
+                    {
+                        if (r1 == idx0)
+                            row1 = row0;
+                        else
+                            row1 = hfilter_row<S128, HBOX> (L, src + (size_t) r1 * L.src_pitch, sm_raw, hs);
+                        idx1 = r1;
+                    }
+                }
+                Px<S128> v;
+                if (F == 256)
+                    v = px_halve<S128> (row0, 0);
+                else if (F == 0)
+                    v = px_halve<S128> (row1, 0);
+                else
+                    v = px_lerp<S128> (row0, row1, F);
+                px_add<S128> (acc, v);
+            }
+            out = px_halve<S128> (acc, d.v_halvings);
+        }
+
+        if (active)
+        {
+            uint8_t *o = dst + (size_t) (y - L.first_row) * L.dst_pitch + (size_t) hs.x * d.bpp_out;
+            store_raw_px (o, pack_px<S128> (out, d, L.luts), d.bpp_out);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ *
+ * Host-side dispatch                                                                         *
+ * ------------------------------------------------------------------------------------------ */
+
+static const char *const kernel_names[SMOL_KERNEL_MAX] =
+{
+    "auto", "general", "taps_direct", "half2x", "box"
+};
+
+extern "C" const char *
+smol_cuda_kernel_name (int kernel_id)
+{
+    if (kernel_id < 0 || kernel_id >= SMOL_KERNEL_MAX)
+        return "invalid";
+    return kernel_names[kernel_id];
+}
+
+extern "C" int
+smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
+{
+    (void) launch;
+    if (forced > SMOL_KERNEL_AUTO && forced < SMOL_KERNEL_MAX)
+        return SMOL_KERNEL_GENERAL;
+    return SMOL_KERNEL_GENERAL;
+}
+
+template <bool S128, bool HBOX, bool VBOX>
+static cudaError_t
+launch_general (const SmolLaunch &L, cudaStream_t stream)
+{
+    const uint32_t TW = SMOL_BLOCK / L.lanes_per_col;
+    dim3 grid ((L.d.w_out + TW - 1) / TW, (L.n_rows + L.rows_per_cta - 1) / L.rows_per_cta, L.n_images);
+    /* chunk + one extra pixel for the taps + 16 bytes of alignment slack, rounded to 16 */
+    size_t smem = ((size_t) (L.chunk_px + 1) * L.d.bpp_in + 16 + 15) & ~(size_t) 15;
+
+    smol_general_kernel<S128, HBOX, VBOX><<<grid, SMOL_BLOCK, smem, stream>>> (L);
+    return cudaGetLastError ();
+}
+
+/* Launch shape for the general kernel. */
+static void
+shape_general (SmolLaunch &L)
+{
+    const SmolJobDesc &d = L.d;
+    uint32_t G = 1;
+
+    if (d.h_kind == SMOL_AXIS_BOX)
+    {
+        /* one thread per ~8..16 source pixels of a span */
+        const uint32_t ratio = d.w_in / d.w_out;
+        while (G < 32 && ratio >= 16 * G)
+            G *= 2;
+    }
+    L.lanes_per_col = G;
+    L.chunk_px = 4096;
+
+    if (d.v_kind == SMOL_AXIS_BOX)
+    {
+        L.rows_per_cta = 1;
+    }
+    else
+    {
+        /* walking several rows per CTA lets the two-row cache work; keep >= ~8 CTAs per SM */
+        const uint32_t TW = SMOL_BLOCK / G;
+        const uint64_t col_tiles = (d.w_out + TW - 1) / TW;
+        uint32_t th = 16;
+        while (th > 1 && col_tiles * ((L.n_rows + th - 1) / th) * L.n_images < 148u * 8u)
+            th >>= 1;
+        L.rows_per_cta = th;
+    }
+}
+
+extern "C" int
+smol_cuda_launch (const SmolLaunch *launch, int kernel_id, void *stream_p, const char **name_out)
+{
+    cudaStream_t stream = (cudaStream_t) stream_p;
+    SmolLaunch L = *launch;
+    const bool hb = L.d.h_kind == SMOL_AXIS_BOX, vb = L.d.v_kind == SMOL_AXIS_BOX;
+    cudaError_t err;
+
+    (void) kernel_id;
+    if (name_out)
+        *name_out = kernel_names[SMOL_KERNEL_GENERAL];
+
+    if (L.n_rows == 0 || L.n_images == 0)
+        return 0;
+
+    shape_general (L);
+
+    if (L.d.storage128)
+    {
+        if (hb && vb)       err = launch_general<true, true, true> (L, stream);
+        else if (hb)        err = launch_general<true, true, false> (L, stream);
+        else if (vb)        err = launch_general<true, false, true> (L, stream);
+        else                err = launch_general<true, false, false> (L, stream);
+    }
+    else
+    {
+        if (hb && vb)       err = launch_general<false, true, true> (L, stream);
+        else if (hb)        err = launch_general<false, true, false> (L, stream);
+        else if (vb)        err = launch_general<false, false, true> (L, stream);
+        else                err = launch_general<false, false, false> (L, stream);
+    }
+    return (int) err;
+}

@@ -1,0 +1,1141 @@
+/* smolscale-cuda.c -- host side of the B200 implementation of the smolscale.h API.
+ *
+ * What lives here (all plain C; the only CUDA it touches is the runtime's C API):
+ *   - job planning: which filter each axis gets, which intermediate encoding, the fixed-point
+ *     offset / weight tables -- integer code that must reproduce the reference's choices exactly
+ *     (reference smolscale.c:427-478, :724-814; smolscale-generic.c:14-135);
+ *   - pointer classification (host / pinned / managed / device) and, for host memory, staging of
+ *     exactly the source row band (+ filter halo) a batch needs;
+ *   - per-device state: the data tables, a cache of uploaded filter tables keyed by geometry,
+ *     a small pool of stream + staging-buffer "lanes" so concurrent smol_scale_batch callers
+ *     (the reference's threading model, smolscale.h:70-74) overlap instead of serialising;
+ *   - the seven public entry points and the optional smol_cuda_* extensions.
+ *
+ * There is no CPU implementation of the pipeline in this file or anywhere in the product: if
+ * CUDA is unusable the entry points abort with a message. */
+
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <cuda_runtime_api.h>
+
+#include "smolscale.h"
+#include "smolscale-cuda.h"
+#include "smolscale-cuda-private.h"
+#include "smolscale-cuda-luts.h"
+
+#define SMOL_MAX_DEVICES 16
+#define SMOL_MAX_LANES 16
+#define SMOL_TAB_CACHE_MAX 96
+
+#define SMOL_EXPORT __attribute__ ((visibility ("default")))
+
+static void
+smol_fatal (const char *what, const char *detail)
+{
+    fprintf (stderr, "smolscale-cuda: fatal: %s%s%s\n", what, detail ? ": " : "", detail ? detail : "");
+    fflush (stderr);
+    abort ();
+}
+
+#define CK(call) \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) smol_fatal (#call, cudaGetErrorString (e_)); } while (0)
+
+/* ------------------------------------------------------------------------------------------ *
+ * Planning (pure host code)                                                                  *
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct
+{
+    int filter;             /* SMOL_CUDA_AXIS_* (the reference's choice) */
+    uint32_t halvings;
+    uint32_t bilin_dim;
+    int storage_bits;
+}
+AxisPick;
+
+/* reference smolscale.c:427-478 */
+static AxisPick
+pick_axis (uint32_t dim_in, uint32_t dim_out, uint8_t with_srgb)
+{
+    AxisPick a;
+
+    a.halvings = 0;
+    a.bilin_dim = dim_out;
+    a.storage_bits = with_srgb ? 128 : 64;
+
+    if (dim_in > dim_out * 255)
+    {
+        a.filter = SMOL_CUDA_AXIS_BOX;
+        a.storage_bits = 128;
+    }
+    else if (dim_in > dim_out * 8)
+    {
+        a.filter = SMOL_CUDA_AXIS_BOX;
+    }
+    else if (dim_in == 1)
+    {
+        a.filter = SMOL_CUDA_AXIS_ONE;
+    }
+    else if (dim_in == dim_out)
+    {
+        a.filter = SMOL_CUDA_AXIS_COPY;
+    }
+    else
+    {
+        uint32_t d = dim_out;
+
+        for (;;)
+        {
+            d *= 2;
+            if (d >= dim_in)
+                break;
+            a.halvings++;
+        }
+        a.filter = SMOL_CUDA_AXIS_BILINEAR;
+        a.bilin_dim = dim_out << a.halvings;
+    }
+    return a;
+}
+
+typedef struct
+{
+    int alpha_idx;      /* -1: none */
+    int col0;
+    int bgr;
+    int unassoc;
+    int bpp;
+}
+TypeInfo;
+
+/* Memory layout of the ten public pixel types (reference smolscale.h:14-35, smolscale.c:45-75). */
+static TypeInfo
+type_info (SmolPixelType t)
+{
+    TypeInfo ti;
+
+    if ((int) t < 0 || t >= SMOL_PIXEL_MAX)
+        smol_fatal ("invalid SmolPixelType", NULL);
+
+    if (t == SMOL_PIXEL_RGB8 || t == SMOL_PIXEL_BGR8)
+    {
+        ti.bpp = 3; ti.alpha_idx = -1; ti.col0 = 0; ti.unassoc = 0;
+        ti.bgr = (t == SMOL_PIXEL_BGR8);
+        return ti;
+    }
+    ti.bpp = 4;
+    ti.unassoc = (t >= SMOL_PIXEL_RGBA8_UNASSOCIATED);
+    switch ((int) t & 3)
+    {
+        case 0: ti.alpha_idx = 3; ti.col0 = 0; ti.bgr = 0; break;   /* RGBA */
+        case 1: ti.alpha_idx = 3; ti.col0 = 0; ti.bgr = 1; break;   /* BGRA */
+        case 2: ti.alpha_idx = 0; ti.col0 = 1; ti.bgr = 0; break;   /* ARGB */
+        default: ti.alpha_idx = 0; ti.col0 = 1; ti.bgr = 1; break;  /* ABGR */
+    }
+    return ti;
+}
+
+/* Reference-layout tables: (absolute offset, F) uint16 pairs. */
+
+/* reference smolscale-generic.c:14-66 (offsets kept absolute for both axes) */
+static uint16_t *
+make_bilinear_pairs (uint32_t dim_in, uint32_t n)
+{
+    uint16_t *t = malloc ((size_t) n * 2 * sizeof (uint16_t));
+    const uint64_t unit = (uint64_t) 1 << 32;
+    uint64_t step, pos;
+    uint32_t i;
+
+    if (!t)
+        smol_fatal ("out of memory", NULL);
+
+    if (dim_in > n)
+    {
+        step = ((uint64_t) dim_in * unit) / n;
+        pos = (step - unit) / 2;
+    }
+    else
+    {
+        step = ((uint64_t) (dim_in - 1) * unit) / (n > 1 ? n - 1 : 1);
+        pos = 0;
+    }
+
+    for (i = 0; i < n; i++)
+    {
+        uint64_t at = pos + (uint64_t) i * step;
+        uint32_t ofs = (uint32_t) (at >> 32) & 0xffff;
+
+        if (ofs >= dim_in - 1)
+            break;
+        t[2 * i] = (uint16_t) ofs;
+        t[2 * i + 1] = (uint16_t) (256 - ((at >> 24) & 0xff));
+    }
+    /* once a sample would need the pixel past the end: 100 % of the last pixel */
+    for (; i < n; i++)
+    {
+        t[2 * i] = (uint16_t) (dim_in - 2);
+        t[2 * i + 1] = 0;
+    }
+    return t;
+}
+
+/* reference smolscale-generic.c:68-135 (absolute offsets, dim_out + 1 pairs) */
+static uint16_t *
+make_box_pairs (uint32_t dim_in, uint32_t dim_out, uint32_t *span_mul)
+{
+    uint16_t *t = malloc (((size_t) dim_out + 1) * 2 * sizeof (uint16_t));
+    const uint64_t step = ((uint64_t) dim_in << 16) / dim_out;
+    uint64_t whole = step >> 16, part = (step >> 8) & 0xff;
+    uint64_t num = ((uint64_t) 255) << 24;
+    uint64_t den = whole * 255 + (part * 255) / 256;
+    uint32_t begin = 0, i;
+
+    if (!t)
+        smol_fatal ("out of memory", NULL);
+    *span_mul = (uint32_t) ((num + den / 2) / den);
+
+    for (i = 0; i < dim_out; i++)
+    {
+        uint64_t at = (uint64_t) (i + 1) * step;
+        uint32_t end = (uint32_t) (at >> 16) & 0xffff;
+
+        if (begin >= dim_in - 1)
+        {
+            begin = dim_in - 1;
+            break;
+        }
+        if (end > dim_in - 1)
+        {
+            end = dim_in - 1;
+            if (end <= begin)
+                break;
+        }
+        t[2 * i] = (uint16_t) begin;
+        t[2 * i + 1] = (uint16_t) ((at >> 8) & 0xff);
+        begin = end;
+    }
+    for (; i <= dim_out; i++)
+    {
+        t[2 * i] = (uint16_t) begin;
+        t[2 * i + 1] = 0;
+    }
+    return t;
+}
+
+typedef struct
+{
+    int filter;                 /* SMOL_CUDA_AXIS_* */
+    uint32_t dim_in, dim_out;
+    uint32_t halvings, bilin_dim;
+    uint32_t span_mul;
+    uint16_t *pairs;            /* reference-layout pairs, NULL for copy / one */
+    uint32_t n_pairs;
+    uint32_t *dev_entries;      /* host copy of the device table (packed ofs | F << 16) */
+    uint32_t n_entries;
+    uint8_t kind;               /* SMOL_AXIS_* */
+    uint8_t all_half;
+}
+AxisPlan;
+
+static void
+axis_plan_init (AxisPlan *ap, AxisPick pick, uint32_t dim_in, uint32_t dim_out)
+{
+    uint32_t i;
+
+    memset (ap, 0, sizeof (*ap));
+    ap->filter = pick.filter;
+    ap->dim_in = dim_in;
+    ap->dim_out = dim_out;
+    ap->halvings = pick.halvings;
+    ap->bilin_dim = pick.bilin_dim;
+
+    if (pick.filter == SMOL_CUDA_AXIS_BOX)
+    {
+        ap->kind = SMOL_AXIS_BOX;
+        ap->pairs = make_box_pairs (dim_in, dim_out, &ap->span_mul);
+        ap->n_pairs = dim_out + 1;
+        ap->n_entries = dim_out + 1;
+    }
+    else
+    {
+        ap->kind = SMOL_AXIS_TAPS;
+        ap->n_entries = pick.bilin_dim;
+        if (pick.filter == SMOL_CUDA_AXIS_BILINEAR)
+        {
+            ap->pairs = make_bilinear_pairs (dim_in, pick.bilin_dim);
+            ap->n_pairs = pick.bilin_dim;
+        }
+    }
+
+    ap->dev_entries = malloc ((size_t) ap->n_entries * sizeof (uint32_t));
+    if (!ap->dev_entries)
+        smol_fatal ("out of memory", NULL);
+
+    for (i = 0; i < ap->n_entries; i++)
+    {
+        uint32_t ofs, F;
+
+        if (ap->pairs)
+        {
+            ofs = ap->pairs[2 * i];
+            F = ap->pairs[2 * i + 1];
+        }
+        else if (pick.filter == SMOL_CUDA_AXIS_COPY)
+        {
+            ofs = i; F = 256;       /* reference generic:1591-1611, :2306-2318 */
+        }
+        else
+        {
+            ofs = 0; F = 256;       /* reference generic:1558-1589, :2262-2304 */
+        }
+        ap->dev_entries[i] = ofs | (F << 16);
+    }
+
+    ap->all_half = 0;
+    if (pick.filter == SMOL_CUDA_AXIS_BILINEAR)
+    {
+        ap->all_half = 1;
+        for (i = 0; i < ap->n_entries; i++)
+            if (ap->dev_entries[i] != ((2 * i) | (128u << 16)))
+            {
+                ap->all_half = 0;
+                break;
+            }
+    }
+}
+
+static void
+axis_plan_clear (AxisPlan *ap)
+{
+    free (ap->pairs);
+    free (ap->dev_entries);
+    ap->pairs = NULL;
+    ap->dev_entries = NULL;
+}
+
+typedef struct
+{
+    SmolJobDesc d;
+    AxisPlan ax, ay;
+    int storage_bits;
+}
+JobPlan;
+
+static void
+job_plan_init (JobPlan *jp,
+               SmolPixelType type_in, uint32_t w_in, uint32_t h_in,
+               SmolPixelType type_out, uint32_t w_out, uint32_t h_out,
+               uint8_t with_srgb)
+{
+    TypeInfo ti = type_info (type_in), to = type_info (type_out);
+    AxisPick px = pick_axis (w_in, w_out, with_srgb);
+    AxisPick py = pick_axis (h_in, h_out, with_srgb);
+    int linear = with_srgb ? 1 : 0;
+    int both_unassoc = ti.unassoc && to.unassoc;
+    SmolJobDesc *d = &jp->d;
+
+    memset (jp, 0, sizeof (*jp));
+    jp->storage_bits = px.storage_bits > py.storage_bits ? px.storage_bits : py.storage_bits;   /* smolscale.c:862 */
+
+    /* unassociated in and out: 16 bits per channel internally (smolscale.c:751-758) */
+    if (both_unassoc)
+        jp->storage_bits = 128;
+    /* not enough head room for linear light beyond 2^13 : 1 (smolscale.c:760-770) */
+    if (w_in > w_out * 8191 || h_in > h_out * 8191)
+        linear = 0;
+
+    axis_plan_init (&jp->ax, px, w_in, w_out);
+    axis_plan_init (&jp->ay, py, h_in, h_out);
+
+    d->w_in = w_in; d->h_in = h_in; d->w_out = w_out; d->h_out = h_out;
+    d->bpp_in = (uint8_t) ti.bpp; d->bpp_out = (uint8_t) to.bpp;
+    d->in_alpha_idx = ti.alpha_idx < 0 ? 0xff : (uint8_t) ti.alpha_idx;
+    d->in_col0 = (uint8_t) ti.col0;
+    d->out_alpha_idx = to.alpha_idx < 0 ? 0xff : (uint8_t) to.alpha_idx;
+    d->out_col0 = (uint8_t) to.col0;
+    d->in_unassoc = (uint8_t) ti.unassoc;
+    d->out_unassoc = (uint8_t) to.unassoc;
+    d->swap_rb = (uint8_t) (ti.bgr != to.bgr);
+    d->storage128 = jp->storage_bits == 128;
+    if (both_unassoc)
+        d->mid = linear ? SMOL_MID_P16L : SMOL_MID_P16;
+    else
+        d->mid = linear ? SMOL_MID_P8L : SMOL_MID_P8;
+    /* Linear light to a 24bpp destination: the reference's repack search (smolscale.c:647-719)
+     * lands on its "123" packer -- which gamma-compresses the still-premultiplied value
+     * (generic:922-935) -- for 32bpp sources whose colour order is reversed in the output and for
+     * 24bpp sources whose colour order is kept; on the "321" packer (unpremultiply first,
+     * generic:1010-1023) otherwise. */
+    d->pack24_direct = (uint8_t) ((ti.bpp == 4) ? d->swap_rb : !d->swap_rb);
+    d->h_kind = jp->ax.kind; d->v_kind = jp->ay.kind;
+    d->h_halvings = (uint8_t) jp->ax.halvings; d->v_halvings = (uint8_t) jp->ay.halvings;
+    d->all_half_x = jp->ax.all_half; d->all_half_y = jp->ay.all_half;
+    d->span_mul_x = jp->ax.span_mul; d->span_mul_y = jp->ay.span_mul;
+    d->n_tab_x = jp->ax.n_entries; d->n_tab_y = jp->ay.n_entries;
+}
+
+static void
+job_plan_clear (JobPlan *jp)
+{
+    axis_plan_clear (&jp->ax);
+    axis_plan_clear (&jp->ay);
+}
+
+/* Source rows read by output rows [first, first + n): [*r0, *r0 + *nr). */
+static void
+plan_source_rows (const JobPlan *jp, uint32_t first, uint32_t n, uint32_t *r0, uint32_t *nr)
+{
+    const AxisPlan *ay = &jp->ay;
+    uint32_t lo, hi;
+
+    if (n == 0)
+    {
+        *r0 = 0; *nr = 0;
+        return;
+    }
+    if (ay->kind == SMOL_AXIS_BOX)
+    {
+        lo = ay->dev_entries[first] & 0xffff;
+        hi = ay->dev_entries[first + n] & 0xffff;
+    }
+    else
+    {
+        uint32_t i0 = first << ay->halvings;
+        uint32_t i1 = ((first + n) << ay->halvings) - 1;
+
+        lo = ay->dev_entries[i0] & 0xffff;
+        hi = (ay->dev_entries[i1] & 0xffff) + 1;
+        /* ONE has all offsets 0 and F = 256; COPY needs only its own rows */
+        if (ay->filter != SMOL_CUDA_AXIS_BILINEAR)
+            hi = ay->dev_entries[i1] & 0xffff;
+    }
+    if (hi > jp->d.h_in - 1)
+        hi = jp->d.h_in - 1;
+    *r0 = lo;
+    *nr = hi - lo + 1;
+}
+
+/* ------------------------------------------------------------------------------------------ *
+ * Per-device state                                                                           *
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct
+{
+    int used;
+    uint8_t kind;
+    uint32_t filter, dim_in, n_entries;
+    uint32_t *dev;
+    int refs;
+    uint64_t stamp;
+}
+TabEntry;
+
+typedef struct
+{
+    cudaStream_t stream;
+    void *d_in, *d_out;
+    size_t d_in_cap, d_out_cap;
+    int busy;
+}
+Lane;
+
+typedef struct
+{
+    int ready;
+    SmolDeviceLuts *luts;
+    TabEntry tabs[SMOL_TAB_CACHE_MAX];
+    uint64_t clock;
+    Lane lanes[SMOL_MAX_LANES];
+    int n_lanes;
+}
+DeviceState;
+
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_lane_free = PTHREAD_COND_INITIALIZER;
+static DeviceState g_dev[SMOL_MAX_DEVICES];
+static int g_device_count = -1;
+static int g_forced_kernel = 0;
+
+static uint64_t g_stat_launches, g_stat_h2d, g_stat_d2h, g_stat_uploads;
+
+static __thread void *tl_stream = NULL;
+static __thread int tl_device = -1;
+
+static int
+device_count_locked (void)
+{
+    if (g_device_count < 0)
+    {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount (&n);
+
+        if (e != cudaSuccess)
+        {
+            (void) cudaGetLastError ();
+            n = 0;
+        }
+        if (n > SMOL_MAX_DEVICES)
+            n = SMOL_MAX_DEVICES;
+        g_device_count = n;
+    }
+    return g_device_count;
+}
+
+/* Caller holds g_lock and has made `dev` current. */
+static DeviceState *
+device_state_locked (int dev)
+{
+    DeviceState *ds;
+
+    if (device_count_locked () <= 0)
+        smol_fatal ("no usable CUDA device (this library has no CPU fallback)", NULL);
+    if (dev < 0 || dev >= g_device_count)
+        smol_fatal ("device ordinal out of range", NULL);
+
+    ds = &g_dev[dev];
+    if (!ds->ready)
+    {
+        SmolDeviceLuts *h = malloc (sizeof (*h));
+
+        if (!h)
+            smol_fatal ("out of memory", NULL);
+        memcpy (h->inv_div_p8, smol_lut_inv_div_p8, sizeof (h->inv_div_p8));
+        memcpy (h->inv_div_p8l, smol_lut_inv_div_p8l, sizeof (h->inv_div_p8l));
+        memcpy (h->inv_div_p16, smol_lut_inv_div_p16, sizeof (h->inv_div_p16));
+        memcpy (h->inv_div_p16l, smol_lut_inv_div_p16l, sizeof (h->inv_div_p16l));
+        memcpy (h->from_srgb, smol_lut_from_srgb, sizeof (h->from_srgb));
+        memcpy (h->to_srgb, smol_lut_to_srgb, sizeof (h->to_srgb));
+        CK (cudaMalloc ((void **) &ds->luts, sizeof (*h)));
+        CK (cudaMemcpy (ds->luts, h, sizeof (*h), cudaMemcpyHostToDevice));
+        free (h);
+        ds->ready = 1;
+    }
+    return ds;
+}
+
+/* Looks up / uploads one axis table.  Caller holds g_lock, device is current. */
+static TabEntry *
+tab_acquire_locked (DeviceState *ds, const AxisPlan *ap)
+{
+    TabEntry *free_slot = NULL, *victim = NULL;
+    int i;
+
+    for (i = 0; i < SMOL_TAB_CACHE_MAX; i++)
+    {
+        TabEntry *t = &ds->tabs[i];
+
+        if (!t->used)
+        {
+            if (!free_slot)
+                free_slot = t;
+            continue;
+        }
+        if (t->kind == ap->kind && t->filter == (uint32_t) ap->filter
+            && t->dim_in == ap->dim_in && t->n_entries == ap->n_entries)
+        {
+            t->refs++;
+            t->stamp = ++ds->clock;
+            return t;
+        }
+        if (t->refs == 0 && (!victim || t->stamp < victim->stamp))
+            victim = t;
+    }
+
+    if (!free_slot)
+    {
+        if (!victim)
+            smol_fatal ("filter table cache exhausted (too many live contexts)", NULL);
+        CK (cudaFree (victim->dev));    /* implicit device synchronisation: nothing can still read it */
+        victim->used = 0;
+        free_slot = victim;
+    }
+
+    free_slot->used = 1;
+    free_slot->kind = ap->kind;
+    free_slot->filter = (uint32_t) ap->filter;
+    free_slot->dim_in = ap->dim_in;
+    free_slot->n_entries = ap->n_entries;
+    free_slot->refs = 1;
+    free_slot->stamp = ++ds->clock;
+    CK (cudaMalloc ((void **) &free_slot->dev, (size_t) ap->n_entries * sizeof (uint32_t)));
+    CK (cudaMemcpy (free_slot->dev, ap->dev_entries, (size_t) ap->n_entries * sizeof (uint32_t),
+                    cudaMemcpyHostToDevice));
+    __atomic_add_fetch (&g_stat_uploads, 1, __ATOMIC_RELAXED);
+    return free_slot;
+}
+
+static Lane *
+lane_acquire (int dev)
+{
+    Lane *lane = NULL;
+    DeviceState *ds;
+    int i;
+
+    pthread_mutex_lock (&g_lock);
+    ds = device_state_locked (dev);
+    for (;;)
+    {
+        for (i = 0; i < ds->n_lanes; i++)
+            if (!ds->lanes[i].busy)
+            {
+                lane = &ds->lanes[i];
+                break;
+            }
+        if (lane)
+            break;
+        if (ds->n_lanes < SMOL_MAX_LANES)
+        {
+            lane = &ds->lanes[ds->n_lanes++];
+            memset (lane, 0, sizeof (*lane));
+            CK (cudaStreamCreateWithFlags (&lane->stream, cudaStreamNonBlocking));
+            break;
+        }
+        pthread_cond_wait (&g_lane_free, &g_lock);
+    }
+    lane->busy = 1;
+    pthread_mutex_unlock (&g_lock);
+    return lane;
+}
+
+static void
+lane_release (Lane *lane)
+{
+    pthread_mutex_lock (&g_lock);
+    lane->busy = 0;
+    pthread_cond_signal (&g_lane_free);
+    pthread_mutex_unlock (&g_lock);
+}
+
+static void
+lane_reserve (void **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap)
+        return;
+    if (*buf)
+        CK (cudaFree (*buf));
+    need = (need + ((size_t) 1 << 20) - 1) & ~(((size_t) 1 << 20) - 1);
+    CK (cudaMalloc (buf, need));
+    *cap = need;
+}
+
+/* ------------------------------------------------------------------------------------------ *
+ * Context                                                                                    *
+ * ------------------------------------------------------------------------------------------ */
+
+struct SmolScaleCtx
+{
+    const char *pixels_in;
+    char *pixels_out;
+    uint32_t rowstride_in, rowstride_out;
+    SmolPixelType pixel_type_in, pixel_type_out;
+    SmolPostRowFunc *post_row_func;
+    void *user_data;
+
+    JobPlan plan;
+
+    /* lazily acquired device-resident tables, one pair per device */
+    pthread_mutex_t lock;
+    TabEntry *tab_x[SMOL_MAX_DEVICES], *tab_y[SMOL_MAX_DEVICES];
+};
+
+static SmolScaleCtx *
+ctx_new (const void *pixels_in, SmolPixelType pixel_type_in,
+         uint32_t width_in, uint32_t height_in, uint32_t rowstride_in,
+         void *pixels_out, SmolPixelType pixel_type_out,
+         uint32_t width_out, uint32_t height_out, uint32_t rowstride_out,
+         uint8_t with_srgb, SmolPostRowFunc post_row_func, void *user_data)
+{
+    SmolScaleCtx *ctx = calloc (1, sizeof (*ctx));
+
+    if (!ctx)
+        smol_fatal ("out of memory", NULL);
+    if (width_in == 0 || height_in == 0 || width_out == 0 || height_out == 0
+        || width_in > 65535 || height_in > 65535 || width_out > 65535 || height_out > 65535)
+        smol_fatal ("image dimensions must be in [1, 65535]", NULL);
+
+    ctx->pixels_in = pixels_in;
+    ctx->pixels_out = pixels_out;
+    ctx->rowstride_in = rowstride_in;
+    ctx->rowstride_out = rowstride_out;
+    ctx->pixel_type_in = pixel_type_in;
+    ctx->pixel_type_out = pixel_type_out;
+    ctx->post_row_func = post_row_func;
+    ctx->user_data = user_data;
+    pthread_mutex_init (&ctx->lock, NULL);
+    job_plan_init (&ctx->plan, pixel_type_in, width_in, height_in,
+                   pixel_type_out, width_out, height_out, with_srgb);
+    return ctx;
+}
+
+static void
+ctx_free (SmolScaleCtx *ctx)
+{
+    int i;
+
+    pthread_mutex_lock (&g_lock);
+    for (i = 0; i < SMOL_MAX_DEVICES; i++)
+    {
+        if (ctx->tab_x[i])
+            ctx->tab_x[i]->refs--;
+        if (ctx->tab_y[i])
+            ctx->tab_y[i]->refs--;
+    }
+    pthread_mutex_unlock (&g_lock);
+    pthread_mutex_destroy (&ctx->lock);
+    job_plan_clear (&ctx->plan);
+    free (ctx);
+}
+
+/* Device must be current. */
+static void
+ctx_device_tables (SmolScaleCtx *ctx, int dev, const uint32_t **tx, const uint32_t **ty, const SmolDeviceLuts **luts)
+{
+    pthread_mutex_lock (&ctx->lock);
+    if (!ctx->tab_x[dev])
+    {
+        DeviceState *ds;
+
+        pthread_mutex_lock (&g_lock);
+        ds = device_state_locked (dev);
+        ctx->tab_x[dev] = tab_acquire_locked (ds, &ctx->plan.ax);
+        ctx->tab_y[dev] = tab_acquire_locked (ds, &ctx->plan.ay);
+        pthread_mutex_unlock (&g_lock);
+    }
+    *tx = ctx->tab_x[dev]->dev;
+    *ty = ctx->tab_y[dev]->dev;
+    *luts = g_dev[dev].luts;
+    pthread_mutex_unlock (&ctx->lock);
+}
+
+/* ------------------------------------------------------------------------------------------ *
+ * Row rendering                                                                              *
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct
+{
+    int is_device;      /* device or managed: a kernel can dereference it */
+    int device;
+}
+PtrClass;
+
+static PtrClass
+classify_pointer (const void *p)
+{
+    struct cudaPointerAttributes attr;
+    PtrClass pc = { 0, -1 };
+    cudaError_t e;
+
+    if (!p)
+        return pc;
+    e = cudaPointerGetAttributes (&attr, p);
+    if (e != cudaSuccess)
+    {
+        (void) cudaGetLastError ();
+        return pc;
+    }
+    if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)
+    {
+        pc.is_device = 1;
+        pc.device = attr.device;
+    }
+    return pc;
+}
+
+static size_t
+align16 (size_t v)
+{
+    return (v + 15) & ~(size_t) 15;
+}
+
+static void
+launch_checked (const SmolLaunch *L, cudaStream_t stream)
+{
+    int kid = smol_cuda_pick_kernel (L, g_forced_kernel);
+    int e = smol_cuda_launch (L, kid, stream, NULL);
+
+    if (e != 0)
+        smol_fatal ("kernel launch failed", cudaGetErrorString ((cudaError_t) e));
+    __atomic_add_fetch (&g_stat_launches, 1, __ATOMIC_RELAXED);
+}
+
+/* 2D copy that also tolerates pitches smaller than the row width (rows then overlap in the
+ * pitched buffer, which the reference handles naturally because it only ever walks rows). */
+static void
+copy_rows_async (void *dst, size_t dpitch, const void *src, size_t spitch,
+                 size_t width_bytes, size_t n_rows, enum cudaMemcpyKind kind, cudaStream_t stream)
+{
+    if (n_rows == 0 || width_bytes == 0)
+        return;
+    if (dpitch == width_bytes && spitch == width_bytes)
+    {
+        CK (cudaMemcpyAsync (dst, src, width_bytes * n_rows, kind, stream));
+    }
+    else if (dpitch >= width_bytes && spitch >= width_bytes)
+    {
+        CK (cudaMemcpy2DAsync (dst, dpitch, src, spitch, width_bytes, n_rows, kind, stream));
+    }
+    else
+    {
+        size_t r;
+
+        for (r = 0; r < n_rows; r++)
+            CK (cudaMemcpyAsync ((char *) dst + r * dpitch, (const char *) src + r * spitch,
+                                 width_bytes, kind, stream));
+    }
+}
+
+static void
+do_rows (const SmolScaleCtx *cctx, void *outrows_dest, uint32_t first_row, uint32_t n_rows)
+{
+    SmolScaleCtx *ctx = (SmolScaleCtx *) cctx;
+    const SmolJobDesc *d = &ctx->plan.d;
+    const size_t in_row_bytes = (size_t) d->w_in * d->bpp_in;
+    const size_t out_row_bytes = (size_t) d->w_out * d->bpp_out;
+    PtrClass pc_in, pc_out;
+    SmolLaunch L;
+    int prev_dev = -1, dev;
+    uint32_t r0, nr;
+
+    if (n_rows == 0)
+        return;
+    if ((uint64_t) first_row + n_rows > d->h_out)
+        smol_fatal ("row range outside the output image", NULL);
+
+    pthread_mutex_lock (&g_lock);
+    if (device_count_locked () <= 0)
+        smol_fatal ("no usable CUDA device (this library has no CPU fallback)", NULL);
+    pthread_mutex_unlock (&g_lock);
+
+    pc_in = classify_pointer (ctx->pixels_in);
+    pc_out = classify_pointer (outrows_dest);
+
+    CK (cudaGetDevice (&prev_dev));
+    if (pc_out.is_device)
+        dev = pc_out.device;
+    else if (pc_in.is_device)
+        dev = pc_in.device;
+    else
+        dev = tl_device >= 0 ? tl_device : prev_dev;
+    if (dev != prev_dev)
+        CK (cudaSetDevice (dev));
+
+    memset (&L, 0, sizeof (L));
+    L.d = *d;
+    L.n_images = 1;
+    L.first_row = first_row;
+    L.n_rows = n_rows;
+    ctx_device_tables (ctx, dev, &L.tab_x, &L.tab_y, &L.luts);
+
+    if (pc_in.is_device && pc_out.is_device && !ctx->post_row_func)
+    {
+        /* Everything already lives on the GPU: enqueue and return (stream-ordered). */
+        L.src = (const uint8_t *) ctx->pixels_in;
+        L.src_pitch = ctx->rowstride_in;
+        L.dst = (uint8_t *) outrows_dest;
+        L.dst_pitch = ctx->rowstride_out;
+        launch_checked (&L, (cudaStream_t) tl_stream);
+    }
+    else
+    {
+        Lane *lane = lane_acquire (dev);
+        cudaStream_t s = lane->stream;
+
+        plan_source_rows (&ctx->plan, first_row, n_rows, &r0, &nr);
+
+        if (pc_in.is_device)
+        {
+            L.src = (const uint8_t *) ctx->pixels_in;
+            L.src_pitch = ctx->rowstride_in;
+        }
+        else
+        {
+            const size_t pitch = align16 (in_row_bytes);
+
+            lane_reserve (&lane->d_in, &lane->d_in_cap, pitch * nr + 16);
+            copy_rows_async (lane->d_in, pitch,
+                             ctx->pixels_in + (size_t) r0 * ctx->rowstride_in, ctx->rowstride_in,
+                             in_row_bytes, nr, cudaMemcpyHostToDevice, s);
+            __atomic_add_fetch (&g_stat_h2d, in_row_bytes * nr, __ATOMIC_RELAXED);
+            /* the kernel addresses rows from row 0 of the image; only rows [r0, r0 + nr) are read */
+            L.src = (const uint8_t *) lane->d_in - (size_t) r0 * pitch;
+            L.src_pitch = (uint32_t) pitch;
+        }
+
+        if (pc_out.is_device)
+        {
+            L.dst = (uint8_t *) outrows_dest;
+            L.dst_pitch = ctx->rowstride_out;
+        }
+        else
+        {
+            const size_t pitch = align16 (out_row_bytes);
+
+            lane_reserve (&lane->d_out, &lane->d_out_cap, pitch * n_rows + 16);
+            L.dst = (uint8_t *) lane->d_out;
+            L.dst_pitch = (uint32_t) pitch;
+        }
+
+        launch_checked (&L, s);
+
+        if (!pc_out.is_device)
+        {
+            copy_rows_async (outrows_dest, ctx->rowstride_out, lane->d_out, L.dst_pitch,
+                             out_row_bytes, n_rows, cudaMemcpyDeviceToHost, s);
+            __atomic_add_fetch (&g_stat_d2h, out_row_bytes * n_rows, __ATOMIC_RELAXED);
+        }
+        CK (cudaStreamSynchronize (s));
+
+        if (ctx->post_row_func)
+        {
+            /* reference smolscale.c:502-503: once per finished row, on the calling thread */
+            uint32_t i;
+
+            if (!pc_out.is_device)
+            {
+                for (i = 0; i < n_rows; i++)
+                    ctx->post_row_func ((uint32_t *) ((char *) outrows_dest + (size_t) i * ctx->rowstride_out),
+                                        (int) d->w_out, ctx->user_data);
+            }
+            else
+            {
+                /* device destination: bounce each row through host memory */
+                uint32_t *tmp = malloc (align16 (out_row_bytes) + 16);
+
+                if (!tmp)
+                    smol_fatal ("out of memory", NULL);
+                for (i = 0; i < n_rows; i++)
+                {
+                    char *row = (char *) outrows_dest + (size_t) i * ctx->rowstride_out;
+
+                    CK (cudaMemcpy (tmp, row, out_row_bytes, cudaMemcpyDeviceToHost));
+                    ctx->post_row_func (tmp, (int) d->w_out, ctx->user_data);
+                    CK (cudaMemcpy (row, tmp, out_row_bytes, cudaMemcpyHostToDevice));
+                }
+                free (tmp);
+            }
+        }
+        lane_release (lane);
+    }
+
+    if (dev != prev_dev)
+        CK (cudaSetDevice (prev_dev));
+}
+
+/* ------------------------------------------------------------------------------------------ *
+ * Public API (reference smolscale.c:882-1008)                                                *
+ * ------------------------------------------------------------------------------------------ */
+
+SMOL_EXPORT SmolScaleCtx *
+smol_scale_new (const void *pixels_in, SmolPixelType pixel_type_in,
+                uint32_t width_in, uint32_t height_in, uint32_t rowstride_in,
+                void *pixels_out, SmolPixelType pixel_type_out,
+                uint32_t width_out, uint32_t height_out, uint32_t rowstride_out,
+                uint8_t with_srgb)
+{
+    return ctx_new (pixels_in, pixel_type_in, width_in, height_in, rowstride_in,
+                    pixels_out, pixel_type_out, width_out, height_out, rowstride_out,
+                    with_srgb, NULL, NULL);
+}
+
+SMOL_EXPORT SmolScaleCtx *
+smol_scale_new_full (const void *pixels_in, SmolPixelType pixel_type_in,
+                     uint32_t width_in, uint32_t height_in, uint32_t rowstride_in,
+                     void *pixels_out, SmolPixelType pixel_type_out,
+                     uint32_t width_out, uint32_t height_out, uint32_t rowstride_out,
+                     uint8_t with_srgb,
+                     SmolPostRowFunc post_row_func, void *user_data)
+{
+    return ctx_new (pixels_in, pixel_type_in, width_in, height_in, rowstride_in,
+                    pixels_out, pixel_type_out, width_out, height_out, rowstride_out,
+                    with_srgb, post_row_func, user_data);
+}
+
+SMOL_EXPORT void
+smol_scale_destroy (SmolScaleCtx *scale_ctx)
+{
+    if (scale_ctx)
+        ctx_free (scale_ctx);
+}
+
+SMOL_EXPORT void
+smol_scale_batch (const SmolScaleCtx *scale_ctx, uint32_t first_outrow, uint32_t n_outrows)
+{
+    do_rows (scale_ctx,
+             scale_ctx->pixels_out + (size_t) first_outrow * scale_ctx->rowstride_out,
+             first_outrow, n_outrows);
+}
+
+SMOL_EXPORT void
+smol_scale_batch_full (const SmolScaleCtx *scale_ctx, void *outrows_dest,
+                       uint32_t first_outrow, uint32_t n_outrows)
+{
+    do_rows (scale_ctx, outrows_dest, first_outrow, n_outrows);
+}
+
+SMOL_EXPORT void
+smol_scale_simple (const void *pixels_in, SmolPixelType pixel_type_in,
+                   uint32_t width_in, uint32_t height_in, uint32_t rowstride_in,
+                   void *pixels_out, SmolPixelType pixel_type_out,
+                   uint32_t width_out, uint32_t height_out, uint32_t rowstride_out,
+                   uint8_t with_srgb)
+{
+    SmolScaleCtx *ctx = ctx_new (pixels_in, pixel_type_in, width_in, height_in, rowstride_in,
+                                 pixels_out, pixel_type_out, width_out, height_out, rowstride_out,
+                                 with_srgb, NULL, NULL);
+
+    do_rows (ctx, pixels_out, 0, height_out);
+    ctx_free (ctx);
+}
+
+/* ------------------------------------------------------------------------------------------ *
+ * Extensions (smolscale-cuda.h)                                                              *
+ * ------------------------------------------------------------------------------------------ */
+
+SMOL_EXPORT int
+smol_cuda_device_count (void)
+{
+    int n;
+
+    pthread_mutex_lock (&g_lock);
+    n = device_count_locked ();
+    pthread_mutex_unlock (&g_lock);
+    return n;
+}
+
+SMOL_EXPORT void
+smol_cuda_set_device (int device)
+{
+    tl_device = device;
+}
+
+SMOL_EXPORT void
+smol_cuda_set_stream (void *cuda_stream)
+{
+    tl_stream = cuda_stream;
+}
+
+SMOL_EXPORT void
+smol_cuda_synchronize (void)
+{
+    CK (cudaStreamSynchronize ((cudaStream_t) tl_stream));
+}
+
+SMOL_EXPORT void
+smol_cuda_scale_images (const void *pixels_in, size_t image_stride_in,
+                        SmolPixelType pixel_type_in,
+                        uint32_t width_in, uint32_t height_in, uint32_t rowstride_in,
+                        void *pixels_out, size_t image_stride_out,
+                        SmolPixelType pixel_type_out,
+                        uint32_t width_out, uint32_t height_out, uint32_t rowstride_out,
+                        uint8_t with_srgb, uint32_t n_images)
+{
+    SmolScaleCtx *ctx;
+    PtrClass pc_in = classify_pointer (pixels_in), pc_out = classify_pointer (pixels_out);
+    SmolLaunch L;
+    int prev_dev = -1, dev;
+    uint32_t done;
+
+    if (n_images == 0)
+        return;
+    if (!pc_in.is_device || !pc_out.is_device)
+        smol_fatal ("smol_cuda_scale_images needs device (or managed) memory for both buffers", NULL);
+
+    ctx = ctx_new (pixels_in, pixel_type_in, width_in, height_in, rowstride_in,
+                   pixels_out, pixel_type_out, width_out, height_out, rowstride_out,
+                   with_srgb, NULL, NULL);
+    CK (cudaGetDevice (&prev_dev));
+    dev = pc_out.device;
+    if (dev != prev_dev)
+        CK (cudaSetDevice (dev));
+
+    memset (&L, 0, sizeof (L));
+    L.d = ctx->plan.d;
+    L.src_pitch = rowstride_in;
+    L.dst_pitch = rowstride_out;
+    L.src_image_stride = image_stride_in;
+    L.dst_image_stride = image_stride_out;
+    L.first_row = 0;
+    L.n_rows = height_out;
+    ctx_device_tables (ctx, dev, &L.tab_x, &L.tab_y, &L.luts);
+
+    /* grid.z carries the image index and is limited to 65535 */
+    for (done = 0; done < n_images; done += 65535)
+    {
+        L.src = (const uint8_t *) pixels_in + (size_t) done * image_stride_in;
+        L.dst = (uint8_t *) pixels_out + (size_t) done * image_stride_out;
+        L.n_images = n_images - done > 65535 ? 65535 : n_images - done;
+        launch_checked (&L, (cudaStream_t) tl_stream);
+    }
+
+    if (dev != prev_dev)
+        CK (cudaSetDevice (prev_dev));
+    ctx_free (ctx);
+}
+
+SMOL_EXPORT void
+smol_cuda_plan_query (SmolPixelType pixel_type_in, uint32_t width_in, uint32_t height_in,
+                      SmolPixelType pixel_type_out, uint32_t width_out, uint32_t height_out,
+                      uint8_t with_srgb,
+                      SmolCudaPlanInfo *info, uint16_t *tab_x, uint16_t *tab_y)
+{
+    JobPlan jp;
+    SmolLaunch L;
+
+    job_plan_init (&jp, pixel_type_in, width_in, height_in, pixel_type_out, width_out, height_out, with_srgb);
+    if (info)
+    {
+        memset (info, 0, sizeof (*info));
+        info->filter_h = jp.ax.filter; info->filter_v = jp.ay.filter;
+        info->halvings_h = jp.ax.halvings; info->halvings_v = jp.ay.halvings;
+        info->bilin_w = jp.ax.bilin_dim; info->bilin_h = jp.ay.bilin_dim;
+        info->storage_bits = jp.storage_bits;
+        info->mid = jp.d.mid;
+        info->span_mul_x = jp.ax.span_mul; info->span_mul_y = jp.ay.span_mul;
+        info->n_tab_x = jp.ax.n_pairs; info->n_tab_y = jp.ay.n_pairs;
+        memset (&L, 0, sizeof (L));
+        L.d = jp.d;
+        L.n_images = 1;
+        L.n_rows = height_out;
+        info->kernel_id = smol_cuda_pick_kernel (&L, g_forced_kernel);
+        strncpy (info->kernel_name, smol_cuda_kernel_name (info->kernel_id), sizeof (info->kernel_name) - 1);
+    }
+    if (tab_x && jp.ax.pairs)
+        memcpy (tab_x, jp.ax.pairs, (size_t) jp.ax.n_pairs * 2 * sizeof (uint16_t));
+    if (tab_y && jp.ay.pairs)
+        memcpy (tab_y, jp.ay.pairs, (size_t) jp.ay.n_pairs * 2 * sizeof (uint16_t));
+    job_plan_clear (&jp);
+}
+
+SMOL_EXPORT void
+smol_cuda_band_source_rows (const SmolScaleCtx *scale_ctx,
+                            uint32_t first_outrow, uint32_t n_outrows,
+                            uint32_t *first_inrow, uint32_t *n_inrows)
+{
+    plan_source_rows (&scale_ctx->plan, first_outrow, n_outrows, first_inrow, n_inrows);
+}
+
+SMOL_EXPORT void
+smol_cuda_get_stats (SmolCudaStats *stats)
+{
+    stats->kernel_launches = __atomic_load_n (&g_stat_launches, __ATOMIC_RELAXED);
+    stats->h2d_bytes = __atomic_load_n (&g_stat_h2d, __ATOMIC_RELAXED);
+    stats->d2h_bytes = __atomic_load_n (&g_stat_d2h, __ATOMIC_RELAXED);
+    stats->table_uploads = __atomic_load_n (&g_stat_uploads, __ATOMIC_RELAXED);
+}
+
+SMOL_EXPORT void
+smol_cuda_reset_stats (void)
+{
+    __atomic_store_n (&g_stat_launches, 0, __ATOMIC_RELAXED);
+    __atomic_store_n (&g_stat_h2d, 0, __ATOMIC_RELAXED);
+    __atomic_store_n (&g_stat_d2h, 0, __ATOMIC_RELAXED);
+    __atomic_store_n (&g_stat_uploads, 0, __ATOMIC_RELAXED);
+}
+
+SMOL_EXPORT void
+smol_cuda_force_kernel (int kernel_id)
+{
+    g_forced_kernel = kernel_id;
+}
