@@ -1,0 +1,261 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (ctypes binding of
+libsmolscale_cuda.so), against the committed golden digests (generated from the compiled
+reference) and against the plain-C oracle on seeded inputs.  Bar: bit-exact."""
+import ctypes
+import hashlib
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "digests.json")
+
+
+def cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so=None, srgb=0, fill=0xCD):
+    so = so or wo * cases.bpp(to)
+    out = np.full(so * (ho - 1) + wo * cases.bpp(to), fill, np.uint8)
+    sb.scale_simple(src, ti, wi, hi, si, out, to, wo, ho, so, srgb)
+    return out
+
+
+def describe(got, want):
+    bad = np.nonzero(got != want)[0]
+    return "%d bytes differ, first at %s: got %s want %s" % (bad.size, bad[:4], got[bad[:4]], want[bad[:4]])
+
+
+def test_golden_digests(sb):
+    """Every committed golden vector, incl. the five BASELINE configurations at full size."""
+    with open(GOLDEN) as f:
+        golden = json.load(f)["digests"]
+    bad = []
+    for name, g in sorted(golden.items()):
+        ti, wi, hi, si, to, wo, ho, so, srgb, mode, seed = g["job"]
+        src = cases.make_image(ti, wi, hi, si, mode, seed)
+        out = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, srgb)
+        if hashlib.sha256(out.tobytes()).hexdigest() != g["sha256"]:
+            bad.append(name)
+    assert not bad, "CUDA output differs from the reference digests: %s" % bad[:10]
+
+
+def test_random_matrix_vs_oracle(sb, restatement):
+    for idx, job in enumerate(cases.job_matrix(4242, 600)):
+        ti, wi, hi, si, to, wo, ho, so, srgb, mode = job
+        src = cases.make_image(ti, wi, hi, si, mode, seed=idx)
+        want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
+        got = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, srgb)
+        assert np.array_equal(got, want), (job, describe(got, want))
+
+
+def test_unaligned_host_pointers(sb, restatement):
+    """Odd base addresses and odd pitches on both sides (verify.c uses pitch 3 and 4)."""
+    for off_in, off_out, ti, to in [(1, 3, cases.RGBA8_P, cases.ARGB8_U), (2, 1, cases.RGB8, cases.BGR8),
+                                    (3, 2, cases.ABGR8_U, cases.RGB8), (1, 1, cases.BGR8, cases.BGRA8_P)]:
+        wi, hi, wo, ho = 53, 31, 29, 17
+        si, so = wi * cases.bpp(ti) + 1, wo * cases.bpp(to) + 3
+        img = cases.make_image(ti, wi, hi, si, "random", seed=off_in)
+        backing = np.zeros(img.size + 8, np.uint8)
+        backing[off_in:off_in + img.size] = img
+        src = backing[off_in:off_in + img.size]
+        want = restatement.scale_simple(img, ti, wi, hi, si, to, wo, ho, so, 0)
+        out_backing = np.full(want.size + 8, 0xCD, np.uint8)
+        out = out_backing[off_out:off_out + want.size]
+        sb.scale_simple(src.ctypes.data, ti, wi, hi, si, out.ctypes.data, to, wo, ho, so, 0)
+        assert np.array_equal(out, want), describe(out, want)
+        assert (out_backing[:off_out] == 0xCD).all() and (out_backing[off_out + want.size:] == 0xCD).all()
+
+
+def test_device_pointers(sb, restatement):
+    """Device-resident input and output (torch CUDA tensors), incl. unaligned views and odd pitches."""
+    import torch
+    sb.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        for idx, job in enumerate(cases.job_matrix(777, 150)):
+            ti, wi, hi, si, to, wo, ho, so, srgb, mode = job
+            src = cases.make_image(ti, wi, hi, si, mode, seed=idx)
+            want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
+            off_in, off_out = idx % 5, (idx * 3) % 7
+            d_in = torch.zeros(src.size + 16, dtype=torch.uint8, device="cuda")
+            d_in[off_in:off_in + src.size] = torch.from_numpy(src).cuda()
+            d_out = torch.full((want.size + 16,), 0xCD, dtype=torch.uint8, device="cuda")
+            sb.scale_simple(d_in.data_ptr() + off_in, ti, wi, hi, si,
+                            d_out.data_ptr() + off_out, to, wo, ho, so, srgb)
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy()
+            assert np.array_equal(got[off_out:off_out + want.size], want), (job, describe(got[off_out:off_out + want.size], want))
+            assert (got[:off_out] == 0xCD).all() and (got[off_out + want.size:] == 0xCD).all()
+    finally:
+        sb.set_stream(None)
+
+
+def test_mixed_pointers(sb, restatement):
+    import torch
+    ti, wi, hi, to, wo, ho = cases.BGRA8_P, 640, 360, cases.RGBA8_U, 200, 100
+    src = cases.make_image(ti, wi, hi, None, "premul", seed=1)
+    want = restatement.scale_simple(src, ti, wi, hi, wi * 4, to, wo, ho, None, 0)
+    # host -> device
+    d_out = torch.zeros(want.size, dtype=torch.uint8, device="cuda")
+    sb.scale_simple(src, ti, wi, hi, wi * 4, d_out, to, wo, ho, wo * 4, 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), want)
+    # device -> host
+    d_in = torch.from_numpy(src).cuda()
+    torch.cuda.synchronize()
+    got = np.zeros_like(want)
+    sb.scale_simple(d_in, ti, wi, hi, wi * 4, got, to, wo, ho, wo * 4, 0)
+    assert np.array_equal(got, want)
+    # pinned host memory
+    p_in = torch.from_numpy(src).pin_memory()
+    p_out = torch.zeros(want.size, dtype=torch.uint8).pin_memory()
+    sb.scale_simple(p_in, ti, wi, hi, wi * 4, p_out, to, wo, ho, wo * 4, 0)
+    assert np.array_equal(p_out.numpy(), want)
+
+
+@pytest.mark.parametrize("geom", [(cases.RGBA8_P, 300, 220, cases.BGRA8_U, 111, 97, 0),     # bilinear 1h / 1h
+                                  (cases.ARGB8_U, 1200, 900, cases.ARGB8_U, 40, 51, 1),     # box, P16 linear
+                                  (cases.RGB8, 60, 40, cases.RGBA8_P, 190, 133, 0),         # magnify
+                                  (cases.BGRA8_P, 2048, 1024, cases.RGB8, 256, 128, 1),     # 2 halvings, linear, 24bpp out
+                                  (cases.ABGR8_P, 3000, 7, cases.ABGR8_P, 11, 7, 0)])       # box x copy
+def test_batch_api_bands(sb, restatement, geom):
+    """smol_scale_new + smol_scale_batch / _batch_full in arbitrary bands == one-shot result
+    (reference contract smolscale.h:70-82)."""
+    ti, wi, hi, to, wo, ho, srgb = geom
+    si, so = wi * cases.bpp(ti), wo * cases.bpp(to) + 4
+    src = cases.make_image(ti, wi, hi, si, "random", seed=5)
+    want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
+    rng = np.random.default_rng(8)
+
+    out = np.full(want.size, 0xCD, np.uint8)
+    ctx = sb.ScaleCtx(src, ti, wi, hi, si, out, to, wo, ho, so, srgb)
+    bands, y = [], 0
+    while y < ho:
+        n = int(min(ho - y, rng.integers(1, 24)))
+        bands.append((y, n))
+        y += n
+    for i in rng.permutation(len(bands)):          # any order
+        ctx.batch(*bands[i])
+    assert np.array_equal(out, want), describe(out, want)
+
+    for y, n in bands[::3]:                        # batch_full: rows land at the given address
+        dest = np.full(so * (n - 1) + wo * cases.bpp(to), 0xCD, np.uint8)
+        ctx.batch_full(dest, y, n)
+        assert np.array_equal(dest, want[y * so: y * so + dest.size])
+    ctx.destroy()
+
+
+def test_batch_threads(sb, restatement):
+    """Concurrent smol_scale_batch on one shared context from T threads (test.c:838-883 pattern)."""
+    ti, wi, hi, to, wo, ho = cases.BGRA8_P, 1920, 1080, cases.BGRA8_U, 960, 540
+    src = cases.make_image(ti, wi, hi, None, "premul", seed=9)
+    want = restatement.scale_simple(src, ti, wi, hi, wi * 4, to, wo, ho, None, 0)
+    out = np.zeros_like(want)
+    ctx = sb.ScaleCtx(src, ti, wi, hi, wi * 4, out, to, wo, ho, wo * 4, 0)
+    T = 12
+    per = (ho + T - 1) // T
+    threads = [threading.Thread(target=ctx.batch, args=(y, min(per, ho - y))) for y in range(0, ho, per)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    ctx.destroy()
+    assert np.array_equal(out, want), describe(out, want)
+
+
+def test_post_row_func(sb, restatement):
+    """SmolPostRowFunc (smolscale.h:37-39, smolscale.c:502-503): once per finished row, may modify it."""
+    import torch
+    ti, wi, hi, to, wo, ho = cases.RGBA8_P, 200, 120, cases.RGBA8_P, 64, 48
+    src = cases.make_image(ti, wi, hi, None, "random", seed=2)
+    want = restatement.scale_simple(src, ti, wi, hi, wi * 4, to, wo, ho, None, 0).copy()
+    want32 = want.view(np.uint32)
+    want32 ^= np.uint32(0x00FF00FF)
+    calls = []
+
+    def cb(row, width, user):
+        calls.append(width)
+        for i in range(width):
+            row[i] ^= 0x00FF00FF
+
+    out = np.zeros_like(want)
+    ctx = sb.ScaleCtx(src, ti, wi, hi, wi * 4, out, to, wo, ho, wo * 4, 0, post_row_func=cb)
+    ctx.batch(0, 20)
+    ctx.batch(20, ho - 20)
+    ctx.destroy()
+    assert calls == [wo] * ho
+    assert np.array_equal(out, want)
+
+    calls.clear()
+    d_out = torch.zeros(want.size, dtype=torch.uint8, device="cuda")
+    ctx = sb.ScaleCtx(src, ti, wi, hi, wi * 4, d_out, to, wo, ho, wo * 4, 0, post_row_func=cb)
+    ctx.batch(0, ho)
+    ctx.destroy()
+    assert calls == [wo] * ho
+    assert np.array_equal(d_out.cpu().numpy(), want)
+
+
+def test_scale_images_batch(sb, restatement):
+    """smol_cuda_scale_images (one launch, grid.z = image) == one smol_scale_simple per image."""
+    import torch
+    for ti, wi, hi, to, wo, ho, srgb in [(cases.ARGB8_P, 256, 256, cases.ARGB8_P, 32, 32, 0),
+                                         (cases.RGBA8_U, 190, 120, cases.BGR8, 17, 11, 1)]:
+        n = 9
+        si, so = wi * cases.bpp(ti), wo * cases.bpp(to)
+        in_stride, out_stride = si * hi + 64, so * ho + 16
+        h_in = np.zeros(in_stride * n, np.uint8)
+        wants = []
+        for i in range(n):
+            img = cases.make_image(ti, wi, hi, si, "premul", seed=100 + i)
+            h_in[i * in_stride: i * in_stride + img.size] = img
+            wants.append(restatement.scale_simple(img, ti, wi, hi, si, to, wo, ho, so, srgb))
+        d_in = torch.from_numpy(h_in).cuda()
+        d_out = torch.full((out_stride * n,), 0xCD, dtype=torch.uint8, device="cuda")
+        sb.set_stream(torch.cuda.current_stream().cuda_stream)
+        sb.scale_images(d_in, in_stride, ti, wi, hi, si, d_out, out_stride, to, wo, ho, so, srgb, n)
+        torch.cuda.synchronize()
+        sb.set_stream(None)
+        got = d_out.cpu().numpy()
+        for i in range(n):
+            g = got[i * out_stride: i * out_stride + wants[i].size]
+            assert np.array_equal(g, wants[i]), (i, describe(g, wants[i]))
+            assert (got[i * out_stride + wants[i].size: (i + 1) * out_stride] == 0xCD).all()
+
+
+def test_solid_colours(sb, restatement):
+    """test.c:1128-1298 (`check` mode) in miniature: solid colours swept over widths that hit every
+    filter class.  The oracle is the judge (integer box ratios legitimately lose the last pixel,
+    SURVEY appendix C.10); for the non-box filters the colour must additionally survive exactly."""
+    colours = [(0, 0, 0, 0), (255, 255, 255, 255), (128, 64, 32, 16), (255, 10, 200, 100), (7, 7, 7, 7)]
+    sizes = [1, 2, 3, 5, 8, 9, 17, 31, 64, 100, 257, 1000, 2049]
+    for a, r, g, b in colours:
+        for wi in sizes:
+            for wo in (1, 2, 7, 64, 333):
+                src = np.tile(np.array([a, r, g, b], np.uint8), wi * 3)
+                out = cuda_scale(sb, src, cases.ARGB8_P, wi, 3, wi * 4, cases.ARGB8_P, wo, 2, wo * 4, 0)
+                want = restatement.scale_simple(src, cases.ARGB8_P, wi, 3, wi * 4, cases.ARGB8_P, wo, 2, wo * 4, 0)
+                assert np.array_equal(out, want), (a, r, g, b, wi, wo)
+                if wi <= 8 * wo:
+                    assert (out.reshape(-1, 4) == np.array([a, r, g, b], np.uint8)).all(), (a, r, g, b, wi, wo)
+
+
+def test_baseline_config_properties(sb, restatement):
+    """Full-size BASELINE shapes: band-split invariance and agreement with the oracle on a sampled
+    row window (the digests in test_golden_digests already pin the whole images)."""
+    for name, ti, wi, hi, to, wo, ho, srgb, mode in cases.BASELINE_CONFIGS:
+        si, so = wi * cases.bpp(ti), wo * cases.bpp(to)
+        src = cases.make_image(ti, wi, hi, si, mode, seed=3)
+        whole = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, srgb)
+        out = np.zeros_like(whole)
+        ctx = sb.ScaleCtx(src, ti, wi, hi, si, out, to, wo, ho, so, srgb)
+        edges = sorted(set([0, ho] + [int(x) for x in np.random.default_rng(1).integers(1, ho, 6)]))
+        for y0, y1 in zip(edges[:-1], edges[1:]):
+            ctx.batch(y0, y1 - y0)
+        ctx.destroy()
+        assert np.array_equal(out, whole), name
+        y0 = ho // 3
+        win = restatement.scale_rows(src, ti, wi, hi, si, to, wo, ho, y0, 5, so, srgb)
+        assert np.array_equal(win, whole[y0 * so: y0 * so + win.size]), name

@@ -1,0 +1,146 @@
+"""CPU tests of the product's host logic: the C-ABI library loads, exports every declared symbol,
+and plans jobs (filters, encoding, fixed-point tables) exactly like the reference.  No compute
+calls are made -- those need a GPU."""
+import ctypes
+import itertools
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(sb):
+    lib = sb.lib()
+    declared = set()
+    for header in ("smolscale.h", "smolscale-cuda.h"):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        declared |= set(re.findall(r"\b(smol_[a-z_]+)\s*\(", text))
+    assert declared == set(sb.EXPORTED_SYMBOLS)
+    for name in sorted(declared):
+        assert getattr(lib, name) is not None
+
+
+def test_enum_values_are_abi(sb):
+    names = ["RGBA8_PREMULTIPLIED", "BGRA8_PREMULTIPLIED", "ARGB8_PREMULTIPLIED", "ABGR8_PREMULTIPLIED",
+             "RGBA8_UNASSOCIATED", "BGRA8_UNASSOCIATED", "ARGB8_UNASSOCIATED", "ABGR8_UNASSOCIATED",
+             "RGB8", "BGR8"]
+    hdr = open(os.path.join(ROOT, "include", "smolscale.h")).read()
+    for i, n in enumerate(names):
+        assert int(getattr(sb.PixelType, n)) == i
+        assert re.search(r"SMOL_PIXEL_%s\s*=\s*%d\b" % (n, i), hdr)
+    assert re.search(r"SMOL_PIXEL_MAX\s*=\s*10\b", hdr)
+
+
+def test_product_does_not_touch_the_oracle():
+    """The product path must not include, link or import anything under oracle/."""
+    pkg = os.path.join(ROOT, "smolscale_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".c", ".cu", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in text and "liboracle" not in text and "smol_oracle" not in text, f
+    import subprocess
+    out = subprocess.run(["ldd", os.path.join(pkg, "libsmolscale_cuda.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "smolref" not in out
+
+
+def test_plan_matches_restatement(sb, restatement):
+    dims = [(1, 1), (1, 7), (2, 3), (3, 2), (5, 5), (7, 3), (10, 4), (17, 2), (16, 2), (100, 11), (100, 12),
+            (520, 2), (2, 520), (65535, 1), (65535, 7), (2, 65535), (65534, 65535), (65535, 65534),
+            (9000, 1000), (4320, 450), (7680, 800), (3840, 1920), (1024, 4096), (2048, 256), (16383, 2)]
+    for (a, b), (ti, to), srgb in itertools.product(dims, [(0, 0), (4, 5), (8, 2), (6, 9), (1, 5)], (0, 1)):
+        p = sb.plan_query(ti, a, a, to, b, b, srgb, tables=True)
+        q = restatement.plan(ti, a, a, to, b, b, srgb)
+        for k in ("filter_h", "filter_v", "halvings_h", "halvings_v", "bilin_w", "bilin_h",
+                  "storage_bits", "mid", "span_mul_x", "span_mul_y", "n_tab_x", "n_tab_y"):
+            assert p[k] == q[k], (a, b, ti, to, srgb, k)
+        assert np.array_equal(p["tab_x"], q["tab_x"]) and np.array_equal(p["tab_y"], q["tab_y"])
+
+
+class _RefCtx(ctypes.Structure):
+    """Layout of the reference's private SmolScaleCtx (smolscale-private.h:280-312), x86-64."""
+    _fields_ = [("pixels_in", ctypes.c_void_p), ("pixels_out", ctypes.c_void_p),
+                ("width_in", ctypes.c_uint32), ("height_in", ctypes.c_uint32), ("rowstride_in", ctypes.c_uint32),
+                ("width_out", ctypes.c_uint32), ("height_out", ctypes.c_uint32), ("rowstride_out", ctypes.c_uint32),
+                ("pixel_type_in", ctypes.c_int), ("pixel_type_out", ctypes.c_int),
+                ("filter_h", ctypes.c_int), ("filter_v", ctypes.c_int),
+                ("storage_type", ctypes.c_int), ("gamma_type", ctypes.c_int),
+                ("unpack_row_func", ctypes.c_void_p), ("pack_row_func", ctypes.c_void_p),
+                ("hfilter_func", ctypes.c_void_p), ("vfilter_func", ctypes.c_void_p),
+                ("post_row_func", ctypes.c_void_p), ("user_data", ctypes.c_void_p),
+                ("precalc_x", ctypes.POINTER(ctypes.c_uint16)), ("precalc_y", ctypes.POINTER(ctypes.c_uint16)),
+                ("span_mul_x", ctypes.c_uint32), ("span_mul_y", ctypes.c_uint32),
+                ("precalc_x_storage", ctypes.c_void_p),
+                ("width_bilin_out", ctypes.c_uint32), ("height_bilin_out", ctypes.c_uint32),
+                ("width_halvings", ctypes.c_uint), ("height_halvings", ctypes.c_uint)]
+
+
+@pytest.mark.ref
+def test_plan_matches_reference_context(sb, reference):
+    """Compare our planner with the reference's own context: filter classes, storage, span
+    multipliers and the precalc tables themselves (x table is relative in the reference,
+    generic:47, so it is prefix-summed before comparing)."""
+    REF_COPY, REF_ONE, REF_BIL0, REF_BOX = 0, 1, 2, 9
+    dims = [(1, 7), (5, 5), (7, 3), (10, 4), (17, 2), (100, 11), (100, 12), (520, 2), (65535, 7), (2, 65535),
+            (65534, 65535), (9000, 1000), (4320, 450), (7680, 800), (3840, 1920), (1024, 4096), (2048, 256)]
+    src = np.zeros(16, np.uint8)
+    for (a, b), (ti, to), srgb in itertools.product(dims, [(0, 0), (4, 5), (8, 2)], (0, 1)):
+        ctxp = reference.lib.smol_scale_new(src.ctypes.data, ti, a, a, a * 4, None, to, b, b, b * 4, srgb)
+        ctx = _RefCtx.from_address(ctxp)
+        p = sb.plan_query(ti, a, a, to, b, b, srgb, tables=True)
+
+        def cls(f):
+            return {REF_COPY: 0, REF_ONE: 1, REF_BOX: 3}.get(f, 2)
+        assert cls(ctx.filter_h) == p["filter_h"] and cls(ctx.filter_v) == p["filter_v"]
+        assert {2: 64, 3: 128}[ctx.storage_type] == p["storage_bits"]
+        if p["filter_h"] == 2:
+            assert ctx.filter_h - REF_BIL0 == p["halvings_h"] and ctx.width_bilin_out == p["bilin_w"]
+            n = p["bilin_w"]
+            rx = np.ctypeslib.as_array(ctx.precalc_x, shape=(n * 2,)).astype(np.uint32)
+            assert np.array_equal(np.cumsum(rx[0::2]), p["tab_x"][0::2])
+            assert np.array_equal(rx[1::2], p["tab_x"][1::2])
+        if p["filter_h"] == 3:
+            assert ctx.span_mul_x == p["span_mul_x"]
+            n = b + 1
+            rx = np.ctypeslib.as_array(ctx.precalc_x, shape=(n * 2,)).astype(np.uint32)
+            # reference x entries: (whole pixels between the edge pixels, F); box i starts where i-1 ended
+            starts = np.concatenate([[0], np.cumsum(rx[0:2 * b:2] + 1)])
+            assert np.array_equal(starts[:b], p["tab_x"][0:2 * b:2])
+            assert np.array_equal(rx[1:2 * b:2], p["tab_x"][1:2 * b:2])
+            assert starts[b] == p["tab_x"][2 * b]
+        if p["filter_v"] in (2, 3):
+            n = p["n_tab_y"]
+            ry = np.ctypeslib.as_array(ctx.precalc_y, shape=(n * 2,))
+            assert np.array_equal(ry, p["tab_y"])
+            if p["filter_v"] == 3:
+                assert ctx.span_mul_y == p["span_mul_y"]
+        reference.lib.smol_scale_destroy(ctxp)
+
+
+def test_band_source_rows(sb):
+    src = np.zeros(16, np.uint8)
+    for (hi, ho) in [(2160, 1080), (4320, 450), (768, 3072), (2048, 256), (100, 100), (1, 50), (600, 7)]:
+        ctx = sb.ScaleCtx(src, 0, 8, hi, 32, None, 0, 8, ho, 32, 0)
+        p = sb.plan_query(0, 8, hi, 0, 8, ho, 0, tables=True)
+        covered_lo, covered_hi = hi, -1
+        for first in range(0, ho, max(1, ho // 7)):
+            n = min(max(1, ho // 7), ho - first)
+            r0, nr = ctx.band_source_rows(first, n)
+            assert nr >= 1 and r0 + nr <= hi
+            covered_lo, covered_hi = min(covered_lo, r0), max(covered_hi, r0 + nr - 1)
+            if p["filter_v"] == 2:       # bilinear: rows ofs .. ofs + 1 of every sample in the band
+                h = p["halvings_v"]
+                ofs = p["tab_y"][0::2][(first << h):((first + n) << h)]
+                assert r0 == ofs.min() and r0 + nr - 1 == min(int(ofs.max()) + 1, hi - 1)
+            if p["filter_v"] == 3:
+                ofs = p["tab_y"][0::2]
+                assert r0 == ofs[first] and r0 + nr - 1 == ofs[first + n]
+        if p["filter_v"] in (2, 3) and hi > ho:
+            assert covered_lo == 0
+        ctx.destroy()
