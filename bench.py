@@ -1,0 +1,440 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the smolscale scaling pipeline on B200 (and the reference on the host CPU).
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+  N > 1 is launched under torchrun (one rank per GPU); rank 0 prints ONE JSON line.
+
+What is measured
+  metric   output Mpix/s (BASELINE.json: "output Mpix/s and achieved HBM GB/s (% of peak)")
+  workload BASELINE.json configs[1]: 3840x2160 BGRA8 premultiplied -> 1920x1080 BGRA8 unassociated
+           (bilinear, 2:1, unpremultiply in the pack stage).  Other configs: --config cfg1|cfg3|cfg4|cfg5.
+  step     one pass over a batch of FRAMES distinct synthetic frames (default 16 x 33 MB = 531 MB of
+           input, larger than the 126 MB L2, so every launch streams from HBM; no flush needed).
+  value    whole-job output Mpix/s with inputs resident in HBM (device pointers, stream-ordered
+           launches, optionally replayed as one CUDA graph per step).
+  e2e      same metric through the public C API with PINNED HOST buffers: every frame is copied
+           host->device, scaled and copied back inside the timed region.
+  roofline achieved = algorithmic bytes per launch (h_in*w_in*bpp_in + h_out*w_out*bpp_out)
+           / average launch duration in the timed region (CUDA events on the launching stream).
+  cpu_baseline  the reference's AVX2 build (oracle/_ref, else the plain-C oracle port) on the
+           box's host cores, row bands across T threads (test.c:838-883 pattern), bounded sample.
+
+Multi-GPU: frames are independent, so ranks shard by frame with no data-path collective
+(weak scaling: every rank processes FRAMES frames per step); value = all frames / max-over-ranks time.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+RGBA8_P, BGRA8_P, ARGB8_P, ABGR8_P, RGBA8_U, BGRA8_U, ARGB8_U, ABGR8_U, RGB8, BGR8 = range(10)
+
+CONFIGS = {
+    # name: (type_in, w_in, h_in, type_out, w_out, h_out, srgb, premul-valid input, default frames per step, description)
+    "cfg1": (RGBA8_P, 1920, 1080, RGBA8_P, 960, 540, 0, True, 64, "1920x1080 RGBA8 premul -> 960x540 bilinear"),
+    "cfg2": (BGRA8_P, 3840, 2160, BGRA8_U, 1920, 1080, 0, True, 16,
+             "3840x2160 BGRA8 premul -> 1920x1080 BGRA8 unassociated, bilinear"),
+    "cfg3": (RGBA8_P, 7680, 4320, RGBA8_P, 800, 450, 1, True, 4, "7680x4320 RGBA8 -> 800x450 box, sRGB linearisation"),
+    "cfg4": (RGB8, 1024, 768, RGB8, 4096, 3072, 0, False, 16, "1024x768 RGB8 -> 4096x3072 bilinear upscale"),
+    "cfg5": (ARGB8_P, 2048, 2048, ARGB8_P, 256, 256, 0, True, 64, "2048x2048 ARGB8 -> 256x256 thumbnails (batched launch)"),
+}
+
+TYPE_NAMES = ["RGBA8_P", "BGRA8_P", "ARGB8_P", "ABGR8_P", "RGBA8_U", "BGRA8_U", "ARGB8_U", "ABGR8_U", "RGB8", "BGR8"]
+
+
+def bpp(t):
+    return 3 if t >= RGB8 else 4
+
+
+def alpha_index(t):
+    if t >= RGB8:
+        return None
+    return 3 if (t & 3) < 2 else 0
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_frames_device(torch, cfg, n_frames, seed, device):
+    """n_frames distinct synthetic frames in one device buffer (frame i at i * frame_bytes)."""
+    ti, wi, hi = cfg[0], cfg[1], cfg[2]
+    premul = cfg[7]
+    b = bpp(ti)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    buf = torch.randint(0, 256, (n_frames, hi, wi, b), dtype=torch.uint8, device=device, generator=g)
+    ai = alpha_index(ti)
+    if premul and ai is not None:
+        # premultiplied-valid pixels: colour = round(colour * alpha / 255)   
+        al = buf[..., ai:ai + 1].to(torch.int32)
+        col = (buf.to(torch.int32) * al + 127) // 255
+        col[..., ai:ai + 1] = al
+        buf = col.to(torch.uint8)
+    return buf.contiguous()
+
+
+def run_reference_arm(args, cfg_name, cfg, rank, world):
+    """--impl reference: the reference's own CPU implementation, all host threads, bounded sample."""
+    import oracle
+    ti, wi, hi, to, wo, ho, srgb, premul, frames_default, desc = cfg
+    if rank != 0:
+        return
+    avx2_path = os.path.join(ROOT, "oracle", "_ref", "libsmolref_avx2.so")
+    gen_path = os.path.join(ROOT, "oracle", "_ref", "libsmolref.so")
+    if os.path.exists(avx2_path):
+        lib_path, kind, label = avx2_path, "reference", "reference AVX2 build (oracle/_ref/libsmolref_avx2.so)"
+    elif os.path.exists(gen_path):
+        lib_path, kind, label = gen_path, "reference", "reference generic build (oracle/_ref/libsmolref.so)"
+    else:
+        lib_path, kind, label = None, "port", "plain-C oracle port (oracle/liboracle.so), single thread"
+    cores = os.cpu_count() or 1
+    frames = args.cpu_frames
+    rng = np.random.default_rng(1)
+    src = rng.integers(0, 256, size=(2, hi * wi * bpp(ti)), dtype=np.uint8)
+    out = np.zeros(ho * wo * bpp(to), np.uint8)
+
+    def one_step():
+        t0 = time.perf_counter()
+        if lib_path:
+            h = run_reference_arm.harness
+            for f in range(frames):
+                h.scale_threaded(src[f & 1], ti, wi, hi, wi * bpp(ti), out, to, wo, ho, wo * bpp(to), srgb, cores, 1)
+        else:
+            chk = oracle.restatement()
+            for f in range(frames):
+                chk._simple(src[f & 1].ctypes.data, ti, wi, hi, wi * bpp(ti), out.ctypes.data, to, wo, ho,
+                            wo * bpp(to), srgb)
+        return time.perf_counter() - t0
+
+    if lib_path:
+        run_reference_arm.harness = oracle.Harness(lib_path)
+    for _ in range(args.warmup):
+        one_step()
+    t = sum(one_step() for _ in range(args.steps))
+    ms_per_step = t / args.steps * 1e3
+    value = frames * wo * ho / 1e6 / (ms_per_step / 1e3)
+    used = cores if lib_path else 1
+    line = {
+        "impl": "reference", "metric": "output Mpix/s", "value": round(value, 2), "unit": "Mpix/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": desc, "config": cfg_name, "frames_per_step": frames,
+                   "types": "%s->%s" % (TYPE_NAMES[ti], TYPE_NAMES[to]), "srgb": srgb},
+        "cpu_baseline": {"value": round(value, 2), "unit": "Mpix/s", "cores": used, "kind": kind,
+                         "sample": "%d frames per step, %s, %d row-band threads" % (frames, label, used)},
+        "e2e": {"value": round(value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(cfg, budget_s=12.0):
+    """Bounded sample of the same workload on the host cores (rank 0, N=1 only)."""
+    import oracle
+    ti, wi, hi, to, wo, ho, srgb = cfg[:7]
+    avx2_path = os.path.join(ROOT, "oracle", "_ref", "libsmolref_avx2.so")
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(1)
+    src = rng.integers(0, 256, size=hi * wi * bpp(ti), dtype=np.uint8)
+    out = np.zeros(ho * wo * bpp(to), np.uint8)
+    if os.path.exists(avx2_path):
+        h = oracle.Harness(avx2_path)
+        h.scale_threaded(src, ti, wi, hi, wi * bpp(ti), out, to, wo, ho, wo * bpp(to), srgb, cores, 1)
+        n, t0 = 0, time.perf_counter()
+        while True:
+            h.scale_threaded(src, ti, wi, hi, wi * bpp(ti), out, to, wo, ho, wo * bpp(to), srgb, cores, 1)
+            n += 1
+            el = time.perf_counter() - t0
+            if el * cores > budget_s or n >= 400:
+                break
+        h.close()
+        return {"value": round(n * wo * ho / 1e6 / el, 2), "unit": "Mpix/s", "cores": cores, "kind": "reference",
+                "sample": "%d frames, reference AVX2 build, %d row-band threads (smol_scale_batch_full), %.2f s wall"
+                          % (n, cores, el)}
+    chk = oracle.restatement()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        chk._simple(src.ctypes.data, ti, wi, hi, wi * bpp(ti), out.ctypes.data, to, wo, ho, wo * bpp(to), srgb)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 100:
+            break
+    return {"value": round(n * wo * ho / 1e6 / el, 2), "unit": "Mpix/s", "cores": 1, "kind": "port",
+            "sample": "%d frames, plain-C oracle port, 1 thread, %.2f s wall" % (n, el)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per step (0 = config default)")
+    ap.add_argument("--cpu-frames", type=int, default=24, help="--impl reference: frames per step")
+    ap.add_argument("--no-graph", action="store_true", help="launch directly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel", type=int, default=0, help="force a kernel family (testing)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg_name = args.config
+    cfg = CONFIGS[cfg_name]
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg_name, cfg, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import smolscale_b200 as sb
+
+    if not torch.cuda.is_available() or sb.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    ti, wi, hi, to, wo, ho, srgb, premul, frames_default, desc = cfg
+    frames = args.frames or frames_default
+    si, so = wi * bpp(ti), wo * bpp(to)
+    in_bytes, out_bytes = si * hi, so * ho
+    alg_bytes = in_bytes + out_bytes
+
+    d_in = synth_frames_device(torch, cfg, frames, 1234 + rank, device).view(-1)
+    d_out = torch.zeros(frames * out_bytes, dtype=torch.uint8, device=device)
+    if args.kernel:
+        sb.force_kernel(args.kernel)
+
+    stream = torch.cuda.Stream(device=device)
+    batched = cfg_name == "cfg5"
+
+    def enqueue_step():
+        if batched:
+            sb.scale_images(d_in.data_ptr(), in_bytes, ti, wi, hi, si, d_out.data_ptr(), out_bytes, to, wo, ho, so,
+                            srgb, frames)
+        else:
+            for f in range(frames):
+                sb.scale_simple(d_in.data_ptr() + f * in_bytes, ti, wi, hi, si,
+                                d_out.data_ptr() + f * out_bytes, to, wo, ho, so, srgb)
+
+    with torch.cuda.stream(stream):
+        sb.set_stream(stream.cuda_stream)
+        enqueue_step()                      # first touch: table upload, module load
+        stream.synchronize()
+        graph = None
+        if not args.no_graph:
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    enqueue_step()
+            except Exception as e:          # fall back to direct launches
+                sys.stderr.write("bench: CUDA graph capture unavailable (%s); launching directly\n" % (e,))
+                graph = None
+                torch.cuda.synchronize()
+        sb.set_stream(stream.cuda_stream)
+
+        def step():
+            if graph is not None:
+                graph.replay()
+            else:
+                enqueue_step()
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        stream.synchronize()
+
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sb.reset_stats()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        elapsed_ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        launches_direct = sb.stats()["kernel_launches"]
+
+    launches_per_step = 1 if batched else frames
+    # launches counted by the library when launching directly; when a graph replays them the
+    # library is not re-entered, so count what the graph contains
+    gpu_launches = launches_direct if graph is None else launches_per_step * args.steps
+
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * frames * wo * ho / 1e6 / (ms_per_step / 1e3)
+
+    # ---- correctness guard: one frame of the timed output against the oracle (rank 0) ----
+    check = None
+    if rank == 0:
+        try:
+            import oracle
+            f = frames - 1
+            src = d_in[f * in_bytes:(f + 1) * in_bytes].cpu().numpy()
+            got = d_out[f * out_bytes:(f + 1) * out_bytes].cpu().numpy()
+            y0 = ho // 2
+            rows = min(4, ho - y0)
+            want = oracle.restatement().scale_rows(src, ti, wi, hi, si, to, wo, ho, y0, rows, so, srgb)
+            check = bool(np.array_equal(want, got[y0 * so:y0 * so + want.size]))
+        except Exception as e:
+            check = "unchecked: %s" % (e,)
+
+    # ---- end to end through the public API with pinned host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        e2e_frames = min(frames, 8)
+        h_in = torch.empty(e2e_frames * in_bytes, dtype=torch.uint8).pin_memory()
+        h_in.copy_(d_in[:e2e_frames * in_bytes])
+        h_out = torch.zeros(e2e_frames * out_bytes, dtype=torch.uint8).pin_memory()
+        sb.set_device(local_rank)
+
+        def e2e_step():
+            for f in range(e2e_frames):
+                sb.scale_simple(h_in.data_ptr() + f * in_bytes, ti, wi, hi, si,
+                                h_out.data_ptr() + f * out_bytes, to, wo, ho, so, srgb)
+
+        for _ in range(2):
+            e2e_step()
+        if world > 1:
+            dist.barrier()
+        k = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(k):
+            e2e_step()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+        e2e = {"value": round(world * k * e2e_frames * wo * ho / 1e6 / e2e_s, 2), "unit": "Mpix/s",
+               "h2d_bytes_per_step": e2e_frames * in_bytes, "d2h_bytes_per_step": e2e_frames * out_bytes,
+               "frames_per_step": e2e_frames, "api": "smol_scale_simple, pinned host pointers, synchronous"}
+        if rank == 0 and check is True:
+            same = torch.equal(h_out[:out_bytes].to(device), d_out[:out_bytes])
+            e2e["matches_device_path"] = bool(same)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    kernel_ms = elapsed_ms / (args.steps * launches_per_step)
+    alg_per_launch = alg_bytes * (frames if batched else 1)
+    achieved = alg_per_launch / (kernel_ms * 1e-3) / 1e9
+    plan = sb.plan_query(ti, wi, hi, to, wo, ho, srgb)
+
+    line = {
+        "metric": "output Mpix/s", "value": round(value, 2), "unit": "Mpix/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": desc, "config": cfg_name, "frames_per_step_per_gpu": frames,
+                   "types": "%s->%s" % (TYPE_NAMES[ti], TYPE_NAMES[to]), "srgb": srgb,
+                   "l2": "inputs larger than L2: %d distinct frames = %.0f MB in + %.0f MB out per step"
+                         % (frames, frames * in_bytes / 1e6, frames * out_bytes / 1e6),
+                   "launch": "cuda graph replay" if graph is not None else "direct stream-ordered launches",
+                   "kernel": plan["kernel_name"], "parallelism": "frames sharded across %d GPU(s), no collective" % world},
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": round(kernel_ms, 6)},
+        "e2e": e2e,
+        "gpu_launches": int(gpu_launches),
+        "clocks": clocks,
+        "parity_spot_check": check,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline_sample(cfg)
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "Mpix/s", "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -533,6 +533,221 @@ smol_general_kernel (const SmolLaunch L)
 }
 
 /* ------------------------------------------------------------------------------------------ *
+ * "half" kernel: exact 2^k : 1 reductions on both axes (every bilinear weight is 128 and sample *
+ * i reads pixels 2i, 2i + 1 -- BASELINE configs 1, 2 and 5), 32bpp premultiplied or alpha-less  *
+ * source, 8-bit premultiplied intermediate.                                                    *
+ *                                                                                              *
+ * With F = 128 the reference's tap ((p - q) * 128 >> 8) + q is, lane by lane, floor ((p + q)/2) *
+ * (SURVEY A.7), so all the filtering can be done on the packed source bytes without unpacking   *
+ * to 16-bit lanes: one output pixel of a 2:1 job is three byte-wise floor averages.  Halvings   *
+ * (sum of 2^n such samples, then >> n) are accumulated in 16-bit lanes.  A thread produces four *
+ * adjacent output pixels: 128-bit loads of the source rows, one 128-bit store.                  *
+ * ------------------------------------------------------------------------------------------ */
+
+__device__ __forceinline__ uint32_t byte_avg_floor (uint32_t a, uint32_t b)
+{
+    /* per byte: floor ((a + b) / 2) without carries between bytes */
+    return (a & b) + (((a ^ b) & 0xfefefefeu) >> 1);
+}
+
+struct HalfParams
+{
+    const uint8_t *src; uint8_t *dst;
+    uint32_t src_pitch, dst_pitch;
+    size_t src_image_stride, dst_image_stride;
+    uint32_t w_out, first_row, n_rows, n_images;
+    uint32_t items_per_row;         /* ceil (w_out / 4) */
+    uint32_t alpha_shift;           /* 8 * byte index of alpha in a source pixel */
+    uint32_t col_shift;             /* 8 * byte index of the first colour byte */
+    uint32_t prmt_sel;              /* source byte order -> destination byte order */
+    const uint32_t *inv_div_p8;     /* device LUT */
+};
+
+/* unpremultiply one packed pixel in source byte order (reference generic:246-259 via :892-901) */
+__device__ __forceinline__ uint32_t half_unpremul (uint32_t v, const HalfParams &P, const uint32_t *__restrict__ sm_inv)
+{
+    const uint32_t a = (v >> P.alpha_shift) & 0xff;
+    /* sm_inv holds inv_div_p8 << 3, so (c * inv) >> 13 & 0xff is byte 2 of the 32-bit product
+     * (c <= 255 and inv < 2^21 keep it below 2^32) */
+    const uint32_t inv8 = sm_inv[a];
+    const uint32_t c0 = (v >> P.col_shift) & 0xff;
+    const uint32_t c1 = (v >> (P.col_shift + 8)) & 0xff;
+    const uint32_t c2 = (v >> (P.col_shift + 16)) & 0xff;
+    const uint32_t u0 = __byte_perm (c0 * inv8, 0, 0x4442);
+    const uint32_t u1 = __byte_perm (c1 * inv8, 0, 0x4442);
+    const uint32_t u2 = __byte_perm (c2 * inv8, 0, 0x4442);
+    return (a << P.alpha_shift) | ((u0 | (u1 << 8) | (u2 << 16)) << P.col_shift);
+}
+
+/* Horizontally reduced value of one output pixel on one source row, as packed bytes.
+ * px points at the 2 << HH source pixels of this output pixel (already loaded). */
+template <int HH>
+__device__ __forceinline__ uint32_t half_hreduce (const uint32_t *px)
+{
+    if constexpr (HH == 0)
+    {
+        return byte_avg_floor (px[0], px[1]);
+    }
+    else
+    {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < (1 << HH); k++)
+        {
+            const uint32_t v = byte_avg_floor (px[2 * k], px[2 * k + 1]);
+            lo += v & 0x00ff00ffu;
+            hi += (v >> 8) & 0x00ff00ffu;
+        }
+        lo = (lo >> HH) & 0x00ff00ffu;
+        hi = (hi >> HH) & 0x00ff00ffu;
+        return lo | (hi << 8);
+    }
+}
+
+template <int HH, int VH, bool UNPREMUL>
+__global__ void __launch_bounds__ (256)
+smol_half_kernel (const HalfParams P)
+{
+    __shared__ uint32_t sm_inv[256];
+
+    if constexpr (UNPREMUL)
+    {
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
+            sm_inv[i] = __ldg (&P.inv_div_p8[i]) << 3;
+        __syncthreads ();
+    }
+
+    constexpr int SRC_PER_OUT = 2 << HH;            /* source pixels per output pixel per row */
+    constexpr int VEC_PER_OUT = SRC_PER_OUT / 4 > 0 ? SRC_PER_OUT / 4 : 1;
+    const uint64_t items_per_image = (uint64_t) P.items_per_row * P.n_rows;
+    const uint64_t n_items = items_per_image * P.n_images;
+
+    for (uint64_t item = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; item < n_items;
+         item += (uint64_t) gridDim.x * blockDim.x)
+    {
+        const uint32_t img = (uint32_t) (item / items_per_image);
+        const uint32_t rem = (uint32_t) (item - (uint64_t) img * items_per_image);
+        const uint32_t yl = rem / P.items_per_row;
+        const uint32_t x = (rem - yl * P.items_per_row) * 4;
+        const uint32_t y = P.first_row + yl;
+        const uint8_t *src = P.src + (size_t) img * P.src_image_stride;
+        uint8_t *dst = P.dst + (size_t) img * P.dst_image_stride + (size_t) yl * P.dst_pitch + (size_t) x * 4;
+        const uint32_t n_px = min (4u, P.w_out - x);
+        uint32_t out[4];
+
+        if (n_px == 4)
+        {
+            uint32_t acc_lo[4] = { 0, 0, 0, 0 }, acc_hi[4] = { 0, 0, 0, 0 };
+
+#pragma unroll
+            for (int kv = 0; kv < (1 << VH); kv++)
+            {
+                const uint32_t r = 2 * ((y << VH) + kv);
+                const uint8_t *row0 = src + (size_t) r * P.src_pitch + (size_t) x * SRC_PER_OUT * 4;
+                const uint8_t *row1 = row0 + P.src_pitch;
+                uint32_t h0[4], h1[4];
+
+                if constexpr (HH == 0)
+                {
+                    /* 4 output pixels = 8 source pixels = two 128-bit loads per row */
+                    uint4 a0 = ldg_nc_v4 (row0), a1 = ldg_nc_v4 (row0 + 16);
+                    uint4 b0 = ldg_nc_v4 (row1), b1 = ldg_nc_v4 (row1 + 16);
+                    h0[0] = byte_avg_floor (a0.x, a0.y); h0[1] = byte_avg_floor (a0.z, a0.w);
+                    h0[2] = byte_avg_floor (a1.x, a1.y); h0[3] = byte_avg_floor (a1.z, a1.w);
+                    h1[0] = byte_avg_floor (b0.x, b0.y); h1[1] = byte_avg_floor (b0.z, b0.w);
+                    h1[2] = byte_avg_floor (b1.x, b1.y); h1[3] = byte_avg_floor (b1.z, b1.w);
+                }
+                else
+                {
+#pragma unroll
+                    for (int o = 0; o < 4; o++)
+                    {
+                        uint32_t pa[SRC_PER_OUT], pb[SRC_PER_OUT];
+#pragma unroll
+                        for (int v = 0; v < VEC_PER_OUT; v++)
+                        {
+                            const uint4 a = __ldg (reinterpret_cast<const uint4 *> (row0) + o * VEC_PER_OUT + v);
+                            const uint4 b = __ldg (reinterpret_cast<const uint4 *> (row1) + o * VEC_PER_OUT + v);
+                            pa[4 * v] = a.x; pa[4 * v + 1] = a.y; pa[4 * v + 2] = a.z; pa[4 * v + 3] = a.w;
+                            pb[4 * v] = b.x; pb[4 * v + 1] = b.y; pb[4 * v + 2] = b.z; pb[4 * v + 3] = b.w;
+                        }
+                        h0[o] = half_hreduce<HH> (pa);
+                        h1[o] = half_hreduce<HH> (pb);
+                    }
+                }
+
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+                {
+                    const uint32_t v = byte_avg_floor (h0[o], h1[o]);
+                    if constexpr (VH == 0)
+                        out[o] = v;
+                    else
+                    {
+                        acc_lo[o] += v & 0x00ff00ffu;
+                        acc_hi[o] += (v >> 8) & 0x00ff00ffu;
+                    }
+                }
+            }
+
+            if constexpr (VH > 0)
+            {
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+                    out[o] = ((acc_lo[o] >> VH) & 0x00ff00ffu) | (((acc_hi[o] >> VH) & 0x00ff00ffu) << 8);
+            }
+
+#pragma unroll
+            for (int o = 0; o < 4; o++)
+            {
+                uint32_t v = out[o];
+                if constexpr (UNPREMUL)
+                    v = half_unpremul (v, P, sm_inv);
+                out[o] = __byte_perm (v, 0, P.prmt_sel);
+            }
+            *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
+        }
+        else
+        {
+            /* ragged end of a row: one pixel at a time, same arithmetic */
+            for (uint32_t o = 0; o < n_px; o++)
+            {
+                uint32_t acc_lo = 0, acc_hi = 0, res = 0;
+
+                for (int kv = 0; kv < (1 << VH); kv++)
+                {
+                    const uint32_t r = 2 * ((y << VH) + kv);
+                    const uint32_t *row0 = reinterpret_cast<const uint32_t *> (src + (size_t) r * P.src_pitch)
+                                           + (size_t) (x + o) * SRC_PER_OUT;
+                    const uint32_t *row1 = reinterpret_cast<const uint32_t *> (src + (size_t) (r + 1) * P.src_pitch)
+                                           + (size_t) (x + o) * SRC_PER_OUT;
+                    uint32_t pa[SRC_PER_OUT], pb[SRC_PER_OUT];
+#pragma unroll
+                    for (int k = 0; k < SRC_PER_OUT; k++)
+                    {
+                        pa[k] = __ldg (row0 + k);
+                        pb[k] = __ldg (row1 + k);
+                    }
+                    const uint32_t v = byte_avg_floor (half_hreduce<HH> (pa), half_hreduce<HH> (pb));
+                    if (VH == 0)
+                        res = v;
+                    else
+                    {
+                        acc_lo += v & 0x00ff00ffu;
+                        acc_hi += (v >> 8) & 0x00ff00ffu;
+                    }
+                }
+                if (VH > 0)
+                    res = ((acc_lo >> VH) & 0x00ff00ffu) | (((acc_hi >> VH) & 0x00ff00ffu) << 8);
+                if constexpr (UNPREMUL)
+                    res = half_unpremul (res, P, sm_inv);
+                reinterpret_cast<uint32_t *> (dst)[o] = __byte_perm (res, 0, P.prmt_sel);
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ *
  * Host-side dispatch                                                                         *
  * ------------------------------------------------------------------------------------------ */
 
@@ -549,13 +764,119 @@ smol_cuda_kernel_name (int kernel_id)
     return kernel_names[kernel_id];
 }
 
+static bool
+aligned16 (const void *p)
+{
+    return (reinterpret_cast<uintptr_t> (p) & 15) == 0;
+}
+
+static bool
+half_eligible (const SmolLaunch &L)
+{
+    const SmolJobDesc &d = L.d;
+
+    return d.h_kind == SMOL_AXIS_TAPS && d.v_kind == SMOL_AXIS_TAPS
+           && d.all_half_x && d.all_half_y
+           && d.mid == SMOL_MID_P8 && !d.storage128
+           && d.bpp_in == 4 && d.bpp_out == 4 && !d.in_unassoc
+           && aligned16 (L.src) && aligned16 (L.dst)
+           && (L.src_pitch & 15) == 0 && (L.dst_pitch & 15) == 0
+           && (L.src_image_stride & 15) == 0 && (L.dst_image_stride & 15) == 0;
+}
+
 extern "C" int
 smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
 {
-    (void) launch;
-    if (forced > SMOL_KERNEL_AUTO && forced < SMOL_KERNEL_MAX)
+    const bool half_ok = half_eligible (*launch);
+
+    if (forced == SMOL_KERNEL_GENERAL)
         return SMOL_KERNEL_GENERAL;
+    if (forced == SMOL_KERNEL_HALF2X && half_ok)
+        return SMOL_KERNEL_HALF2X;
+    if (forced > SMOL_KERNEL_AUTO && forced < SMOL_KERNEL_MAX && forced != SMOL_KERNEL_HALF2X)
+        return SMOL_KERNEL_GENERAL;
+    if (half_ok)
+        return SMOL_KERNEL_HALF2X;
     return SMOL_KERNEL_GENERAL;
+}
+
+static int g_num_sms = 0;
+
+static int
+num_sms ()
+{
+    if (g_num_sms == 0)
+    {
+        int dev = 0, n = 148;
+        if (cudaGetDevice (&dev) == cudaSuccess)
+            cudaDeviceGetAttribute (&n, cudaDevAttrMultiProcessorCount, dev);
+        g_num_sms = n > 0 ? n : 148;
+    }
+    return g_num_sms;
+}
+
+template <int HH, int VH>
+static cudaError_t
+launch_half_hv (const HalfParams &P, bool unpremul, dim3 grid, cudaStream_t stream)
+{
+    if (unpremul)
+        smol_half_kernel<HH, VH, true><<<grid, 256, 0, stream>>> (P);
+    else
+        smol_half_kernel<HH, VH, false><<<grid, 256, 0, stream>>> (P);
+    return cudaGetLastError ();
+}
+
+static cudaError_t
+launch_half (const SmolLaunch &L, cudaStream_t stream)
+{
+    const SmolJobDesc &d = L.d;
+    HalfParams P;
+    uint32_t sel = 0;
+
+    P.src = L.src; P.dst = L.dst;
+    P.src_pitch = L.src_pitch; P.dst_pitch = L.dst_pitch;
+    P.src_image_stride = L.src_image_stride; P.dst_image_stride = L.dst_image_stride;
+    P.w_out = d.w_out; P.first_row = L.first_row; P.n_rows = L.n_rows; P.n_images = L.n_images;
+    P.items_per_row = (d.w_out + 3) / 4;
+    P.alpha_shift = (d.in_alpha_idx == 0xff ? 0 : d.in_alpha_idx) * 8;
+    P.col_shift = d.in_col0 * 8;
+    P.inv_div_p8 = L.luts->inv_div_p8;
+
+    /* destination byte j takes source byte perm[j] */
+    for (int j = 0; j < 4; j++)
+    {
+        uint32_t from;
+        if (j == d.out_alpha_idx)
+            from = d.in_alpha_idx;
+        else
+        {
+            const int i = j - d.out_col0;
+            from = d.in_col0 + (d.swap_rb ? 2 - i : i);
+        }
+        sel |= from << (4 * j);
+    }
+    P.prmt_sel = sel;
+
+    const uint64_t n_items = (uint64_t) P.items_per_row * L.n_rows * L.n_images;
+    uint64_t blocks = (n_items + 255) / 256;
+    const uint64_t cap = (uint64_t) num_sms () * 8 * 4;   /* a few waves of resident CTAs, grid-stride beyond */
+    if (blocks > cap)
+        blocks = cap;
+    dim3 grid ((unsigned) blocks);
+    const bool unpremul = d.out_unassoc;
+
+    switch (d.h_halvings * 3 + d.v_halvings)
+    {
+        case 0: return launch_half_hv<0, 0> (P, unpremul, grid, stream);
+        case 1: return launch_half_hv<0, 1> (P, unpremul, grid, stream);
+        case 2: return launch_half_hv<0, 2> (P, unpremul, grid, stream);
+        case 3: return launch_half_hv<1, 0> (P, unpremul, grid, stream);
+        case 4: return launch_half_hv<1, 1> (P, unpremul, grid, stream);
+        case 5: return launch_half_hv<1, 2> (P, unpremul, grid, stream);
+        case 6: return launch_half_hv<2, 0> (P, unpremul, grid, stream);
+        case 7: return launch_half_hv<2, 1> (P, unpremul, grid, stream);
+        default: return launch_half_hv<2, 2> (P, unpremul, grid, stream);
+    }
 }
 
 template <bool S128, bool HBOX, bool VBOX>
@@ -612,12 +933,16 @@ smol_cuda_launch (const SmolLaunch *launch, int kernel_id, void *stream_p, const
     const bool hb = L.d.h_kind == SMOL_AXIS_BOX, vb = L.d.v_kind == SMOL_AXIS_BOX;
     cudaError_t err;
 
-    (void) kernel_id;
+    if (kernel_id <= SMOL_KERNEL_AUTO || kernel_id >= SMOL_KERNEL_MAX)
+        kernel_id = smol_cuda_pick_kernel (launch, SMOL_KERNEL_AUTO);
     if (name_out)
-        *name_out = kernel_names[SMOL_KERNEL_GENERAL];
+        *name_out = kernel_names[kernel_id];
 
     if (L.n_rows == 0 || L.n_images == 0)
         return 0;
+
+    if (kernel_id == SMOL_KERNEL_HALF2X && half_eligible (L))
+        return (int) launch_half (L, stream);
 
     shape_general (L);
 

@@ -89,6 +89,25 @@ def job_matrix(seed, n_jobs, axis_pairs=AXIS_PAIRS, max_pixels=300000):
     return jobs
 
 
+# exact 2^k : 1 reductions (every bilinear weight 128): the packed-byte "half" kernel family
+HALF_AXIS_PAIRS = [(2, 1), (4, 1), (8, 1), (8, 4), (10, 5), (16, 4), (28, 7), (24, 3), (64, 8), (62, 31),
+                   (36, 9), (50, 25), (256, 32)]
+
+
+def half_jobs(seed=5):
+    """Jobs that are eligible for the half kernel (32bpp premultiplied / alpha-less-free source,
+    32bpp destination) over every halving combination and ragged widths."""
+    rng = np.random.default_rng(seed)
+    jobs = []
+    for (wi, wo) in HALF_AXIS_PAIRS:
+        for (hi, ho) in HALF_AXIS_PAIRS:
+            ti = int(rng.integers(0, 4))
+            to = int(rng.integers(0, 8))
+            mode = IMAGE_MODES[int(rng.integers(len(IMAGE_MODES)))]
+            jobs.append((ti, wi, hi, wi * 4, to, wo, ho, wo * 4, 0, mode))
+    return jobs
+
+
 def all_type_pairs():
     return list(itertools.product(ALL_TYPES, ALL_TYPES))
 

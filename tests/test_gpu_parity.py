@@ -52,6 +52,33 @@ def test_random_matrix_vs_oracle(sb, restatement):
         assert np.array_equal(got, want), (job, describe(got, want))
 
 
+def test_half_kernel_family(sb, restatement):
+    """Exact 2^k:1 jobs: automatic dispatch (packed-byte kernel) == general kernel == oracle,
+    with device pointers both 16-byte aligned (fast path) and misaligned (fallback)."""
+    import torch
+    n_fast = 0
+    for idx, job in enumerate(cases.half_jobs()):
+        ti, wi, hi, si, to, wo, ho, so, srgb, mode = job
+        src = cases.make_image(ti, wi, hi, si, mode, seed=idx)
+        want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
+        p = sb.plan_query(ti, wi, hi, to, wo, ho, srgb)
+        n_fast += p["kernel_name"] == "half2x"
+        for forced in (0, 1):
+            sb.force_kernel(forced)
+            try:
+                got = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, srgb)
+            finally:
+                sb.force_kernel(0)
+            assert np.array_equal(got, want), (job, forced, describe(got, want))
+        d_in = torch.zeros(src.size + 16, dtype=torch.uint8, device="cuda")
+        d_in[4:4 + src.size] = torch.from_numpy(src).cuda()
+        d_out = torch.zeros(want.size + 16, dtype=torch.uint8, device="cuda")
+        sb.scale_simple(d_in.data_ptr() + 4, ti, wi, hi, si, d_out.data_ptr() + 4, to, wo, ho, so, srgb)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy()[4:4 + want.size], want), job
+    assert n_fast > 100
+
+
 def test_unaligned_host_pointers(sb, restatement):
     """Odd base addresses and odd pitches on both sides (verify.c uses pitch 3 and 4)."""
     for off_in, off_out, ti, to in [(1, 3, cases.RGBA8_P, cases.ARGB8_U), (2, 1, cases.RGB8, cases.BGR8),

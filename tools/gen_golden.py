@@ -41,6 +41,9 @@ def golden_jobs():
             jobs["pairs_box_%03d" % k] = (ti, 331, 97, 331 * cases.bpp(ti), to, 13, 9,
                                           13 * cases.bpp(to), srgb, "alpha_edges", 7000 + k)
             k += 1
+    # exact 2^k:1 reductions (packed-byte kernel family)
+    for i, j in enumerate(cases.half_jobs()):
+        jobs["half_%03d" % i] = j + (3000 + i,)
     # table-edge cases on long axes
     for i, (a, b) in enumerate(cases.BIG_AXIS_PAIRS):
         for srgb in (0, 1):
