@@ -245,6 +245,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel", type=int, default=0, help="force a kernel family (testing)")
+    ap.add_argument("--batched", action="store_true",
+                    help="submit all frames of a step in one launch (smol_cuda_scale_images); default for cfg5")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -280,7 +282,7 @@ def main():
         sb.force_kernel(args.kernel)
 
     stream = torch.cuda.Stream(device=device)
-    batched = cfg_name == "cfg5"
+    batched = cfg_name == "cfg5" or args.batched
 
     def enqueue_step():
         if batched:

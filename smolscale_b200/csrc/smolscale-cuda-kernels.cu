@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "smolscale-cuda-private.h"
 
@@ -544,6 +545,21 @@ smol_general_kernel (const SmolLaunch L)
  * adjacent output pixels: 128-bit loads of the source rows, one 128-bit store.                  *
  * ------------------------------------------------------------------------------------------ */
 
+/* Programmatic dependent launch (PDL): our kernels are launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, let the next kernel in the stream start
+ * its CTAs early (pdl_launch_dependents) and wait for the previous kernel's memory to be
+ * complete and visible before touching any user buffer (pdl_wait).  Stream order is preserved
+ * exactly; only launch latency and prologue overlap the predecessor's tail. */
+__device__ __forceinline__ void pdl_launch_dependents ()
+{
+    asm volatile ("griddepcontrol.launch_dependents;");
+}
+
+__device__ __forceinline__ void pdl_wait ()
+{
+    asm volatile ("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t byte_avg_floor (uint32_t a, uint32_t b)
 {
     /* per byte: floor ((a + b) / 2) without carries between bytes */
@@ -555,28 +571,40 @@ struct HalfParams
     const uint8_t *src; uint8_t *dst;
     uint32_t src_pitch, dst_pitch;
     size_t src_image_stride, dst_image_stride;
-    uint32_t w_out, first_row, n_rows, n_images;
+    uint32_t w_out, first_row, n_rows;
     uint32_t items_per_row;         /* ceil (w_out / 4) */
-    uint32_t alpha_shift;           /* 8 * byte index of alpha in a source pixel */
-    uint32_t col_shift;             /* 8 * byte index of the first colour byte */
     uint32_t prmt_sel;              /* source byte order -> destination byte order */
     const uint32_t *inv_div_p8;     /* device LUT */
 };
 
-/* unpremultiply one packed pixel in source byte order (reference generic:246-259 via :892-901) */
-__device__ __forceinline__ uint32_t half_unpremul (uint32_t v, const HalfParams &P, const uint32_t *__restrict__ sm_inv)
+/* Unpremultiply one packed pixel, kept in source byte order (reference generic:246-259 via
+ * :892-901).  sm_inv holds inv_div_p8 << 3, so ((c * inv) >> 13) & 0xff is byte 2 of the 32-bit
+ * product (c <= 255 and inv < 2^21 keep it below 2^32). */
+template <bool ALPHA_FIRST>
+__device__ __forceinline__ uint32_t half_unpremul (uint32_t v, const uint32_t *__restrict__ sm_inv)
 {
-    const uint32_t a = (v >> P.alpha_shift) & 0xff;
-    /* sm_inv holds inv_div_p8 << 3, so (c * inv) >> 13 & 0xff is byte 2 of the 32-bit product
-     * (c <= 255 and inv < 2^21 keep it below 2^32) */
-    const uint32_t inv8 = sm_inv[a];
-    const uint32_t c0 = (v >> P.col_shift) & 0xff;
-    const uint32_t c1 = (v >> (P.col_shift + 8)) & 0xff;
-    const uint32_t c2 = (v >> (P.col_shift + 16)) & 0xff;
-    const uint32_t u0 = __byte_perm (c0 * inv8, 0, 0x4442);
-    const uint32_t u1 = __byte_perm (c1 * inv8, 0, 0x4442);
-    const uint32_t u2 = __byte_perm (c2 * inv8, 0, 0x4442);
-    return (a << P.alpha_shift) | ((u0 | (u1 << 8) | (u2 << 16)) << P.col_shift);
+    if constexpr (ALPHA_FIRST)
+    {
+        /* bytes: a c0 c1 c2 */
+        const uint32_t inv8 = sm_inv[v & 0xff];
+        const uint32_t p0 = __byte_perm (v, 0, 0x4441) * inv8;
+        const uint32_t p1 = __byte_perm (v, 0, 0x4442) * inv8;
+        const uint32_t p2 = (v >> 24) * inv8;
+        const uint32_t t = __byte_perm (v, p0, 0x4460);        /* a, p0.b2 */
+        const uint32_t u = __byte_perm (p1, p2, 0x4462);       /* p1.b2, p2.b2 */
+        return __byte_perm (t, u, 0x5410);
+    }
+    else
+    {
+        /* bytes: c0 c1 c2 a */
+        const uint32_t inv8 = sm_inv[v >> 24];
+        const uint32_t p0 = (v & 0xff) * inv8;
+        const uint32_t p1 = __byte_perm (v, 0, 0x4441) * inv8;
+        const uint32_t p2 = __byte_perm (v, 0, 0x4442) * inv8;
+        const uint32_t t = __byte_perm (p0, p1, 0x4462);       /* p0.b2, p1.b2 */
+        const uint32_t u = __byte_perm (p2, v, 0x4472);        /* p2.b2, a */
+        return __byte_perm (t, u, 0x5410);
+    }
 }
 
 /* Horizontally reduced value of one output pixel on one source row, as packed bytes.
@@ -604,146 +632,233 @@ __device__ __forceinline__ uint32_t half_hreduce (const uint32_t *px)
     }
 }
 
-template <int HH, int VH, bool UNPREMUL>
+/* PACK: 0 = byte permutation only, 1 = unpremultiply with alpha in byte 3, 2 = ... in byte 0.
+ * Block = (bx, by) threads; thread (tx, ty) of CTA (cx, cy, image) produces output pixels
+ * 4 * (cx * bx + tx) .. + 3 of output row first_row + cy * by + ty. */
+template <int HH, int VH, int PACK>
 __global__ void __launch_bounds__ (256)
 smol_half_kernel (const HalfParams P)
 {
     __shared__ uint32_t sm_inv[256];
 
-    if constexpr (UNPREMUL)
+    pdl_launch_dependents ();
+    if constexpr (PACK != 0)
     {
-        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
+        /* the LUT is library-owned constant data: safe to read before the dependency wait */
+        for (uint32_t i = threadIdx.y * blockDim.x + threadIdx.x; i < 256; i += blockDim.x * blockDim.y)
             sm_inv[i] = __ldg (&P.inv_div_p8[i]) << 3;
         __syncthreads ();
     }
+    pdl_wait ();
 
     constexpr int SRC_PER_OUT = 2 << HH;            /* source pixels per output pixel per row */
     constexpr int VEC_PER_OUT = SRC_PER_OUT / 4 > 0 ? SRC_PER_OUT / 4 : 1;
-    const uint64_t items_per_image = (uint64_t) P.items_per_row * P.n_rows;
-    const uint64_t n_items = items_per_image * P.n_images;
 
-    for (uint64_t item = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; item < n_items;
-         item += (uint64_t) gridDim.x * blockDim.x)
+    const uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t yl = blockIdx.y * blockDim.y + threadIdx.y;
+    if (xi >= P.items_per_row || yl >= P.n_rows)
+        return;
+
+    const uint32_t x = xi * 4;
+    const uint32_t y = P.first_row + yl;
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
+    uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl * P.dst_pitch + (size_t) x * 4;
+    const uint32_t n_px = min (4u, P.w_out - x);
+    uint32_t out[4];
+
+    if (n_px == 4)
     {
-        const uint32_t img = (uint32_t) (item / items_per_image);
-        const uint32_t rem = (uint32_t) (item - (uint64_t) img * items_per_image);
-        const uint32_t yl = rem / P.items_per_row;
-        const uint32_t x = (rem - yl * P.items_per_row) * 4;
-        const uint32_t y = P.first_row + yl;
-        const uint8_t *src = P.src + (size_t) img * P.src_image_stride;
-        uint8_t *dst = P.dst + (size_t) img * P.dst_image_stride + (size_t) yl * P.dst_pitch + (size_t) x * 4;
-        const uint32_t n_px = min (4u, P.w_out - x);
-        uint32_t out[4];
+        uint32_t acc_lo[4] = { 0, 0, 0, 0 }, acc_hi[4] = { 0, 0, 0, 0 };
 
-        if (n_px == 4)
+#pragma unroll
+        for (int kv = 0; kv < (1 << VH); kv++)
         {
-            uint32_t acc_lo[4] = { 0, 0, 0, 0 }, acc_hi[4] = { 0, 0, 0, 0 };
+            const uint32_t r = 2 * ((y << VH) + kv);
+            const uint8_t *row0 = src + (size_t) r * P.src_pitch + (size_t) x * (SRC_PER_OUT * 4);
+            const uint8_t *row1 = row0 + P.src_pitch;
+            uint32_t h0[4], h1[4];
 
-#pragma unroll
-            for (int kv = 0; kv < (1 << VH); kv++)
+            if constexpr (HH == 0)
             {
-                const uint32_t r = 2 * ((y << VH) + kv);
-                const uint8_t *row0 = src + (size_t) r * P.src_pitch + (size_t) x * SRC_PER_OUT * 4;
-                const uint8_t *row1 = row0 + P.src_pitch;
-                uint32_t h0[4], h1[4];
-
-                if constexpr (HH == 0)
-                {
-                    /* 4 output pixels = 8 source pixels = two 128-bit loads per row */
-                    uint4 a0 = ldg_nc_v4 (row0), a1 = ldg_nc_v4 (row0 + 16);
-                    uint4 b0 = ldg_nc_v4 (row1), b1 = ldg_nc_v4 (row1 + 16);
-                    h0[0] = byte_avg_floor (a0.x, a0.y); h0[1] = byte_avg_floor (a0.z, a0.w);
-                    h0[2] = byte_avg_floor (a1.x, a1.y); h0[3] = byte_avg_floor (a1.z, a1.w);
-                    h1[0] = byte_avg_floor (b0.x, b0.y); h1[1] = byte_avg_floor (b0.z, b0.w);
-                    h1[2] = byte_avg_floor (b1.x, b1.y); h1[3] = byte_avg_floor (b1.z, b1.w);
-                }
-                else
-                {
-#pragma unroll
-                    for (int o = 0; o < 4; o++)
-                    {
-                        uint32_t pa[SRC_PER_OUT], pb[SRC_PER_OUT];
-#pragma unroll
-                        for (int v = 0; v < VEC_PER_OUT; v++)
-                        {
-                            const uint4 a = __ldg (reinterpret_cast<const uint4 *> (row0) + o * VEC_PER_OUT + v);
-                            const uint4 b = __ldg (reinterpret_cast<const uint4 *> (row1) + o * VEC_PER_OUT + v);
-                            pa[4 * v] = a.x; pa[4 * v + 1] = a.y; pa[4 * v + 2] = a.z; pa[4 * v + 3] = a.w;
-                            pb[4 * v] = b.x; pb[4 * v + 1] = b.y; pb[4 * v + 2] = b.z; pb[4 * v + 3] = b.w;
-                        }
-                        h0[o] = half_hreduce<HH> (pa);
-                        h1[o] = half_hreduce<HH> (pb);
-                    }
-                }
-
-#pragma unroll
-                for (int o = 0; o < 4; o++)
-                {
-                    const uint32_t v = byte_avg_floor (h0[o], h1[o]);
-                    if constexpr (VH == 0)
-                        out[o] = v;
-                    else
-                    {
-                        acc_lo[o] += v & 0x00ff00ffu;
-                        acc_hi[o] += (v >> 8) & 0x00ff00ffu;
-                    }
-                }
+                /* 4 output pixels = 8 source pixels = two 128-bit loads per row */
+                const uint4 a0 = ldg_nc_v4 (row0), a1 = ldg_nc_v4 (row0 + 16);
+                const uint4 b0 = ldg_nc_v4 (row1), b1 = ldg_nc_v4 (row1 + 16);
+                h0[0] = byte_avg_floor (a0.x, a0.y); h0[1] = byte_avg_floor (a0.z, a0.w);
+                h0[2] = byte_avg_floor (a1.x, a1.y); h0[3] = byte_avg_floor (a1.z, a1.w);
+                h1[0] = byte_avg_floor (b0.x, b0.y); h1[1] = byte_avg_floor (b0.z, b0.w);
+                h1[2] = byte_avg_floor (b1.x, b1.y); h1[3] = byte_avg_floor (b1.z, b1.w);
             }
-
-            if constexpr (VH > 0)
+            else
             {
 #pragma unroll
                 for (int o = 0; o < 4; o++)
-                    out[o] = ((acc_lo[o] >> VH) & 0x00ff00ffu) | (((acc_hi[o] >> VH) & 0x00ff00ffu) << 8);
+                {
+                    uint32_t pa[SRC_PER_OUT], pb[SRC_PER_OUT];
+#pragma unroll
+                    for (int v = 0; v < VEC_PER_OUT; v++)
+                    {
+                        const uint4 a = __ldg (reinterpret_cast<const uint4 *> (row0) + o * VEC_PER_OUT + v);
+                        const uint4 b = __ldg (reinterpret_cast<const uint4 *> (row1) + o * VEC_PER_OUT + v);
+                        pa[4 * v] = a.x; pa[4 * v + 1] = a.y; pa[4 * v + 2] = a.z; pa[4 * v + 3] = a.w;
+                        pb[4 * v] = b.x; pb[4 * v + 1] = b.y; pb[4 * v + 2] = b.z; pb[4 * v + 3] = b.w;
+                    }
+                    h0[o] = half_hreduce<HH> (pa);
+                    h1[o] = half_hreduce<HH> (pb);
+                }
             }
 
 #pragma unroll
             for (int o = 0; o < 4; o++)
             {
-                uint32_t v = out[o];
-                if constexpr (UNPREMUL)
-                    v = half_unpremul (v, P, sm_inv);
-                out[o] = __byte_perm (v, 0, P.prmt_sel);
+                const uint32_t v = byte_avg_floor (h0[o], h1[o]);
+                if constexpr (VH == 0)
+                    out[o] = v;
+                else
+                {
+                    acc_lo[o] += v & 0x00ff00ffu;
+                    acc_hi[o] += (v >> 8) & 0x00ff00ffu;
+                }
             }
-            *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
         }
+
+        if constexpr (VH > 0)
+        {
+#pragma unroll
+            for (int o = 0; o < 4; o++)
+                out[o] = ((acc_lo[o] >> VH) & 0x00ff00ffu) | (((acc_hi[o] >> VH) & 0x00ff00ffu) << 8);
+        }
+
+#pragma unroll
+        for (int o = 0; o < 4; o++)
+        {
+            uint32_t v = out[o];
+            if constexpr (PACK == 1)
+                v = half_unpremul<false> (v, sm_inv);
+            else if constexpr (PACK == 2)
+                v = half_unpremul<true> (v, sm_inv);
+            out[o] = __byte_perm (v, 0, P.prmt_sel);
+        }
+        *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
+    }
+    else
+    {
+        /* ragged end of a row: one pixel at a time, same arithmetic */
+        for (uint32_t o = 0; o < n_px; o++)
+        {
+            uint32_t acc_lo = 0, acc_hi = 0, res = 0;
+
+            for (int kv = 0; kv < (1 << VH); kv++)
+            {
+                const uint32_t r = 2 * ((y << VH) + kv);
+                const uint32_t *row0 = reinterpret_cast<const uint32_t *> (src + (size_t) r * P.src_pitch)
+                                       + (size_t) (x + o) * SRC_PER_OUT;
+                const uint32_t *row1 = reinterpret_cast<const uint32_t *> (src + (size_t) (r + 1) * P.src_pitch)
+                                       + (size_t) (x + o) * SRC_PER_OUT;
+                uint32_t pa[SRC_PER_OUT], pb[SRC_PER_OUT];
+#pragma unroll
+                for (int k = 0; k < SRC_PER_OUT; k++)
+                {
+                    pa[k] = __ldg (row0 + k);
+                    pb[k] = __ldg (row1 + k);
+                }
+                const uint32_t v = byte_avg_floor (half_hreduce<HH> (pa), half_hreduce<HH> (pb));
+                if (VH == 0)
+                    res = v;
+                else
+                {
+                    acc_lo += v & 0x00ff00ffu;
+                    acc_hi += (v >> 8) & 0x00ff00ffu;
+                }
+            }
+            if (VH > 0)
+                res = ((acc_lo >> VH) & 0x00ff00ffu) | (((acc_hi >> VH) & 0x00ff00ffu) << 8);
+            if constexpr (PACK == 1)
+                res = half_unpremul<false> (res, sm_inv);
+            else if constexpr (PACK == 2)
+                res = half_unpremul<true> (res, sm_inv);
+            reinterpret_cast<uint32_t *> (dst)[o] = __byte_perm (res, 0, P.prmt_sel);
+        }
+    }
+}
+
+/* Variant for 4:1 and 8:1 horizontal reductions (HH = 1, 2).  Here one output pixel spans 16 or
+ * 32 source bytes per row, so the thread <-> data mapping is chosen for the loads: lane L of a
+ * warp reads the L-th 16-byte chunk of the row segment (perfectly coalesced 512 bytes per
+ * instruction, all 2 << VH source rows in flight at once).  With HH = 1 a chunk is exactly one
+ * output pixel; with HH = 2 two neighbouring lanes hold the two halves of an output pixel and
+ * add their partial sums with one shuffle per word. */
+template <int HH, int VH, int PACK>
+__global__ void __launch_bounds__ (256)
+smol_half_wide_kernel (const HalfParams P)
+{
+    static_assert (HH == 1 || HH == 2, "wide variant is for 4:1 and 8:1");
+    __shared__ uint32_t sm_inv[256];
+
+    pdl_launch_dependents ();
+    if constexpr (PACK != 0)
+    {
+        for (uint32_t i = threadIdx.y * blockDim.x + threadIdx.x; i < 256; i += blockDim.x * blockDim.y)
+            sm_inv[i] = __ldg (&P.inv_div_p8[i]) << 3;
+        __syncthreads ();
+    }
+    pdl_wait ();
+
+    constexpr int N_ROWS = 2 << VH;
+    const uint32_t cx = blockIdx.x * blockDim.x + threadIdx.x;      /* 16-byte chunk within the row */
+    const uint32_t yl = blockIdx.y * blockDim.y + threadIdx.y;
+    const uint32_t n_chunks = P.w_out << (HH - 1);
+    const bool live = cx < n_chunks && yl < P.n_rows;               /* dead lanes still shuffle */
+    const uint32_t y = P.first_row + yl;
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride
+                         + (size_t) (y << (VH + 1)) * P.src_pitch + (size_t) cx * 16;
+
+    uint4 rows[N_ROWS];
+#pragma unroll
+    for (int r = 0; r < N_ROWS; r++)
+        rows[r] = live ? ldg_nc_v4 (src + (size_t) r * P.src_pitch) : make_uint4 (0, 0, 0, 0);
+
+    uint32_t acc_lo = 0, acc_hi = 0, res = 0;
+#pragma unroll
+    for (int kv = 0; kv < (1 << VH); kv++)
+    {
+        uint32_t h[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+        {
+            const uint4 q = rows[2 * kv + t];
+            const uint32_t v0 = byte_avg_floor (q.x, q.y), v1 = byte_avg_floor (q.z, q.w);
+            uint32_t lo = (v0 & 0x00ff00ffu) + (v1 & 0x00ff00ffu);
+            uint32_t hi = ((v0 >> 8) & 0x00ff00ffu) + ((v1 >> 8) & 0x00ff00ffu);
+            if constexpr (HH == 2)
+            {
+                lo += __shfl_xor_sync (0xffffffffu, lo, 1);
+                hi += __shfl_xor_sync (0xffffffffu, hi, 1);
+            }
+            h[t] = ((lo >> HH) & 0x00ff00ffu) | (((hi >> HH) & 0x00ff00ffu) << 8);
+        }
+        const uint32_t v = byte_avg_floor (h[0], h[1]);
+        if constexpr (VH == 0)
+            res = v;
         else
         {
-            /* ragged end of a row: one pixel at a time, same arithmetic */
-            for (uint32_t o = 0; o < n_px; o++)
-            {
-                uint32_t acc_lo = 0, acc_hi = 0, res = 0;
-
-                for (int kv = 0; kv < (1 << VH); kv++)
-                {
-                    const uint32_t r = 2 * ((y << VH) + kv);
-                    const uint32_t *row0 = reinterpret_cast<const uint32_t *> (src + (size_t) r * P.src_pitch)
-                                           + (size_t) (x + o) * SRC_PER_OUT;
-                    const uint32_t *row1 = reinterpret_cast<const uint32_t *> (src + (size_t) (r + 1) * P.src_pitch)
-                                           + (size_t) (x + o) * SRC_PER_OUT;
-                    uint32_t pa[SRC_PER_OUT], pb[SRC_PER_OUT];
-#pragma unroll
-                    for (int k = 0; k < SRC_PER_OUT; k++)
-                    {
-                        pa[k] = __ldg (row0 + k);
-                        pb[k] = __ldg (row1 + k);
-                    }
-                    const uint32_t v = byte_avg_floor (half_hreduce<HH> (pa), half_hreduce<HH> (pb));
-                    if (VH == 0)
-                        res = v;
-                    else
-                    {
-                        acc_lo += v & 0x00ff00ffu;
-                        acc_hi += (v >> 8) & 0x00ff00ffu;
-                    }
-                }
-                if (VH > 0)
-                    res = ((acc_lo >> VH) & 0x00ff00ffu) | (((acc_hi >> VH) & 0x00ff00ffu) << 8);
-                if constexpr (UNPREMUL)
-                    res = half_unpremul (res, P, sm_inv);
-                reinterpret_cast<uint32_t *> (dst)[o] = __byte_perm (res, 0, P.prmt_sel);
-            }
+            acc_lo += v & 0x00ff00ffu;
+            acc_hi += (v >> 8) & 0x00ff00ffu;
         }
+    }
+    if constexpr (VH > 0)
+        res = ((acc_lo >> VH) & 0x00ff00ffu) | (((acc_hi >> VH) & 0x00ff00ffu) << 8);
+
+    if constexpr (PACK == 1)
+        res = half_unpremul<false> (res, sm_inv);
+    else if constexpr (PACK == 2)
+        res = half_unpremul<true> (res, sm_inv);
+    res = __byte_perm (res, 0, P.prmt_sel);
+
+    if (live && (HH == 1 || (cx & 1) == 0))
+    {
+        const uint32_t x = HH == 1 ? cx : cx >> 1;
+        uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl * P.dst_pitch;
+        reinterpret_cast<uint32_t *> (dst)[x] = res;
     }
 }
 
@@ -815,15 +930,46 @@ num_sms ()
     return g_num_sms;
 }
 
+/* Launch with programmatic stream serialization allowed (see pdl_wait). */
+template <typename Kernel, typename Params>
+static cudaError_t
+launch_pdl (Kernel kernel, const Params &P, dim3 grid, dim3 block, size_t smem, cudaStream_t stream)
+{
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr;
+
+    memset (&cfg, 0, sizeof (cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx (&cfg, kernel, P);
+}
+
 template <int HH, int VH>
 static cudaError_t
-launch_half_hv (const HalfParams &P, bool unpremul, dim3 grid, cudaStream_t stream)
+launch_half_hv (const HalfParams &P, int pack, dim3 grid, dim3 block, cudaStream_t stream)
 {
-    if (unpremul)
-        smol_half_kernel<HH, VH, true><<<grid, 256, 0, stream>>> (P);
+    if constexpr (HH == 0)
+    {
+        if (pack == 1)
+            return launch_pdl (smol_half_kernel<HH, VH, 1>, P, grid, block, 0, stream);
+        if (pack == 2)
+            return launch_pdl (smol_half_kernel<HH, VH, 2>, P, grid, block, 0, stream);
+        return launch_pdl (smol_half_kernel<HH, VH, 0>, P, grid, block, 0, stream);
+    }
     else
-        smol_half_kernel<HH, VH, false><<<grid, 256, 0, stream>>> (P);
-    return cudaGetLastError ();
+    {
+        if (pack == 1)
+            return launch_pdl (smol_half_wide_kernel<HH, VH, 1>, P, grid, block, 0, stream);
+        if (pack == 2)
+            return launch_pdl (smol_half_wide_kernel<HH, VH, 2>, P, grid, block, 0, stream);
+        return launch_pdl (smol_half_wide_kernel<HH, VH, 0>, P, grid, block, 0, stream);
+    }
 }
 
 static cudaError_t
@@ -836,10 +982,8 @@ launch_half (const SmolLaunch &L, cudaStream_t stream)
     P.src = L.src; P.dst = L.dst;
     P.src_pitch = L.src_pitch; P.dst_pitch = L.dst_pitch;
     P.src_image_stride = L.src_image_stride; P.dst_image_stride = L.dst_image_stride;
-    P.w_out = d.w_out; P.first_row = L.first_row; P.n_rows = L.n_rows; P.n_images = L.n_images;
+    P.w_out = d.w_out; P.first_row = L.first_row; P.n_rows = L.n_rows;
     P.items_per_row = (d.w_out + 3) / 4;
-    P.alpha_shift = (d.in_alpha_idx == 0xff ? 0 : d.in_alpha_idx) * 8;
-    P.col_shift = d.in_col0 * 8;
     P.inv_div_p8 = L.luts->inv_div_p8;
 
     /* destination byte j takes source byte perm[j] */
@@ -857,25 +1001,39 @@ launch_half (const SmolLaunch &L, cudaStream_t stream)
     }
     P.prmt_sel = sel;
 
-    const uint64_t n_items = (uint64_t) P.items_per_row * L.n_rows * L.n_images;
-    uint64_t blocks = (n_items + 255) / 256;
-    const uint64_t cap = (uint64_t) num_sms () * 8 * 4;   /* a few waves of resident CTAs, grid-stride beyond */
-    if (blocks > cap)
-        blocks = cap;
-    dim3 grid ((unsigned) blocks);
-    const bool unpremul = d.out_unassoc;
+    /* threads along x: HH = 0: one per 4 output pixels; HH = 1, 2: one per 16-byte source chunk */
+    const uint32_t n_x = d.h_halvings == 0 ? P.items_per_row : d.w_out << (d.h_halvings - 1);
+
+    /* Block shape: bx threads along x (a multiple of 32 that wastes the fewest lanes on the
+     * row's ragged end), by rows, about 256 threads in all. */
+    uint32_t bx = 32, best_waste = 0xffffffffu;
+    for (uint32_t cand = 256; cand >= 32; cand -= 32)
+    {
+        const uint32_t waste = (n_x + cand - 1) / cand * cand - n_x;
+        if (waste < best_waste)
+        {
+            best_waste = waste;
+            bx = cand;
+        }
+    }
+    uint32_t by = 256 / bx;
+    if (by > L.n_rows)
+        by = L.n_rows;
+    dim3 block (bx, by);
+    dim3 grid ((n_x + bx - 1) / bx, (L.n_rows + by - 1) / by, L.n_images);
+    const int pack = d.out_unassoc ? (d.in_alpha_idx == 0 ? 2 : 1) : 0;
 
     switch (d.h_halvings * 3 + d.v_halvings)
     {
-        case 0: return launch_half_hv<0, 0> (P, unpremul, grid, stream);
-        case 1: return launch_half_hv<0, 1> (P, unpremul, grid, stream);
-        case 2: return launch_half_hv<0, 2> (P, unpremul, grid, stream);
-        case 3: return launch_half_hv<1, 0> (P, unpremul, grid, stream);
-        case 4: return launch_half_hv<1, 1> (P, unpremul, grid, stream);
-        case 5: return launch_half_hv<1, 2> (P, unpremul, grid, stream);
-        case 6: return launch_half_hv<2, 0> (P, unpremul, grid, stream);
-        case 7: return launch_half_hv<2, 1> (P, unpremul, grid, stream);
-        default: return launch_half_hv<2, 2> (P, unpremul, grid, stream);
+        case 0: return launch_half_hv<0, 0> (P, pack, grid, block, stream);
+        case 1: return launch_half_hv<0, 1> (P, pack, grid, block, stream);
+        case 2: return launch_half_hv<0, 2> (P, pack, grid, block, stream);
+        case 3: return launch_half_hv<1, 0> (P, pack, grid, block, stream);
+        case 4: return launch_half_hv<1, 1> (P, pack, grid, block, stream);
+        case 5: return launch_half_hv<1, 2> (P, pack, grid, block, stream);
+        case 6: return launch_half_hv<2, 0> (P, pack, grid, block, stream);
+        case 7: return launch_half_hv<2, 1> (P, pack, grid, block, stream);
+        default: return launch_half_hv<2, 2> (P, pack, grid, block, stream);
     }
 }
 
