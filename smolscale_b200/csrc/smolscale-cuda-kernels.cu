@@ -863,6 +863,226 @@ smol_half_wide_kernel (const HalfParams P)
 }
 
 /* ------------------------------------------------------------------------------------------ *
+ * "taps" kernel: bilinear (any weights) / copy / one on both axes, 8-bit premultiplied          *
+ * intermediate (reference 64bpp storage).  Registers only, no shared-memory staging.           *
+ *                                                                                              *
+ * A pixel is two 32-bit words of two 16-bit lanes each (bytes 0, 2 and bytes 1, 3 of the        *
+ * packed source pixel), so one weighted tap is two multiply-adds per word:                      *
+ *     ((p * F + q * (256 - F)) >> 8) & 0x00ff00ff                                               *
+ * A thread owns four adjacent output columns and walks a strip of output rows top to bottom,    *
+ * keeping the last two horizontally filtered source rows in registers -- the device analogue    *
+ * of the reference's two-row SmolVerticalCtx cache (generic:1648-1682) -- so that on upscales   *
+ * each source row is unpacked and filtered once per strip, not once per output row.            *
+ * ------------------------------------------------------------------------------------------ */
+
+struct TapsParams
+{
+    const uint8_t *src; uint8_t *dst;
+    uint32_t src_pitch, dst_pitch;
+    size_t src_image_stride, dst_image_stride;
+    const uint32_t *tab_x, *tab_y;
+    const uint32_t *inv_div_p8;
+    uint32_t w_in, h_in, w_out;
+    uint32_t first_row, n_rows;
+    uint32_t rows_per_thread;
+    uint32_t bpp_in, bpp_out;
+    uint32_t in_alpha_shift;        /* 8 * byte index of alpha in the source pixel (24bpp: 24, byte forced to 0xff) */
+    uint32_t in_unassoc, out_unassoc;
+    uint32_t prmt_sel;              /* source byte order -> destination byte order */
+};
+
+struct Px16 { uint32_t a, b; };     /* a: bytes 0 and 2, b: bytes 1 and 3, one per 16-bit lane */
+
+__device__ __forceinline__ Px16 taps_unpack (uint32_t raw, const TapsParams &P)
+{
+    Px16 r;
+    r.a = raw & 0x00ff00ffu;
+    r.b = (raw >> 8) & 0x00ff00ffu;
+    if (P.in_unassoc)
+    {
+        /* premultiply the colour lanes: ((c + 1) * (alpha + 1) - 1) >> 8 (generic:238-244); the
+         * alpha lane is cleared first and re-inserted afterwards, as the reference does */
+        const uint32_t alpha = (raw >> P.in_alpha_shift) & 0xff;
+        const uint32_t m = alpha + 1;
+        if (P.in_alpha_shift == 24)
+        {
+            r.b &= 0x000000ffu;
+            r.a = (((r.a + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff00ffu;
+            r.b = ((((r.b + 0x00010001u) * m - 0x00010001u) >> 8) & 0x000000ffu) | (alpha << 16);
+        }
+        else
+        {
+            r.a &= 0x00ff0000u;
+            r.a = ((((r.a + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff0000u) | alpha;
+            r.b = (((r.b + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff00ffu;
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ uint32_t taps_load (const uint8_t *row, uint32_t x, const TapsParams &P)
+{
+    const uint8_t *p = row + (size_t) x * P.bpp_in;
+    if (P.bpp_in == 4)
+    {
+        if ((reinterpret_cast<uintptr_t> (p) & 3) == 0)
+            return __ldg (reinterpret_cast<const uint32_t *> (p));
+        return (uint32_t) __ldg (p) | ((uint32_t) __ldg (p + 1) << 8) | ((uint32_t) __ldg (p + 2) << 16)
+               | ((uint32_t) __ldg (p + 3) << 24);
+    }
+    return (uint32_t) __ldg (p) | ((uint32_t) __ldg (p + 1) << 8) | ((uint32_t) __ldg (p + 2) << 16) | 0xff000000u;
+}
+
+__device__ __forceinline__ uint32_t lerp16 (uint32_t p, uint32_t q, uint32_t F)
+{
+    return ((p * F + q * (256u - F)) >> 8) & 0x00ff00ffu;
+}
+
+/* Horizontally filtered values of the thread's four output columns on source row r. */
+template <int HH>
+__device__ __forceinline__ void taps_hrow (const TapsParams &P, const uint8_t *src, uint32_t r, uint32_t x, Px16 out[4])
+{
+    const uint8_t *row = src + (size_t) r * P.src_pitch;
+#pragma unroll
+    for (int o = 0; o < 4; o++)
+    {
+        const uint32_t xo = min (x + o, P.w_out - 1);
+        uint32_t acc_a = 0, acc_b = 0;
+#pragma unroll
+        for (int k = 0; k < (1 << HH); k++)
+        {
+            const uint32_t e = __ldg (&P.tab_x[(xo << HH) + k]);
+            const uint32_t ofs = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e);
+            const Px16 p = taps_unpack (taps_load (row, ofs, P), P);
+            const Px16 q = taps_unpack (taps_load (row, min (ofs + 1, P.w_in - 1), P), P);
+            acc_a += lerp16 (p.a, q.a, F);
+            acc_b += lerp16 (p.b, q.b, F);
+        }
+        out[o].a = (acc_a >> HH) & 0x00ff00ffu;
+        out[o].b = (acc_b >> HH) & 0x00ff00ffu;
+    }
+}
+
+template <int HH, int VH>
+__global__ void __launch_bounds__ (256)
+smol_taps_kernel (const TapsParams P)
+{
+    __shared__ uint32_t sm_inv[256];
+
+    pdl_launch_dependents ();
+    if (P.out_unassoc)
+    {
+        for (uint32_t i = threadIdx.y * blockDim.x + threadIdx.x; i < 256; i += blockDim.x * blockDim.y)
+            sm_inv[i] = __ldg (&P.inv_div_p8[i]) << 3;
+        __syncthreads ();
+    }
+    pdl_wait ();
+
+    const uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const uint32_t strip = blockIdx.y * blockDim.y + threadIdx.y;
+    const uint32_t yl0 = strip * P.rows_per_thread;
+    if (x >= P.w_out || yl0 >= P.n_rows)
+        return;
+    const uint32_t yl1 = min (yl0 + P.rows_per_thread, P.n_rows);
+    const uint32_t n_px = min (4u, P.w_out - x);
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
+    uint8_t *dst_img = P.dst + (size_t) blockIdx.z * P.dst_image_stride;
+
+    uint32_t idx0 = 0xffffffffu, idx1 = 0xffffffffu;
+    Px16 row0[4], row1[4];
+#pragma unroll
+    for (int o = 0; o < 4; o++)
+        row0[o].a = row0[o].b = row1[o].a = row1[o].b = 0;
+
+    for (uint32_t yl = yl0; yl < yl1; yl++)
+    {
+        const uint32_t y = P.first_row + yl;
+        uint32_t acc_a[4] = { 0, 0, 0, 0 }, acc_b[4] = { 0, 0, 0, 0 };
+
+#pragma unroll
+        for (int kv = 0; kv < (1 << VH); kv++)
+        {
+            const uint32_t e = __ldg (&P.tab_y[(y << VH) + kv]);
+            const uint32_t r0 = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e);
+            const uint32_t r1 = min (r0 + 1, P.h_in - 1);
+
+            if (F != 0)
+            {
+                if (r0 == idx1)
+                {
+#pragma unroll
+                    for (int o = 0; o < 4; o++)
+                    {
+                        const Px16 t = row0[o]; row0[o] = row1[o]; row1[o] = t;
+                    }
+                    const uint32_t ti = idx0; idx0 = idx1; idx1 = ti;
+                }
+                else if (r0 != idx0)
+                {
+                    taps_hrow<HH> (P, src, r0, x, row0);
+                    idx0 = r0;
+                }
+            }
+            if (F != 256 && r1 != idx1)
+            {
+                if (r1 == idx0)
+                {
+#pragma unroll
+                    for (int o = 0; o < 4; o++)
+                        row1[o] = row0[o];
+                }
+                else
+                    taps_hrow<HH> (P, src, r1, x, row1);
+                idx1 = r1;
+            }
+#pragma unroll
+            for (int o = 0; o < 4; o++)
+            {
+                /* F == 256 / F == 0 select one row exactly; the unused operand is multiplied by 0 */
+                const uint32_t pa = F != 0 ? row0[o].a : 0, pb = F != 0 ? row0[o].b : 0;
+                const uint32_t qa = F != 256 ? row1[o].a : 0, qb = F != 256 ? row1[o].b : 0;
+                acc_a[o] += lerp16 (pa, qa, F);
+                acc_b[o] += lerp16 (pb, qb, F);
+            }
+        }
+
+        uint32_t out[4];
+#pragma unroll
+        for (int o = 0; o < 4; o++)
+        {
+            const uint32_t a = (acc_a[o] >> VH) & 0x00ff00ffu, b = (acc_b[o] >> VH) & 0x00ff00ffu;
+            uint32_t v = a | (b << 8);
+            if (P.out_unassoc)
+                v = (P.in_alpha_shift == 0) ? half_unpremul<true> (v, sm_inv) : half_unpremul<false> (v, sm_inv);
+            out[o] = __byte_perm (v, 0, P.prmt_sel);
+        }
+
+        uint8_t *dst = dst_img + (size_t) yl * P.dst_pitch + (size_t) x * P.bpp_out;
+        if (P.bpp_out == 4)
+        {
+            if (n_px == 4 && (reinterpret_cast<uintptr_t> (dst) & 15) == 0)
+                *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
+            else
+                for (uint32_t o = 0; o < n_px; o++)
+                    store_raw_px (dst + 4 * o, out[o], 4);
+        }
+        else
+        {
+            if (n_px == 4 && (reinterpret_cast<uintptr_t> (dst) & 3) == 0)
+            {
+                uint32_t *d32 = reinterpret_cast<uint32_t *> (dst);
+                d32[0] = (out[0] & 0x00ffffffu) | (out[1] << 24);
+                d32[1] = ((out[1] >> 8) & 0x0000ffffu) | (out[2] << 16);
+                d32[2] = ((out[2] >> 16) & 0x000000ffu) | (out[3] << 8);
+            }
+            else
+                for (uint32_t o = 0; o < n_px; o++)
+                    store_raw_px (dst + 3 * o, out[o], 3);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ *
  * Host-side dispatch                                                                         *
  * ------------------------------------------------------------------------------------------ */
 
@@ -899,19 +1119,33 @@ half_eligible (const SmolLaunch &L)
            && (L.src_image_stride & 15) == 0 && (L.dst_image_stride & 15) == 0;
 }
 
+static bool
+taps_eligible (const SmolLaunch &L)
+{
+    const SmolJobDesc &d = L.d;
+
+    return d.h_kind == SMOL_AXIS_TAPS && d.v_kind == SMOL_AXIS_TAPS
+           && d.mid == SMOL_MID_P8 && !d.storage128;
+}
+
 extern "C" int
 smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
 {
     const bool half_ok = half_eligible (*launch);
+    const bool taps_ok = taps_eligible (*launch);
 
     if (forced == SMOL_KERNEL_GENERAL)
         return SMOL_KERNEL_GENERAL;
-    if (forced == SMOL_KERNEL_HALF2X && half_ok)
-        return SMOL_KERNEL_HALF2X;
-    if (forced > SMOL_KERNEL_AUTO && forced < SMOL_KERNEL_MAX && forced != SMOL_KERNEL_HALF2X)
+    if (forced == SMOL_KERNEL_HALF2X)
+        return half_ok ? SMOL_KERNEL_HALF2X : SMOL_KERNEL_GENERAL;
+    if (forced == SMOL_KERNEL_TAPS_DIRECT)
+        return taps_ok ? SMOL_KERNEL_TAPS_DIRECT : SMOL_KERNEL_GENERAL;
+    if (forced > SMOL_KERNEL_AUTO && forced < SMOL_KERNEL_MAX)
         return SMOL_KERNEL_GENERAL;
     if (half_ok)
         return SMOL_KERNEL_HALF2X;
+    if (taps_ok)
+        return SMOL_KERNEL_TAPS_DIRECT;
     return SMOL_KERNEL_GENERAL;
 }
 
@@ -1037,6 +1271,89 @@ launch_half (const SmolLaunch &L, cudaStream_t stream)
     }
 }
 
+/* destination byte j takes source byte perm[j] (PRMT selector); 24bpp sources carry a forced
+ * 0xff in byte 3, 24bpp destinations take their three colour bytes into bytes 0..2 */
+static uint32_t
+byte_order_selector (const SmolJobDesc &d)
+{
+    const uint32_t in_alpha = d.in_alpha_idx == 0xff ? 3 : d.in_alpha_idx;
+    uint32_t sel = 0;
+
+    for (int j = 0; j < 4; j++)
+    {
+        uint32_t from;
+        if (d.out_alpha_idx != 0xff && j == d.out_alpha_idx)
+            from = in_alpha;
+        else
+        {
+            const int i = j - d.out_col0;
+            if (i < 0 || i > 2)
+                from = in_alpha;        /* unused top byte of a 24bpp destination */
+            else
+                from = d.in_col0 + (d.swap_rb ? 2 - i : i);
+        }
+        sel |= from << (4 * j);
+    }
+    return sel;
+}
+
+template <int HH>
+static cudaError_t
+launch_taps_h (const TapsParams &P, uint32_t vh, dim3 grid, dim3 block, cudaStream_t stream)
+{
+    if (vh == 0)
+        return launch_pdl (smol_taps_kernel<HH, 0>, P, grid, block, 0, stream);
+    if (vh == 1)
+        return launch_pdl (smol_taps_kernel<HH, 1>, P, grid, block, 0, stream);
+    return launch_pdl (smol_taps_kernel<HH, 2>, P, grid, block, 0, stream);
+}
+
+static cudaError_t
+launch_taps (const SmolLaunch &L, cudaStream_t stream)
+{
+    const SmolJobDesc &d = L.d;
+    TapsParams P;
+
+    P.src = L.src; P.dst = L.dst;
+    P.src_pitch = L.src_pitch; P.dst_pitch = L.dst_pitch;
+    P.src_image_stride = L.src_image_stride; P.dst_image_stride = L.dst_image_stride;
+    P.tab_x = L.tab_x; P.tab_y = L.tab_y;
+    P.inv_div_p8 = L.luts->inv_div_p8;
+    P.w_in = d.w_in; P.h_in = d.h_in; P.w_out = d.w_out;
+    P.first_row = L.first_row; P.n_rows = L.n_rows;
+    P.bpp_in = d.bpp_in; P.bpp_out = d.bpp_out;
+    P.in_alpha_shift = (d.in_alpha_idx == 0xff ? 3 : d.in_alpha_idx) * 8;
+    P.in_unassoc = d.in_unassoc; P.out_unassoc = d.out_unassoc;
+    P.prmt_sel = byte_order_selector (d);
+
+    /* strip height: long strips amortise the two-row cache (essential on upscales) but leave
+     * fewer threads; keep at least ~2 resident waves of threads on the GPU */
+    const uint64_t x_threads = (d.w_out + 3) / 4;
+    const uint64_t want_threads = (uint64_t) num_sms () * 2048 * 2;
+    uint32_t rpt = 16;
+    while (rpt > 1 && x_threads * ((L.n_rows + rpt - 1) / rpt) * L.n_images < want_threads)
+        rpt >>= 1;
+    if (d.h_in <= d.h_out && rpt < 4)
+        rpt = 4;                        /* magnification: row reuse matters more than thread count */
+    P.rows_per_thread = rpt;
+
+    uint32_t bx = 32;
+    while (bx < 128 && bx < x_threads)
+        bx *= 2;
+    const uint32_t strips = (L.n_rows + rpt - 1) / rpt;
+    uint32_t by = 256 / bx;
+    if (by > strips)
+        by = strips;
+    dim3 block (bx, by);
+    dim3 grid ((unsigned) ((x_threads + bx - 1) / bx), (strips + by - 1) / by, L.n_images);
+
+    if (d.h_halvings == 0)
+        return launch_taps_h<0> (P, d.v_halvings, grid, block, stream);
+    if (d.h_halvings == 1)
+        return launch_taps_h<1> (P, d.v_halvings, grid, block, stream);
+    return launch_taps_h<2> (P, d.v_halvings, grid, block, stream);
+}
+
 template <bool S128, bool HBOX, bool VBOX>
 static cudaError_t
 launch_general (const SmolLaunch &L, cudaStream_t stream)
@@ -1101,6 +1418,10 @@ smol_cuda_launch (const SmolLaunch *launch, int kernel_id, void *stream_p, const
 
     if (kernel_id == SMOL_KERNEL_HALF2X && half_eligible (L))
         return (int) launch_half (L, stream);
+    if (kernel_id == SMOL_KERNEL_TAPS_DIRECT && taps_eligible (L))
+        return (int) launch_taps (L, stream);
+    if (name_out)
+        *name_out = kernel_names[SMOL_KERNEL_GENERAL];
 
     shape_general (L);
 

@@ -43,13 +43,20 @@ def test_golden_digests(sb):
     assert not bad, "CUDA output differs from the reference digests: %s" % bad[:10]
 
 
-def test_random_matrix_vs_oracle(sb, restatement):
-    for idx, job in enumerate(cases.job_matrix(4242, 600)):
-        ti, wi, hi, si, to, wo, ho, so, srgb, mode = job
-        src = cases.make_image(ti, wi, hi, si, mode, seed=idx)
-        want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
-        got = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, srgb)
-        assert np.array_equal(got, want), (job, describe(got, want))
+@pytest.mark.parametrize("forced", [0, 1, 2], ids=["auto", "general", "taps"])
+def test_random_matrix_vs_oracle(sb, restatement, forced):
+    """forced = 0: the dispatcher's choice; 1: everything through the general kernel;
+    2: the direct taps kernel wherever it is eligible (general elsewhere)."""
+    sb.force_kernel(forced)
+    try:
+        for idx, job in enumerate(cases.job_matrix(4242, 600)):
+            ti, wi, hi, si, to, wo, ho, so, srgb, mode = job
+            src = cases.make_image(ti, wi, hi, si, mode, seed=idx)
+            want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
+            got = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, srgb)
+            assert np.array_equal(got, want), (job, describe(got, want))
+    finally:
+        sb.force_kernel(0)
 
 
 def test_half_kernel_family(sb, restatement):
@@ -63,7 +70,7 @@ def test_half_kernel_family(sb, restatement):
         want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
         p = sb.plan_query(ti, wi, hi, to, wo, ho, srgb)
         n_fast += p["kernel_name"] == "half2x"
-        for forced in (0, 1):
+        for forced in (0, 1, 2):
             sb.force_kernel(forced)
             try:
                 got = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, srgb)
