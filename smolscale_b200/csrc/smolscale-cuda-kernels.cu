@@ -1083,12 +1083,208 @@ smol_taps_kernel (const TapsParams P)
 }
 
 /* ------------------------------------------------------------------------------------------ *
+ * "mag" kernel: vertical magnification (h_out > h_in; BASELINE config 4), bilinear / copy / one *
+ * horizontally, 8-bit premultiplied intermediate.                                              *
+ *                                                                                              *
+ * On an upscale every source row feeds several output rows and every source pixel several      *
+ * output columns, so the work is split in two phases per CTA tile (TW output columns x TH       *
+ * output rows) with the intermediate kept in shared memory, never in HBM:                      *
+ *   1. the few source rows the tile needs are staged (coalesced), unpacked once per source     *
+ *      pixel into 16-bit lanes, and filtered horizontally once per (source row, output column) *
+ *      into sm_h;                                                                              *
+ *   2. every thread then produces groups of four adjacent output pixels of one output row:      *
+ *      two 128-bit shared-memory reads per source row, four multiply-adds per pixel, one PRMT   *
+ *      that does shift + mask + byte interleave + channel reorder at once, vector store.        *
+ * ------------------------------------------------------------------------------------------ */
+
+struct MagParams
+{
+    TapsParams t;
+    uint32_t tile_w, tile_h;        /* output tile; tile_w is a multiple of 4 */
+    uint32_t max_src_cols;          /* bound on source columns per tile (smem row pitch of sm_u, in pixels) */
+    uint32_t max_src_rows;          /* bound on source rows per tile */
+    uint32_t acc_prmt_sel;          /* (acc_a, acc_b) high bytes -> destination byte order */
+};
+
+template <int HH>
+__global__ void __launch_bounds__ (256)
+smol_mag_kernel (const MagParams M)
+{
+    extern __shared__ __align__ (16) uint8_t sm_dyn[];
+    __shared__ uint32_t sm_inv[256];
+    const TapsParams &P = M.t;
+
+    pdl_launch_dependents ();
+    if (P.out_unassoc)
+    {
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
+            sm_inv[i] = __ldg (&P.inv_div_p8[i]) << 3;
+    }
+
+    const uint32_t x0 = blockIdx.x * M.tile_w;
+    const uint32_t x1 = min (x0 + M.tile_w, P.w_out);              /* exclusive */
+    const uint32_t yl0 = blockIdx.y * M.tile_h;
+    const uint32_t yl1 = min (yl0 + M.tile_h, P.n_rows);
+    const uint32_t tw = x1 - x0;
+
+    /* source window of the tile (tables are library-owned: readable before the dependency wait) */
+    const uint32_t c_lo = SMOL_TAB_OFS (__ldg (&P.tab_x[x0 << HH]));
+    const uint32_t c_hi = min (SMOL_TAB_OFS (__ldg (&P.tab_x[(x1 << HH) - 1])) + 1, P.w_in - 1);
+    const uint32_t r_lo = SMOL_TAB_OFS (__ldg (&P.tab_y[P.first_row + yl0]));
+    const uint32_t r_hi = min (SMOL_TAB_OFS (__ldg (&P.tab_y[P.first_row + yl1 - 1])) + 1, P.h_in - 1);
+    const uint32_t n_cols = c_hi - c_lo + 1, n_rows = r_hi - r_lo + 1;
+
+    /* shared memory carve-up */
+    const uint32_t raw_pitch = (M.max_src_cols * P.bpp_in + 16 + 15) & ~15u;
+    uint8_t *sm_raw = sm_dyn;                                                   /* one staged source row */
+    uint2 *sm_u = reinterpret_cast<uint2 *> (sm_dyn + raw_pitch);               /* [n_rows][max_src_cols] unpacked */
+    uint2 *sm_h = sm_u + (size_t) M.max_src_rows * M.max_src_cols;              /* [n_rows][tile_w] h-filtered */
+
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
+    uint8_t *dst_img = P.dst + (size_t) blockIdx.z * P.dst_image_stride;
+
+    pdl_wait ();
+
+    /* phase 1a: stage + unpack the source window */
+    for (uint32_t r = 0; r < n_rows; r++)
+    {
+        const uint8_t *gbeg = src + (size_t) (r_lo + r) * P.src_pitch + (size_t) c_lo * P.bpp_in;
+        const uint8_t *gend = gbeg + (size_t) n_cols * P.bpp_in;
+        const uint32_t sm_ofs = (uint32_t) (reinterpret_cast<uintptr_t> (gbeg) & 15);
+
+        __syncthreads ();
+        stage_bytes (sm_raw, gbeg, gend);
+        __syncthreads ();
+        for (uint32_t c = threadIdx.x; c < n_cols; c += blockDim.x)
+        {
+            const uint8_t *p = sm_raw + sm_ofs + (size_t) c * P.bpp_in;
+            uint32_t raw;
+            if (P.bpp_in == 4)
+                raw = (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
+            else
+                raw = (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | 0xff000000u;
+            const Px16 u = taps_unpack (raw, P);
+            sm_u[(size_t) r * M.max_src_cols + c] = make_uint2 (u.a, u.b);
+        }
+    }
+    __syncthreads ();
+
+    /* phase 1b: horizontal filter, once per (source row, output column).  Thread -> column is
+     * fixed (tw <= blockDim), so the tap entries are read once and rows are strided. */
+    {
+        const uint32_t xl = threadIdx.x % tw, r_step = blockDim.x / tw;
+        uint32_t ofs_p[1 << HH], ofs_q[1 << HH], Fk[1 << HH];
+#pragma unroll
+        for (int k = 0; k < (1 << HH); k++)
+        {
+            const uint32_t e = __ldg (&P.tab_x[((x0 + xl) << HH) + k]);
+            ofs_p[k] = SMOL_TAB_OFS (e) - c_lo;
+            ofs_q[k] = min (SMOL_TAB_OFS (e) + 1, P.w_in - 1) - c_lo;
+            Fk[k] = SMOL_TAB_F (e);
+        }
+        for (uint32_t r = threadIdx.x / tw; r < n_rows && r_step > 0; r += r_step)
+        {
+        uint32_t acc_a = 0, acc_b = 0;
+#pragma unroll
+        for (int k = 0; k < (1 << HH); k++)
+        {
+            const uint32_t F = Fk[k];
+            const uint2 p = sm_u[(size_t) r * M.max_src_cols + ofs_p[k]];
+            const uint2 q = sm_u[(size_t) r * M.max_src_cols + ofs_q[k]];
+            if constexpr (HH == 0)
+            {
+                acc_a = p.x * F + q.x * (256u - F);
+                acc_b = p.y * F + q.y * (256u - F);
+            }
+            else
+            {
+                acc_a += lerp16 (p.x, q.x, F);
+                acc_b += lerp16 (p.y, q.y, F);
+            }
+        }
+        uint2 h;
+        if constexpr (HH == 0)
+        {
+            h.x = __byte_perm (acc_a, 0, 0x4341);       /* (acc >> 8) & 0x00ff00ff */
+            h.y = __byte_perm (acc_b, 0, 0x4341);
+        }
+        else
+        {
+            h.x = (acc_a >> HH) & 0x00ff00ffu;
+            h.y = (acc_b >> HH) & 0x00ff00ffu;
+        }
+        sm_h[(size_t) r * M.tile_w + xl] = h;
+        }
+    }
+    __syncthreads ();
+
+    /* phase 2: vertical filter + pack + store, four output pixels per item */
+    const uint32_t groups = (tw + 3) / 4;
+    const uint32_t th = yl1 - yl0;
+    const uint32_t g = threadIdx.x % groups, ry_step = blockDim.x / groups;
+    for (uint32_t ry = threadIdx.x / groups; ry < th && ry_step > 0; ry += ry_step)
+    {
+        const uint32_t yl = yl0 + ry;
+        const uint32_t e = __ldg (&P.tab_y[P.first_row + yl]);
+        const uint32_t r0 = SMOL_TAB_OFS (e) - r_lo, F = SMOL_TAB_F (e), G = 256u - F;
+        const uint32_t r1 = min (SMOL_TAB_OFS (e) + 1, P.h_in - 1) - r_lo;
+        const uint4 *top = reinterpret_cast<const uint4 *> (sm_h + (size_t) r0 * M.tile_w + 4 * g);
+        const uint4 *bot = reinterpret_cast<const uint4 *> (sm_h + (size_t) r1 * M.tile_w + 4 * g);
+        const uint4 t0 = top[0], t1 = top[1], b0 = bot[0], b1 = bot[1];
+        uint32_t out[4];
+
+        /* pixel o: lanes (t.x, t.y) of pixel pairs */
+        const uint32_t ta[4] = { t0.x, t0.z, t1.x, t1.z }, tb[4] = { t0.y, t0.w, t1.y, t1.w };
+        const uint32_t ba[4] = { b0.x, b0.z, b1.x, b1.z }, bb[4] = { b0.y, b0.w, b1.y, b1.w };
+#pragma unroll
+        for (int o = 0; o < 4; o++)
+        {
+            const uint32_t acc_a = ta[o] * F + ba[o] * G;
+            const uint32_t acc_b = tb[o] * F + bb[o] * G;
+            if (P.out_unassoc)
+            {
+                uint32_t v = __byte_perm (acc_a, acc_b, 0x7351);   /* source byte order */
+                v = (P.in_alpha_shift == 0) ? half_unpremul<true> (v, sm_inv) : half_unpremul<false> (v, sm_inv);
+                out[o] = __byte_perm (v, 0, P.prmt_sel);
+            }
+            else
+                out[o] = __byte_perm (acc_a, acc_b, M.acc_prmt_sel);
+        }
+
+        const uint32_t x = x0 + 4 * g;
+        const uint32_t n_px = min (4u, x1 - x);
+        uint8_t *dst = dst_img + (size_t) yl * P.dst_pitch + (size_t) x * P.bpp_out;
+        if (P.bpp_out == 4)
+        {
+            if (n_px == 4 && (reinterpret_cast<uintptr_t> (dst) & 15) == 0)
+                *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
+            else
+                for (uint32_t o = 0; o < n_px; o++)
+                    store_raw_px (dst + 4 * o, out[o], 4);
+        }
+        else
+        {
+            if (n_px == 4 && (reinterpret_cast<uintptr_t> (dst) & 3) == 0)
+            {
+                uint32_t *d32 = reinterpret_cast<uint32_t *> (dst);
+                d32[0] = __byte_perm (out[0], out[1], 0x4210);
+                d32[1] = __byte_perm (out[1], out[2], 0x5421);
+                d32[2] = __byte_perm (out[2], out[3], 0x6542);
+            }
+            else
+                for (uint32_t o = 0; o < n_px; o++)
+                    store_raw_px (dst + 3 * o, out[o], 3);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ *
  * Host-side dispatch                                                                         *
  * ------------------------------------------------------------------------------------------ */
 
 static const char *const kernel_names[SMOL_KERNEL_MAX] =
 {
-    "auto", "general", "taps_direct", "half2x", "box"
+    "auto", "general", "taps_direct", "half2x", "box", "mag"
 };
 
 extern "C" const char *
@@ -1128,11 +1324,21 @@ taps_eligible (const SmolLaunch &L)
            && d.mid == SMOL_MID_P8 && !d.storage128;
 }
 
+static bool
+mag_eligible (const SmolLaunch &L)
+{
+    return taps_eligible (L) && L.d.h_out > L.d.h_in;
+}
+
 extern "C" int
 smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
 {
     const bool half_ok = half_eligible (*launch);
     const bool taps_ok = taps_eligible (*launch);
+    const bool mag_ok = mag_eligible (*launch);
+
+    if (forced == SMOL_KERNEL_MAG)
+        return mag_ok ? SMOL_KERNEL_MAG : SMOL_KERNEL_GENERAL;
 
     if (forced == SMOL_KERNEL_GENERAL)
         return SMOL_KERNEL_GENERAL;
@@ -1144,6 +1350,8 @@ smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
         return SMOL_KERNEL_GENERAL;
     if (half_ok)
         return SMOL_KERNEL_HALF2X;
+    if (mag_ok)
+        return SMOL_KERNEL_MAG;
     if (taps_ok)
         return SMOL_KERNEL_TAPS_DIRECT;
     return SMOL_KERNEL_GENERAL;
@@ -1354,6 +1562,80 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
     return launch_taps_h<2> (P, d.v_halvings, grid, block, stream);
 }
 
+static void
+taps_params_init (TapsParams &P, const SmolLaunch &L)
+{
+    const SmolJobDesc &d = L.d;
+
+    P.src = L.src; P.dst = L.dst;
+    P.src_pitch = L.src_pitch; P.dst_pitch = L.dst_pitch;
+    P.src_image_stride = L.src_image_stride; P.dst_image_stride = L.dst_image_stride;
+    P.tab_x = L.tab_x; P.tab_y = L.tab_y;
+    P.inv_div_p8 = L.luts->inv_div_p8;
+    P.w_in = d.w_in; P.h_in = d.h_in; P.w_out = d.w_out;
+    P.first_row = L.first_row; P.n_rows = L.n_rows;
+    P.rows_per_thread = 1;
+    P.bpp_in = d.bpp_in; P.bpp_out = d.bpp_out;
+    P.in_alpha_shift = (d.in_alpha_idx == 0xff ? 3 : d.in_alpha_idx) * 8;
+    P.in_unassoc = d.in_unassoc; P.out_unassoc = d.out_unassoc;
+    P.prmt_sel = byte_order_selector (d);
+}
+
+static cudaError_t
+launch_mag (const SmolLaunch &L, cudaStream_t stream)
+{
+    const SmolJobDesc &d = L.d;
+    MagParams M;
+
+    taps_params_init (M.t, L);
+    M.tile_w = 256;
+    if (M.tile_w > ((d.w_out + 3) & ~3u))
+        M.tile_w = (d.w_out + 3) & ~3u;
+    M.tile_h = 32;
+    /* source window bounds: a bilinear sample advances at most 2 source pixels (minify <= 2:1 per
+     * sample) and at most 1 source row per output row here (h_out > h_in) */
+    const uint64_t max_cols = ((uint64_t) M.tile_w << d.h_halvings) * 2 + 2;
+    M.max_src_cols = (uint32_t) (max_cols < d.w_in ? max_cols : d.w_in);
+    M.max_src_cols = (M.max_src_cols + 1) & ~1u;        /* keeps sm_h 16-byte aligned */
+    const uint64_t max_rows = (uint64_t) M.tile_h + 2;
+    M.max_src_rows = (uint32_t) (max_rows < d.h_in ? max_rows : d.h_in);
+    /* keep the tile's shared memory modest when the horizontal direction minifies */
+    while (M.tile_h > 4 && (uint64_t) M.max_src_rows * (M.max_src_cols + M.tile_w) * 8 > 96 * 1024)
+    {
+        M.tile_h /= 2;
+        M.max_src_rows = M.tile_h + 2 < d.h_in ? M.tile_h + 2 : d.h_in;
+    }
+
+    /* (acc_a, acc_b) -> destination bytes: source byte s lives in byte 1 (s = 0), 5 (s = 1),
+     * 3 (s = 2), 7 (s = 3) of the PRMT operand pair */
+    static const uint32_t acc_byte[4] = { 1, 5, 3, 7 };
+    uint32_t sel = 0;
+    for (int j = 0; j < 4; j++)
+        sel |= acc_byte[(M.t.prmt_sel >> (4 * j)) & 3] << (4 * j);
+    M.acc_prmt_sel = sel;
+
+    const size_t raw_pitch = ((size_t) M.max_src_cols * d.bpp_in + 16 + 15) & ~(size_t) 15;
+    const size_t smem = raw_pitch + (size_t) M.max_src_rows * (M.max_src_cols + M.tile_w) * 8;
+    dim3 grid ((d.w_out + M.tile_w - 1) / M.tile_w, (L.n_rows + M.tile_h - 1) / M.tile_h, L.n_images);
+    cudaError_t err;
+
+    if (d.h_halvings == 0)
+    {
+        if (smem > 48 * 1024 && (err = cudaFuncSetAttribute (smol_mag_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess)
+            return err;
+        return launch_pdl (smol_mag_kernel<0>, M, grid, dim3 (256), smem, stream);
+    }
+    if (d.h_halvings == 1)
+    {
+        if (smem > 48 * 1024 && (err = cudaFuncSetAttribute (smol_mag_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess)
+            return err;
+        return launch_pdl (smol_mag_kernel<1>, M, grid, dim3 (256), smem, stream);
+    }
+    if (smem > 48 * 1024 && (err = cudaFuncSetAttribute (smol_mag_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess)
+        return err;
+    return launch_pdl (smol_mag_kernel<2>, M, grid, dim3 (256), smem, stream);
+}
+
 template <bool S128, bool HBOX, bool VBOX>
 static cudaError_t
 launch_general (const SmolLaunch &L, cudaStream_t stream)
@@ -1418,6 +1700,8 @@ smol_cuda_launch (const SmolLaunch *launch, int kernel_id, void *stream_p, const
 
     if (kernel_id == SMOL_KERNEL_HALF2X && half_eligible (L))
         return (int) launch_half (L, stream);
+    if (kernel_id == SMOL_KERNEL_MAG && mag_eligible (L))
+        return (int) launch_mag (L, stream);
     if (kernel_id == SMOL_KERNEL_TAPS_DIRECT && taps_eligible (L))
         return (int) launch_taps (L, stream);
     if (name_out)

@@ -28,6 +28,7 @@ enum
     SMOL_KERNEL_TAPS_DIRECT = 2, /* bilinear / copy / one on both axes, 64bpp, register-only */
     SMOL_KERNEL_HALF2X = 3,      /* exact 2^k:1 reductions (all F = 128), 32bpp in, packed-byte math */
     SMOL_KERNEL_BOX = 4,         /* box x box, tuned for large-span downscales */
+    SMOL_KERNEL_MAG = 5,         /* vertical magnification: two-phase shared-memory tile */
     SMOL_KERNEL_MAX
 };
 

@@ -43,10 +43,10 @@ def test_golden_digests(sb):
     assert not bad, "CUDA output differs from the reference digests: %s" % bad[:10]
 
 
-@pytest.mark.parametrize("forced", [0, 1, 2], ids=["auto", "general", "taps"])
+@pytest.mark.parametrize("forced", [0, 1, 2, 5], ids=["auto", "general", "taps", "mag"])
 def test_random_matrix_vs_oracle(sb, restatement, forced):
     """forced = 0: the dispatcher's choice; 1: everything through the general kernel;
-    2: the direct taps kernel wherever it is eligible (general elsewhere)."""
+    2 / 5: the direct taps / magnification kernel wherever eligible (general elsewhere)."""
     sb.force_kernel(forced)
     try:
         for idx, job in enumerate(cases.job_matrix(4242, 600)):
