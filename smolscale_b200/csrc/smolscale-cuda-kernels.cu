@@ -1100,163 +1100,176 @@ smol_taps_kernel (const TapsParams P)
 struct MagParams
 {
     TapsParams t;
-    uint32_t tile_w, tile_h;        /* output tile; tile_w is a multiple of 4 */
-    uint32_t max_src_cols;          /* bound on source columns per tile (smem row pitch of sm_u, in pixels) */
+    uint32_t tile_w, tile_h;        /* output tile; tile_w is a multiple of 4, at most 256 */
+    uint32_t u_pitch;               /* pixels per row of the unpacked source window (even) */
     uint32_t max_src_rows;          /* bound on source rows per tile */
+    uint32_t u_cw;                  /* power of two >= min (u_pitch, 256): thread columns in phase 1a */
     uint32_t acc_prmt_sel;          /* (acc_a, acc_b) high bytes -> destination byte order */
+    uint32_t src_u32_ok;            /* 32bpp source rows are 4-byte aligned */
 };
 
-template <int HH>
+/* Format traits resolved at compile time: BI / BO bytes per pixel in / out, IU / OU unassociated
+ * alpha in / out, AF alpha is the first byte of a 32bpp source pixel (else the last). */
+template <int BI, int BO, bool IU, bool OU, bool AF>
 __global__ void __launch_bounds__ (256)
 smol_mag_kernel (const MagParams M)
 {
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
     __shared__ uint32_t sm_inv[256];
+    __shared__ uint32_t sm_ty[64];
     const TapsParams &P = M.t;
+    const uint32_t tid = threadIdx.x;
 
     pdl_launch_dependents ();
-    if (P.out_unassoc)
-    {
-        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
-            sm_inv[i] = __ldg (&P.inv_div_p8[i]) << 3;
-    }
+    if constexpr (OU)
+        sm_inv[tid] = __ldg (&P.inv_div_p8[tid]) << 3;
 
     const uint32_t x0 = blockIdx.x * M.tile_w;
     const uint32_t x1 = min (x0 + M.tile_w, P.w_out);              /* exclusive */
     const uint32_t yl0 = blockIdx.y * M.tile_h;
     const uint32_t yl1 = min (yl0 + M.tile_h, P.n_rows);
-    const uint32_t tw = x1 - x0;
+    const uint32_t tw = x1 - x0, th = yl1 - yl0;
 
     /* source window of the tile (tables are library-owned: readable before the dependency wait) */
-    const uint32_t c_lo = SMOL_TAB_OFS (__ldg (&P.tab_x[x0 << HH]));
-    const uint32_t c_hi = min (SMOL_TAB_OFS (__ldg (&P.tab_x[(x1 << HH) - 1])) + 1, P.w_in - 1);
+    const uint32_t c_lo = SMOL_TAB_OFS (__ldg (&P.tab_x[x0]));
+    const uint32_t c_hi = min (SMOL_TAB_OFS (__ldg (&P.tab_x[x1 - 1])) + 1, P.w_in - 1);
     const uint32_t r_lo = SMOL_TAB_OFS (__ldg (&P.tab_y[P.first_row + yl0]));
     const uint32_t r_hi = min (SMOL_TAB_OFS (__ldg (&P.tab_y[P.first_row + yl1 - 1])) + 1, P.h_in - 1);
     const uint32_t n_cols = c_hi - c_lo + 1, n_rows = r_hi - r_lo + 1;
+    if (tid < th)
+        sm_ty[tid] = __ldg (&P.tab_y[P.first_row + yl0 + tid]);
 
-    /* shared memory carve-up */
-    const uint32_t raw_pitch = (M.max_src_cols * P.bpp_in + 16 + 15) & ~15u;
-    uint8_t *sm_raw = sm_dyn;                                                   /* one staged source row */
-    uint2 *sm_u = reinterpret_cast<uint2 *> (sm_dyn + raw_pitch);               /* [n_rows][max_src_cols] unpacked */
-    uint2 *sm_h = sm_u + (size_t) M.max_src_rows * M.max_src_cols;              /* [n_rows][tile_w] h-filtered */
+    uint2 *sm_u = reinterpret_cast<uint2 *> (sm_dyn);                           /* [rows][u_pitch] unpacked source */
+    uint32_t *sm_ha = reinterpret_cast<uint32_t *> (sm_u + (size_t) M.max_src_rows * M.u_pitch);
+    uint32_t *sm_hb = sm_ha + (size_t) M.max_src_rows * M.tile_w;               /* two planes [rows][tile_w] */
 
     const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
     uint8_t *dst_img = P.dst + (size_t) blockIdx.z * P.dst_image_stride;
 
     pdl_wait ();
 
-    /* phase 1a: stage + unpack the source window */
-    for (uint32_t r = 0; r < n_rows; r++)
+    /* phase 1a: load + unpack the source window, one source pixel per thread step */
     {
-        const uint8_t *gbeg = src + (size_t) (r_lo + r) * P.src_pitch + (size_t) c_lo * P.bpp_in;
-        const uint8_t *gend = gbeg + (size_t) n_cols * P.bpp_in;
-        const uint32_t sm_ofs = (uint32_t) (reinterpret_cast<uintptr_t> (gbeg) & 15);
-
-        __syncthreads ();
-        stage_bytes (sm_raw, gbeg, gend);
-        __syncthreads ();
-        for (uint32_t c = threadIdx.x; c < n_cols; c += blockDim.x)
+        const uint32_t ct = tid & (M.u_cw - 1), rt = tid / M.u_cw, r_step = 256 / M.u_cw;
+        for (uint32_t r = rt; r < n_rows; r += r_step)
         {
-            const uint8_t *p = sm_raw + sm_ofs + (size_t) c * P.bpp_in;
-            uint32_t raw;
-            if (P.bpp_in == 4)
-                raw = (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
-            else
-                raw = (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | 0xff000000u;
-            const Px16 u = taps_unpack (raw, P);
-            sm_u[(size_t) r * M.max_src_cols + c] = make_uint2 (u.a, u.b);
+            const uint8_t *row = src + (size_t) (r_lo + r) * P.src_pitch + (size_t) c_lo * BI;
+            for (uint32_t c = ct; c < n_cols; c += M.u_cw)
+            {
+                const uint8_t *p = row + c * BI;
+                uint32_t raw;
+                if (BI == 4 && M.src_u32_ok)
+                    raw = __ldg (reinterpret_cast<const uint32_t *> (p));
+                else
+                {
+                    raw = (uint32_t) __ldg (p) | ((uint32_t) __ldg (p + 1) << 8) | ((uint32_t) __ldg (p + 2) << 16);
+                    raw |= BI == 4 ? ((uint32_t) __ldg (p + 3) << 24) : 0xff000000u;
+                }
+                uint32_t a = raw & 0x00ff00ffu, b2 = (raw >> 8) & 0x00ff00ffu;
+                if constexpr (IU)
+                {
+                    /* premultiply: ((c + 1) * (alpha + 1) - 1) >> 8, alpha lane untouched (generic:238-244) */
+                    if constexpr (AF)
+                    {
+                        const uint32_t alpha = raw & 0xff, m = alpha + 1;
+                        a = (((((a & 0x00ff0000u) + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff0000u) | alpha;
+                        b2 = (((b2 + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff00ffu;
+                    }
+                    else
+                    {
+                        const uint32_t alpha = raw >> 24, m = alpha + 1;
+                        a = (((a + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff00ffu;
+                        b2 = (((((b2 & 0x000000ffu) + 0x00010001u) * m - 0x00010001u) >> 8) & 0x000000ffu) | (alpha << 16);
+                    }
+                }
+                sm_u[r * M.u_pitch + c] = make_uint2 (a, b2);
+            }
         }
     }
     __syncthreads ();
 
-    /* phase 1b: horizontal filter, once per (source row, output column).  Thread -> column is
-     * fixed (tw <= blockDim), so the tap entries are read once and rows are strided. */
+    /* phase 1b: horizontal taps, once per (source row, output column); thread -> column fixed */
     {
-        const uint32_t xl = threadIdx.x % tw, r_step = blockDim.x / tw;
-        uint32_t ofs_p[1 << HH], ofs_q[1 << HH], Fk[1 << HH];
-#pragma unroll
-        for (int k = 0; k < (1 << HH); k++)
-        {
-            const uint32_t e = __ldg (&P.tab_x[((x0 + xl) << HH) + k]);
-            ofs_p[k] = SMOL_TAB_OFS (e) - c_lo;
-            ofs_q[k] = min (SMOL_TAB_OFS (e) + 1, P.w_in - 1) - c_lo;
-            Fk[k] = SMOL_TAB_F (e);
-        }
-        for (uint32_t r = threadIdx.x / tw; r < n_rows && r_step > 0; r += r_step)
-        {
-        uint32_t acc_a = 0, acc_b = 0;
-#pragma unroll
-        for (int k = 0; k < (1 << HH); k++)
-        {
-            const uint32_t F = Fk[k];
-            const uint2 p = sm_u[(size_t) r * M.max_src_cols + ofs_p[k]];
-            const uint2 q = sm_u[(size_t) r * M.max_src_cols + ofs_q[k]];
-            if constexpr (HH == 0)
+        const uint32_t xl = tid % tw, r_step = 256 / tw;
+        const uint32_t e = __ldg (&P.tab_x[x0 + xl]);
+        const uint32_t op = SMOL_TAB_OFS (e) - c_lo, oq = min (SMOL_TAB_OFS (e) + 1, P.w_in - 1) - c_lo;
+        const uint32_t F = SMOL_TAB_F (e), G = 256u - F;
+        if (r_step > 0)
+            for (uint32_t r = tid / tw; r < n_rows; r += r_step)
             {
-                acc_a = p.x * F + q.x * (256u - F);
-                acc_b = p.y * F + q.y * (256u - F);
+                const uint2 p = sm_u[r * M.u_pitch + op];
+                const uint2 q = sm_u[r * M.u_pitch + oq];
+                sm_ha[r * M.tile_w + xl] = __byte_perm (p.x * F + q.x * G, 0, 0x4341);   /* (acc >> 8) & 0x00ff00ff */
+                sm_hb[r * M.tile_w + xl] = __byte_perm (p.y * F + q.y * G, 0, 0x4341);
             }
-            else
-            {
-                acc_a += lerp16 (p.x, q.x, F);
-                acc_b += lerp16 (p.y, q.y, F);
-            }
-        }
-        uint2 h;
-        if constexpr (HH == 0)
-        {
-            h.x = __byte_perm (acc_a, 0, 0x4341);       /* (acc >> 8) & 0x00ff00ff */
-            h.y = __byte_perm (acc_b, 0, 0x4341);
-        }
-        else
-        {
-            h.x = (acc_a >> HH) & 0x00ff00ffu;
-            h.y = (acc_b >> HH) & 0x00ff00ffu;
-        }
-        sm_h[(size_t) r * M.tile_w + xl] = h;
-        }
     }
     __syncthreads ();
 
-    /* phase 2: vertical filter + pack + store, four output pixels per item */
-    const uint32_t groups = (tw + 3) / 4;
-    const uint32_t th = yl1 - yl0;
-    const uint32_t g = threadIdx.x % groups, ry_step = blockDim.x / groups;
-    for (uint32_t ry = threadIdx.x / groups; ry < th && ry_step > 0; ry += ry_step)
+    /* phase 2: vertical taps + pack + store.  Lane -> 4 adjacent output pixels (conflict-free
+     * 128-bit shared-memory reads); each thread walks a run of consecutive output rows so the two
+     * source rows stay in registers while only the weight changes (4:1 upscale: ~4 rows per load). */
+    const uint32_t groups = (tw + 3) >> 2;
+    const uint32_t n_runs = 256 / groups;                          /* groups <= 64 */
+    const uint32_t g = tid % groups, run = tid / groups;
+    if (run >= n_runs)
+        return;
+    const uint32_t rows_per_run = (th + n_runs - 1) / n_runs;
+    const uint32_t ry_begin = run * rows_per_run, ry_end = min (ry_begin + rows_per_run, th);
+    const uint32_t x = x0 + 4 * g;
+    const uint32_t n_px = min (4u, x1 - x);
+    const uint32_t *ha = sm_ha + 4 * g, *hb = sm_hb + 4 * g;
+    uint8_t *dst = dst_img + (size_t) (yl0 + ry_begin) * P.dst_pitch + (size_t) x * BO;
+    const bool fast_store = n_px == 4 && (reinterpret_cast<uintptr_t> (dst) & (BO == 4 ? 15 : 3)) == 0
+                            && (P.dst_pitch & (BO == 4 ? 15 : 3)) == 0;
+    uint32_t cur0 = 0xffffffffu, cur1 = 0xffffffffu;
+    uint4 ta = make_uint4 (0, 0, 0, 0), tb = ta, ba = ta, bb = ta;
+
+    for (uint32_t ry = ry_begin; ry < ry_end; ry++, dst += P.dst_pitch)
     {
-        const uint32_t yl = yl0 + ry;
-        const uint32_t e = __ldg (&P.tab_y[P.first_row + yl]);
+        const uint32_t e = sm_ty[ry];
         const uint32_t r0 = SMOL_TAB_OFS (e) - r_lo, F = SMOL_TAB_F (e), G = 256u - F;
         const uint32_t r1 = min (SMOL_TAB_OFS (e) + 1, P.h_in - 1) - r_lo;
-        const uint4 *top = reinterpret_cast<const uint4 *> (sm_h + (size_t) r0 * M.tile_w + 4 * g);
-        const uint4 *bot = reinterpret_cast<const uint4 *> (sm_h + (size_t) r1 * M.tile_w + 4 * g);
-        const uint4 t0 = top[0], t1 = top[1], b0 = bot[0], b1 = bot[1];
+
+        if (r0 != cur0)
+        {
+            if (r0 == cur1)
+            {
+                ta = ba; tb = bb;
+            }
+            else
+            {
+                ta = *reinterpret_cast<const uint4 *> (ha + r0 * M.tile_w);
+                tb = *reinterpret_cast<const uint4 *> (hb + r0 * M.tile_w);
+            }
+            cur0 = r0;
+        }
+        if (r1 != cur1)
+        {
+            ba = *reinterpret_cast<const uint4 *> (ha + r1 * M.tile_w);
+            bb = *reinterpret_cast<const uint4 *> (hb + r1 * M.tile_w);
+            cur1 = r1;
+        }
+
+        const uint32_t acc_a[4] = { ta.x * F + ba.x * G, ta.y * F + ba.y * G, ta.z * F + ba.z * G, ta.w * F + ba.w * G };
+        const uint32_t acc_b[4] = { tb.x * F + bb.x * G, tb.y * F + bb.y * G, tb.z * F + bb.z * G, tb.w * F + bb.w * G };
         uint32_t out[4];
 
-        /* pixel o: lanes (t.x, t.y) of pixel pairs */
-        const uint32_t ta[4] = { t0.x, t0.z, t1.x, t1.z }, tb[4] = { t0.y, t0.w, t1.y, t1.w };
-        const uint32_t ba[4] = { b0.x, b0.z, b1.x, b1.z }, bb[4] = { b0.y, b0.w, b1.y, b1.w };
 #pragma unroll
         for (int o = 0; o < 4; o++)
         {
-            const uint32_t acc_a = ta[o] * F + ba[o] * G;
-            const uint32_t acc_b = tb[o] * F + bb[o] * G;
-            if (P.out_unassoc)
+            if constexpr (OU)
             {
-                uint32_t v = __byte_perm (acc_a, acc_b, 0x7351);   /* source byte order */
-                v = (P.in_alpha_shift == 0) ? half_unpremul<true> (v, sm_inv) : half_unpremul<false> (v, sm_inv);
+                uint32_t v = __byte_perm (acc_a[o], acc_b[o], 0x7351);      /* source byte order */
+                v = half_unpremul<AF> (v, sm_inv);
                 out[o] = __byte_perm (v, 0, P.prmt_sel);
             }
             else
-                out[o] = __byte_perm (acc_a, acc_b, M.acc_prmt_sel);
+                out[o] = __byte_perm (acc_a[o], acc_b[o], M.acc_prmt_sel);
         }
 
-        const uint32_t x = x0 + 4 * g;
-        const uint32_t n_px = min (4u, x1 - x);
-        uint8_t *dst = dst_img + (size_t) yl * P.dst_pitch + (size_t) x * P.bpp_out;
-        if (P.bpp_out == 4)
+        if constexpr (BO == 4)
         {
-            if (n_px == 4 && (reinterpret_cast<uintptr_t> (dst) & 15) == 0)
+            if (fast_store)
                 *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
             else
                 for (uint32_t o = 0; o < n_px; o++)
@@ -1264,7 +1277,7 @@ smol_mag_kernel (const MagParams M)
         }
         else
         {
-            if (n_px == 4 && (reinterpret_cast<uintptr_t> (dst) & 3) == 0)
+            if (fast_store)
             {
                 uint32_t *d32 = reinterpret_cast<uint32_t *> (dst);
                 d32[0] = __byte_perm (out[0], out[1], 0x4210);
@@ -1327,7 +1340,7 @@ taps_eligible (const SmolLaunch &L)
 static bool
 mag_eligible (const SmolLaunch &L)
 {
-    return taps_eligible (L) && L.d.h_out > L.d.h_in;
+    return taps_eligible (L) && L.d.h_out > L.d.h_in && L.d.h_halvings == 0;
 }
 
 extern "C" int
@@ -1581,6 +1594,20 @@ taps_params_init (TapsParams &P, const SmolLaunch &L)
     P.prmt_sel = byte_order_selector (d);
 }
 
+template <int BI, int BO, bool IU, bool OU, bool AF>
+static cudaError_t
+launch_mag_fmt (const MagParams &M, dim3 grid, size_t smem, cudaStream_t stream)
+{
+    if (smem > 48 * 1024)
+    {
+        cudaError_t err = cudaFuncSetAttribute (smol_mag_kernel<BI, BO, IU, OU, AF>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (err != cudaSuccess)
+            return err;
+    }
+    return launch_pdl (smol_mag_kernel<BI, BO, IU, OU, AF>, M, grid, dim3 (256), smem, stream);
+}
+
 static cudaError_t
 launch_mag (const SmolLaunch &L, cudaStream_t stream)
 {
@@ -1592,19 +1619,27 @@ launch_mag (const SmolLaunch &L, cudaStream_t stream)
     if (M.tile_w > ((d.w_out + 3) & ~3u))
         M.tile_w = (d.w_out + 3) & ~3u;
     M.tile_h = 32;
-    /* source window bounds: a bilinear sample advances at most 2 source pixels (minify <= 2:1 per
-     * sample) and at most 1 source row per output row here (h_out > h_in) */
-    const uint64_t max_cols = ((uint64_t) M.tile_w << d.h_halvings) * 2 + 2;
-    M.max_src_cols = (uint32_t) (max_cols < d.w_in ? max_cols : d.w_in);
-    M.max_src_cols = (M.max_src_cols + 1) & ~1u;        /* keeps sm_h 16-byte aligned */
-    const uint64_t max_rows = (uint64_t) M.tile_h + 2;
-    M.max_src_rows = (uint32_t) (max_rows < d.h_in ? max_rows : d.h_in);
-    /* keep the tile's shared memory modest when the horizontal direction minifies */
-    while (M.tile_h > 4 && (uint64_t) M.max_src_rows * (M.max_src_cols + M.tile_w) * 8 > 96 * 1024)
+
+    /* Source window bounds from the sampling step: consecutive samples advance by at most
+     * ceil (dim_in / dim_out) source pixels; + 1 for the second tap, + 2 slack for rounding. */
+    size_t smem;
+    for (;;)
     {
+        const uint64_t cols = ((uint64_t) M.tile_w * d.w_in + d.w_out - 1) / d.w_out + 3;
+        const uint64_t rows = ((uint64_t) M.tile_h * d.h_in + d.h_out - 1) / d.h_out + 3;
+        M.u_pitch = (uint32_t) (cols < d.w_in ? cols : d.w_in);
+        M.u_pitch = (M.u_pitch + 1) & ~1u;                         /* keeps the planes 16-byte aligned */
+        M.max_src_rows = (uint32_t) (rows < d.h_in ? rows : d.h_in);
+        smem = (size_t) M.max_src_rows * ((size_t) M.u_pitch + M.tile_w) * 8;
+        if (smem <= 64 * 1024 || M.tile_h <= 4)
+            break;
         M.tile_h /= 2;
-        M.max_src_rows = M.tile_h + 2 < d.h_in ? M.tile_h + 2 : d.h_in;
     }
+    M.u_cw = 1;
+    while (M.u_cw < 256 && M.u_cw < M.u_pitch)
+        M.u_cw *= 2;
+    M.src_u32_ok = (reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
+                   && (L.src_image_stride & 3) == 0;
 
     /* (acc_a, acc_b) -> destination bytes: source byte s lives in byte 1 (s = 0), 5 (s = 1),
      * 3 (s = 2), 7 (s = 3) of the PRMT operand pair */
@@ -1614,26 +1649,29 @@ launch_mag (const SmolLaunch &L, cudaStream_t stream)
         sel |= acc_byte[(M.t.prmt_sel >> (4 * j)) & 3] << (4 * j);
     M.acc_prmt_sel = sel;
 
-    const size_t raw_pitch = ((size_t) M.max_src_cols * d.bpp_in + 16 + 15) & ~(size_t) 15;
-    const size_t smem = raw_pitch + (size_t) M.max_src_rows * (M.max_src_cols + M.tile_w) * 8;
     dim3 grid ((d.w_out + M.tile_w - 1) / M.tile_w, (L.n_rows + M.tile_h - 1) / M.tile_h, L.n_images);
-    cudaError_t err;
+    const bool af = d.in_alpha_idx == 0;
 
-    if (d.h_halvings == 0)
+    if (d.bpp_in == 3)
     {
-        if (smem > 48 * 1024 && (err = cudaFuncSetAttribute (smol_mag_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess)
-            return err;
-        return launch_pdl (smol_mag_kernel<0>, M, grid, dim3 (256), smem, stream);
+        if (d.bpp_out == 3)     return launch_mag_fmt<3, 3, false, false, false> (M, grid, smem, stream);
+        if (d.out_unassoc)      return launch_mag_fmt<3, 4, false, true, false> (M, grid, smem, stream);
+        return launch_mag_fmt<3, 4, false, false, false> (M, grid, smem, stream);
     }
-    if (d.h_halvings == 1)
+    if (d.in_unassoc)
     {
-        if (smem > 48 * 1024 && (err = cudaFuncSetAttribute (smol_mag_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess)
-            return err;
-        return launch_pdl (smol_mag_kernel<1>, M, grid, dim3 (256), smem, stream);
+        if (d.bpp_out == 3)
+            return af ? launch_mag_fmt<4, 3, true, false, true> (M, grid, smem, stream)
+                      : launch_mag_fmt<4, 3, true, false, false> (M, grid, smem, stream);
+        return af ? launch_mag_fmt<4, 4, true, false, true> (M, grid, smem, stream)
+                  : launch_mag_fmt<4, 4, true, false, false> (M, grid, smem, stream);
     }
-    if (smem > 48 * 1024 && (err = cudaFuncSetAttribute (smol_mag_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess)
-        return err;
-    return launch_pdl (smol_mag_kernel<2>, M, grid, dim3 (256), smem, stream);
+    if (d.bpp_out == 3)
+        return launch_mag_fmt<4, 3, false, false, false> (M, grid, smem, stream);
+    if (d.out_unassoc)
+        return af ? launch_mag_fmt<4, 4, false, true, true> (M, grid, smem, stream)
+                  : launch_mag_fmt<4, 4, false, true, false> (M, grid, smem, stream);
+    return launch_mag_fmt<4, 4, false, false, false> (M, grid, smem, stream);
 }
 
 template <bool S128, bool HBOX, bool VBOX>
