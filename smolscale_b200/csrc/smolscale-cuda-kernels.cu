@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "smolscale-cuda-private.h"
@@ -1104,6 +1105,7 @@ struct MagParams
     uint32_t u_pitch;               /* pixels per row of the unpacked source window (even) */
     uint32_t max_src_rows;          /* bound on source rows per tile */
     uint32_t u_cw;                  /* power of two >= min (u_pitch, 256): thread columns in phase 1a */
+    uint32_t u_cw_log2, tile_w_log2;/* tile_w is a power of two (>= 4) */
     uint32_t acc_prmt_sel;          /* (acc_a, acc_b) high bytes -> destination byte order */
     uint32_t src_u32_ok;            /* 32bpp source rows are 4-byte aligned */
 };
@@ -1150,7 +1152,7 @@ smol_mag_kernel (const MagParams M)
 
     /* phase 1a: load + unpack the source window, one source pixel per thread step */
     {
-        const uint32_t ct = tid & (M.u_cw - 1), rt = tid / M.u_cw, r_step = 256 / M.u_cw;
+        const uint32_t ct = tid & (M.u_cw - 1), rt = tid >> M.u_cw_log2, r_step = 256u >> M.u_cw_log2;
         for (uint32_t r = rt; r < n_rows; r += r_step)
         {
             const uint8_t *row = src + (size_t) (r_lo + r) * P.src_pitch + (size_t) c_lo * BI;
@@ -1190,30 +1192,41 @@ smol_mag_kernel (const MagParams M)
 
     /* phase 1b: horizontal taps, once per (source row, output column); thread -> column fixed */
     {
-        const uint32_t xl = tid % tw, r_step = 256 / tw;
+        /* full tiles: tile_w is a power of two, no divisions */
+        const bool full = tw == M.tile_w;
+        const uint32_t xl = full ? (tid & (M.tile_w - 1)) : tid % tw;
+        const uint32_t r_step = full ? (256u >> M.tile_w_log2) : 256 / tw;
+        const uint32_t r_first = full ? (tid >> M.tile_w_log2) : tid / tw;
         const uint32_t e = __ldg (&P.tab_x[x0 + xl]);
         const uint32_t op = SMOL_TAB_OFS (e) - c_lo, oq = min (SMOL_TAB_OFS (e) + 1, P.w_in - 1) - c_lo;
         const uint32_t F = SMOL_TAB_F (e), G = 256u - F;
         if (r_step > 0)
-            for (uint32_t r = tid / tw; r < n_rows; r += r_step)
+        {
+            uint32_t r = r_first;
+            const uint2 *pu = sm_u + r * M.u_pitch + op, *qu = sm_u + r * M.u_pitch + oq;
+            uint32_t *wa = sm_ha + r * M.tile_w + xl, *wb = sm_hb + r * M.tile_w + xl;
+            const uint32_t u_inc = r_step * M.u_pitch, h_inc = r_step * M.tile_w;
+            for (; r < n_rows; r += r_step, pu += u_inc, qu += u_inc, wa += h_inc, wb += h_inc)
             {
-                const uint2 p = sm_u[r * M.u_pitch + op];
-                const uint2 q = sm_u[r * M.u_pitch + oq];
-                sm_ha[r * M.tile_w + xl] = __byte_perm (p.x * F + q.x * G, 0, 0x4341);   /* (acc >> 8) & 0x00ff00ff */
-                sm_hb[r * M.tile_w + xl] = __byte_perm (p.y * F + q.y * G, 0, 0x4341);
+                const uint2 p = *pu, q = *qu;
+                *wa = __byte_perm (p.x * F + q.x * G, 0, 0x4341);   /* (acc >> 8) & 0x00ff00ff */
+                *wb = __byte_perm (p.y * F + q.y * G, 0, 0x4341);
             }
+        }
     }
     __syncthreads ();
 
     /* phase 2: vertical taps + pack + store.  Lane -> 4 adjacent output pixels (conflict-free
      * 128-bit shared-memory reads); each thread walks a run of consecutive output rows so the two
      * source rows stay in registers while only the weight changes (4:1 upscale: ~4 rows per load). */
-    const uint32_t groups = (tw + 3) >> 2;
-    const uint32_t n_runs = 256 / groups;                          /* groups <= 64 */
-    const uint32_t g = tid % groups, run = tid / groups;
+    const bool full = tw == M.tile_w;
+    const uint32_t groups = (tw + 3) >> 2;                          /* <= 64 */
+    const uint32_t n_runs = full ? (1024u >> M.tile_w_log2) : 256 / groups;
+    const uint32_t g = full ? (tid & (groups - 1)) : tid % groups;
+    const uint32_t run = full ? (tid >> (M.tile_w_log2 - 2)) : tid / groups;
     if (run >= n_runs)
         return;
-    const uint32_t rows_per_run = (th + n_runs - 1) / n_runs;
+    const uint32_t rows_per_run = full ? ((th + n_runs - 1) >> (10 - M.tile_w_log2)) : (th + n_runs - 1) / n_runs;
     const uint32_t ry_begin = run * rows_per_run, ry_end = min (ry_begin + rows_per_run, th);
     const uint32_t x = x0 + 4 * g;
     const uint32_t n_px = min (4u, x1 - x);
@@ -1221,73 +1234,65 @@ smol_mag_kernel (const MagParams M)
     uint8_t *dst = dst_img + (size_t) (yl0 + ry_begin) * P.dst_pitch + (size_t) x * BO;
     const bool fast_store = n_px == 4 && (reinterpret_cast<uintptr_t> (dst) & (BO == 4 ? 15 : 3)) == 0
                             && (P.dst_pitch & (BO == 4 ? 15 : 3)) == 0;
-    uint32_t cur0 = 0xffffffffu, cur1 = 0xffffffffu;
-    uint4 ta = make_uint4 (0, 0, 0, 0), tb = ta, ba = ta, bb = ta;
-
-    for (uint32_t ry = ry_begin; ry < ry_end; ry++, dst += P.dst_pitch)
+    uint32_t ry = ry_begin;
+    uint32_t e = ry < ry_end ? sm_ty[ry] : 0;
+    while (ry < ry_end)
     {
-        const uint32_t e = sm_ty[ry];
-        const uint32_t r0 = SMOL_TAB_OFS (e) - r_lo, F = SMOL_TAB_F (e), G = 256u - F;
-        const uint32_t r1 = min (SMOL_TAB_OFS (e) + 1, P.h_in - 1) - r_lo;
+        /* one segment = consecutive output rows that read the same source row pair */
+        const uint32_t ofs = SMOL_TAB_OFS (e);
+        const uint32_t r0 = ofs - r_lo, r1 = min (ofs + 1, P.h_in - 1) - r_lo;
+        const uint4 ta = *reinterpret_cast<const uint4 *> (ha + r0 * M.tile_w);
+        const uint4 tb = *reinterpret_cast<const uint4 *> (hb + r0 * M.tile_w);
+        const uint4 ba = *reinterpret_cast<const uint4 *> (ha + r1 * M.tile_w);
+        const uint4 bb = *reinterpret_cast<const uint4 *> (hb + r1 * M.tile_w);
 
-        if (r0 != cur0)
+        do
         {
-            if (r0 == cur1)
-            {
-                ta = ba; tb = bb;
-            }
-            else
-            {
-                ta = *reinterpret_cast<const uint4 *> (ha + r0 * M.tile_w);
-                tb = *reinterpret_cast<const uint4 *> (hb + r0 * M.tile_w);
-            }
-            cur0 = r0;
-        }
-        if (r1 != cur1)
-        {
-            ba = *reinterpret_cast<const uint4 *> (ha + r1 * M.tile_w);
-            bb = *reinterpret_cast<const uint4 *> (hb + r1 * M.tile_w);
-            cur1 = r1;
-        }
-
-        const uint32_t acc_a[4] = { ta.x * F + ba.x * G, ta.y * F + ba.y * G, ta.z * F + ba.z * G, ta.w * F + ba.w * G };
-        const uint32_t acc_b[4] = { tb.x * F + bb.x * G, tb.y * F + bb.y * G, tb.z * F + bb.z * G, tb.w * F + bb.w * G };
-        uint32_t out[4];
+            const uint32_t F = SMOL_TAB_F (e), G = 256u - F;
+            const uint32_t acc_a[4] = { ta.x * F + ba.x * G, ta.y * F + ba.y * G, ta.z * F + ba.z * G, ta.w * F + ba.w * G };
+            const uint32_t acc_b[4] = { tb.x * F + bb.x * G, tb.y * F + bb.y * G, tb.z * F + bb.z * G, tb.w * F + bb.w * G };
+            uint32_t out[4];
 
 #pragma unroll
-        for (int o = 0; o < 4; o++)
-        {
-            if constexpr (OU)
+            for (int o = 0; o < 4; o++)
             {
-                uint32_t v = __byte_perm (acc_a[o], acc_b[o], 0x7351);      /* source byte order */
-                v = half_unpremul<AF> (v, sm_inv);
-                out[o] = __byte_perm (v, 0, P.prmt_sel);
+                if constexpr (OU)
+                {
+                    uint32_t v = __byte_perm (acc_a[o], acc_b[o], 0x7351);      /* source byte order */
+                    v = half_unpremul<AF> (v, sm_inv);
+                    out[o] = __byte_perm (v, 0, P.prmt_sel);
+                }
+                else
+                    out[o] = __byte_perm (acc_a[o], acc_b[o], M.acc_prmt_sel);
             }
-            else
-                out[o] = __byte_perm (acc_a[o], acc_b[o], M.acc_prmt_sel);
-        }
 
-        if constexpr (BO == 4)
-        {
-            if (fast_store)
-                *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
-            else
-                for (uint32_t o = 0; o < n_px; o++)
-                    store_raw_px (dst + 4 * o, out[o], 4);
-        }
-        else
-        {
-            if (fast_store)
+            if constexpr (BO == 4)
             {
-                uint32_t *d32 = reinterpret_cast<uint32_t *> (dst);
-                d32[0] = __byte_perm (out[0], out[1], 0x4210);
-                d32[1] = __byte_perm (out[1], out[2], 0x5421);
-                d32[2] = __byte_perm (out[2], out[3], 0x6542);
+                if (fast_store)
+                    *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
+                else
+                    for (uint32_t o = 0; o < n_px; o++)
+                        store_raw_px (dst + 4 * o, out[o], 4);
             }
             else
-                for (uint32_t o = 0; o < n_px; o++)
-                    store_raw_px (dst + 3 * o, out[o], 3);
+            {
+                if (fast_store)
+                {
+                    uint32_t *d32 = reinterpret_cast<uint32_t *> (dst);
+                    d32[0] = __byte_perm (out[0], out[1], 0x4210);
+                    d32[1] = __byte_perm (out[1], out[2], 0x5421);
+                    d32[2] = __byte_perm (out[2], out[3], 0x6542);
+                }
+                else
+                    for (uint32_t o = 0; o < n_px; o++)
+                        store_raw_px (dst + 3 * o, out[o], 3);
+            }
+
+            ry++;
+            dst += P.dst_pitch;
+            e = sm_ty[min (ry, th - 1)];
         }
+        while (ry < ry_end && SMOL_TAB_OFS (e) == ofs);
     }
 }
 
@@ -1615,10 +1620,23 @@ launch_mag (const SmolLaunch &L, cudaStream_t stream)
     MagParams M;
 
     taps_params_init (M.t, L);
-    M.tile_w = 256;
-    if (M.tile_w > ((d.w_out + 3) & ~3u))
-        M.tile_w = (d.w_out + 3) & ~3u;
-    M.tile_h = 32;
+    /* power-of-two tile width: the smallest of 4..256 that covers the row, else the cap */
+    static int tune_tw = -1, tune_th = -1;
+    if (tune_tw < 0)
+    {
+        const char *a = getenv ("SMOL_MAG_TW"), *b = getenv ("SMOL_MAG_TH");
+        tune_tw = a ? atoi (a) : 0;
+        tune_th = b ? atoi (b) : 0;
+    }
+    const uint32_t tw_cap = tune_tw > 0 ? (uint32_t) tune_tw : 256;
+    M.tile_w = 4;
+    M.tile_w_log2 = 2;
+    while (M.tile_w < tw_cap && M.tile_w < d.w_out)
+    {
+        M.tile_w *= 2;
+        M.tile_w_log2++;
+    }
+    M.tile_h = tune_th > 0 ? (uint32_t) tune_th : 32;
 
     /* Source window bounds from the sampling step: consecutive samples advance by at most
      * ceil (dim_in / dim_out) source pixels; + 1 for the second tap, + 2 slack for rounding. */
@@ -1631,13 +1649,17 @@ launch_mag (const SmolLaunch &L, cudaStream_t stream)
         M.u_pitch = (M.u_pitch + 1) & ~1u;                         /* keeps the planes 16-byte aligned */
         M.max_src_rows = (uint32_t) (rows < d.h_in ? rows : d.h_in);
         smem = (size_t) M.max_src_rows * ((size_t) M.u_pitch + M.tile_w) * 8;
-        if (smem <= 64 * 1024 || M.tile_h <= 4)
+        if (smem <= 56 * 1024 || M.tile_h <= 4)
             break;
         M.tile_h /= 2;
     }
     M.u_cw = 1;
+    M.u_cw_log2 = 0;
     while (M.u_cw < 256 && M.u_cw < M.u_pitch)
+    {
         M.u_cw *= 2;
+        M.u_cw_log2++;
+    }
     M.src_u32_ok = (reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
                    && (L.src_image_stride & 3) == 0;
 
