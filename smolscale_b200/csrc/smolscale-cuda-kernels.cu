@@ -1297,6 +1297,313 @@ smol_mag_kernel (const MagParams M)
 }
 
 /* ------------------------------------------------------------------------------------------ *
+ * "box" kernel: box filter on both axes (large downscales; BASELINE config 3), 32bpp source.     *
+ *                                                                                              *
+ * Almost all the work of a big downscale is per SOURCE pixel (unpack, and for linear light the  *
+ * unpremultiply -> sRGB table -> premultiply chain), so the kernel is organised around feeding  *
+ * source pixels to threads with as little overhead as possible:                                *
+ *   - the unit of work is one WARP producing 32 / G adjacent output pixels of one output row    *
+ *     (G lanes share a column when spans are long); warps stride over the work items, so load   *
+ *     balance is at warp granularity and no block-wide barrier is ever needed;                  *
+ *   - for each source row of the item the warp copies the row segment it needs into its own     *
+ *     shared-memory buffer with cp.async (16-byte, fully coalesced, zero-filled past the row's  *
+ *     end), double-buffered so the copy of row r + 1 overlaps the arithmetic on row r;          *
+ *   - each lane then walks its own span in shared memory (stride ~ratio words between lanes:    *
+ *     practically conflict-free), unpacks and accumulates in registers, applies the two edge    *
+ *     weights, normalises with span_mul_x (the reference quantises after the horizontal pass,   *
+ *     generic:1263-1270) and adds the row into its vertical accumulator with the row's weight;  *
+ *   - after the last row: normalise with span_mul_y, repack, store.                            *
+ * The data tables live in shared memory (data-dependent gathers).                              *
+ * ------------------------------------------------------------------------------------------ */
+
+enum { BM_P8_P = 0, BM_P8_U = 1, BM_P8L_P = 2, BM_P8L_U = 3, BM_P16_U = 4, BM_P16L_U = 5 };
+
+struct BoxParams
+{
+    SmolJobDesc d;
+    const uint8_t *src; uint8_t *dst;
+    uint32_t src_pitch, dst_pitch;
+    size_t src_image_stride, dst_image_stride;
+    const uint32_t *tab_x, *tab_y;
+    const SmolDeviceLuts *luts;
+    uint32_t first_row, n_rows, n_images;
+    uint32_t lanes_per_col_log2;    /* G = 1 << this */
+    uint32_t x_tiles;               /* items per output row */
+    uint32_t seg_bytes;             /* bytes per staging buffer (multiple of 16) */
+    uint32_t alpha_shift, col_shift;/* bit positions in the packed source pixel */
+};
+
+__device__ __forceinline__ void cp_async_16 (uint32_t smem_addr, const void *gptr, uint32_t src_bytes)
+{
+    asm volatile ("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit ()
+{
+    asm volatile ("cp.async.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void cp_async_wait ()
+{
+    asm volatile ("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+
+/* Per-pixel lanes.  128bpp modes: v[0] = alpha lane, v[1..3] = colours (32-bit lanes).
+ * 64bpp modes: v[0] = bytes 0 and 2, v[1] = bytes 1 and 3 of the source pixel (16-bit lanes). */
+template <int MODE> struct BoxPx { uint32_t v[MODE >= BM_P8L_P ? 4 : 2]; };
+
+template <int MODE>
+__device__ __forceinline__ BoxPx<MODE>
+box_unpack (uint32_t raw, const BoxParams &P, const uint32_t *__restrict__ sm_inv8, const uint32_t *__restrict__ sm_from)
+{
+    BoxPx<MODE> r;
+
+    if constexpr (MODE == BM_P8_P)
+    {
+        r.v[0] = raw & 0x00ff00ffu;
+        r.v[1] = (raw >> 8) & 0x00ff00ffu;
+    }
+    else if constexpr (MODE == BM_P8_U)
+    {
+        /* ((c + 1) * (alpha + 1) - 1) >> 8 on the colour lanes (generic:238-244) */
+        const uint32_t alpha = (raw >> P.alpha_shift) & 0xff, m = alpha + 1;
+        uint32_t a = raw & 0x00ff00ffu, b = (raw >> 8) & 0x00ff00ffu;
+        if (P.alpha_shift == 0)
+        {
+            a = (((((a & 0x00ff0000u) + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff0000u) | alpha;
+            b = (((b + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff00ffu;
+        }
+        else
+        {
+            a = (((a + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff00ffu;
+            b = (((((b & 0x000000ffu) + 0x00010001u) * m - 0x00010001u) >> 8) & 0x000000ffu) | (alpha << 16);
+        }
+        r.v[0] = a;
+        r.v[1] = b;
+    }
+    else
+    {
+        const uint32_t alpha = (raw >> P.alpha_shift) & 0xff;
+        const uint32_t cols = raw >> P.col_shift;
+        uint32_t c[3] = { cols & 0xff, (cols >> 8) & 0xff, (cols >> 16) & 0xff };
+
+        if constexpr (MODE == BM_P8L_P || MODE == BM_P8L_U)
+        {
+            const uint32_t m = (alpha << 3) + 1;
+            if constexpr (MODE == BM_P8L_P)
+            {
+                /* unpremultiply (generic:227-236): sm_inv8 = inv_div_p8 << 3, result = byte 2 */
+                const uint32_t inv8 = sm_inv8[alpha];
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+                    c[i] = __byte_perm (c[i] * inv8, 0, 0x4442);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+            {
+                const uint32_t lin = sm_from[c[i]];                 /* generic:185-199 */
+                c[i] = (lin * m + (m - 1)) >> 11;                   /* ((lin + 1) * m - 1) >> 11 <= 2040, generic:261-269 */
+            }
+            r.v[0] = alpha;
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                c[i] = (MODE == BM_P16L_U ? sm_from[c[i]] : c[i]) * alpha;  /* generic:616-660, :708-752 */
+            r.v[0] = (alpha << 8) | 0x80;
+        }
+        r.v[1] = c[0]; r.v[2] = c[1]; r.v[3] = c[2];
+    }
+    return r;
+}
+
+template <int MODE> __device__ __forceinline__ void box_add (BoxPx<MODE> &a, const BoxPx<MODE> &b)
+{
+#pragma unroll
+    for (int i = 0; i < (MODE >= BM_P8L_P ? 4 : 2); i++) a.v[i] += b.v[i];
+}
+
+/* ((p * w) >> 8) & mask (generic:1177-1192) */
+template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_weight (const BoxPx<MODE> &p, uint32_t w)
+{
+    BoxPx<MODE> r;
+#pragma unroll
+    for (int i = 0; i < (MODE >= BM_P8L_P ? 4 : 2); i++)
+        r.v[i] = ((p.v[i] * w) >> 8) & (MODE >= BM_P8L_P ? 0x00ffffffu : 0x00ff00ffu);
+    return r;
+}
+
+/* scale_64bpp / scale_128bpp_half (generic:1231-1261), lane by lane */
+template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_scale (const BoxPx<MODE> &acc, uint32_t mul)
+{
+    BoxPx<MODE> r;
+    if constexpr (MODE >= BM_P8L_P)
+    {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            r.v[i] = (uint32_t) (((uint64_t) acc.v[i] * mul + (1u << 23)) >> 24) & 0xffffu;
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+        {
+            const uint32_t lo = (uint32_t) (((uint64_t) (acc.v[i] & 0xffffu) * mul + (1u << 23)) >> 24) & 0xffu;
+            const uint32_t hi = (uint32_t) (((uint64_t) (acc.v[i] >> 16) * mul + (1u << 23)) >> 24) & 0xffu;
+            r.v[i] = lo | (hi << 16);
+        }
+    }
+    return r;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__ (256)
+smol_box_kernel (const BoxParams P)
+{
+    extern __shared__ __align__ (16) uint8_t sm_dyn[];
+    __shared__ uint32_t sm_inv8[256];
+    __shared__ uint32_t sm_from[256];
+    constexpr bool S128 = MODE >= BM_P8L_P;
+    const SmolJobDesc &d = P.d;
+
+    pdl_launch_dependents ();
+    if constexpr (MODE == BM_P8L_P)
+        sm_inv8[threadIdx.x] = P.luts->inv_div_p8[threadIdx.x] << 3;
+    if constexpr (MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U)
+        sm_from[threadIdx.x] = P.luts->from_srgb[threadIdx.x];
+    __syncthreads ();
+    pdl_wait ();
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t G = 1u << P.lanes_per_col_log2, g = lane & (G - 1);
+    const uint32_t cols_per_item = 32u >> P.lanes_per_col_log2;
+    uint8_t *bufs = sm_dyn + (size_t) warp * 2 * P.seg_bytes;
+    const uint32_t bufs_addr = (uint32_t) __cvta_generic_to_shared (bufs);
+    const uint32_t row_bytes = d.w_in * 4;
+
+    const uint32_t items_per_image = P.x_tiles * P.n_rows;
+    const uint32_t n_items = items_per_image * P.n_images;
+    const uint32_t warp_stride = gridDim.x * (blockDim.x >> 5);
+
+    for (uint32_t item = blockIdx.x * (blockDim.x >> 5) + warp; item < n_items; item += warp_stride)
+    {
+        const uint32_t img = item / items_per_image;
+        const uint32_t rem = item - img * items_per_image;
+        const uint32_t yl = rem / P.x_tiles, xt = rem - yl * P.x_tiles;
+        const uint32_t y = P.first_row + yl;
+        const uint32_t x_first = xt * cols_per_item;
+        const uint32_t x_last = min (x_first + cols_per_item, d.w_out) - 1;
+        uint32_t x = x_first + (lane >> P.lanes_per_col_log2);
+        const bool store = x <= x_last && g == 0;
+        x = min (x, x_last);
+
+        /* horizontal span of this lane's column (generic:1427-1556 in absolute offsets) */
+        const uint32_t ex0 = __ldg (&P.tab_x[x]), ex1 = __ldg (&P.tab_x[x + 1]);
+        const uint32_t hL = SMOL_TAB_OFS (ex0), hR = SMOL_TAB_OFS (ex1), wr = SMOL_TAB_F (ex0);
+        const uint32_t wl = x == 0 ? 256u : 255u - SMOL_TAB_F (__ldg (&P.tab_x[x - 1]));
+        /* segment of the source rows the whole item reads, as an aligned byte window */
+        const uint32_t sx0 = SMOL_TAB_OFS (__ldg (&P.tab_x[x_first]));
+        const uint32_t sx1 = SMOL_TAB_OFS (__ldg (&P.tab_x[x_last + 1]));
+        const uint32_t win0 = (sx0 * 4) & ~15u;
+        const uint32_t n_chunks = (((sx1 + 1) * 4 + 15) & ~15u) - win0 >> 4;
+
+        /* vertical span (generic:2112-2161 / :2198-2260) */
+        const uint32_t ey0 = __ldg (&P.tab_y[y]), ey1 = __ldg (&P.tab_y[y + 1]);
+        const uint32_t T = SMOL_TAB_OFS (ey0), B = SMOL_TAB_OFS (ey1), Fy = SMOL_TAB_F (ey0);
+        const uint32_t w1 = y == 0 ? 256u : 255u - SMOL_TAB_F (__ldg (&P.tab_y[y - 1]));
+        const uint32_t w2 = S128 ? Fy - 1 : Fy;     /* 128bpp weighs the trailing row by F - 1 (generic:2247-2249) */
+        const uint32_t r_end = Fy > 0 ? B : B - 1;  /* last source row that contributes */
+
+        const uint8_t *src = P.src + (size_t) img * P.src_image_stride + win0;
+
+        auto prefetch = [&] (uint32_t r, uint32_t slot)
+        {
+            const uint8_t *grow = src + (size_t) r * P.src_pitch;
+            const uint32_t sbase = bufs_addr + slot * P.seg_bytes;
+            for (uint32_t k = lane; k < n_chunks; k += 32)
+            {
+                const uint32_t ofs = win0 + 16 * k;
+                const uint32_t valid = ofs < row_bytes ? min (16u, row_bytes - ofs) : 0u;
+                /* past the row's end: zero-fill only (source size 0), address kept inside the row */
+                cp_async_16 (sbase + 16 * k, valid ? grow + 16 * k : grow, valid);
+            }
+            cp_async_commit ();
+        };
+
+        BoxPx<MODE> vacc;
+#pragma unroll
+        for (int i = 0; i < (S128 ? 4 : 2); i++) vacc.v[i] = 0;
+
+        prefetch (T, 0);
+        for (uint32_t r = T; r <= r_end; r++)
+        {
+            const uint32_t slot = (r - T) & 1;
+            if (r < r_end)
+            {
+                prefetch (r + 1, slot ^ 1);
+                cp_async_wait<1> ();
+            }
+            else
+                cp_async_wait<0> ();
+            __syncwarp ();
+
+            const uint32_t *px = reinterpret_cast<const uint32_t *> (bufs + slot * P.seg_bytes) - (win0 >> 2);
+            BoxPx<MODE> acc;
+#pragma unroll
+            for (int i = 0; i < (S128 ? 4 : 2); i++) acc.v[i] = 0;
+
+            /* whole pixels hL + 1 .. hR - 1, interleaved over the G lanes of the column */
+            for (uint32_t j = hL + 1 + g; j < hR; j += G)
+                box_add<MODE> (acc, box_unpack<MODE> (px[j], P, sm_inv8, sm_from));
+            /* edge pixels: lane 0 of the column takes the left one, the last lane the right one */
+            if (g == 0)
+                box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE> (px[hL], P, sm_inv8, sm_from), wl));
+            if (g == G - 1 && wr > 0)
+                box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE> (px[hR], P, sm_inv8, sm_from), wr));
+            for (uint32_t m = G >> 1; m; m >>= 1)
+            {
+#pragma unroll
+                for (int i = 0; i < (S128 ? 4 : 2); i++)
+                    acc.v[i] += __shfl_xor_sync (0xffffffffu, acc.v[i], m);
+            }
+
+            BoxPx<MODE> h = box_scale<MODE> (acc, d.span_mul_x);
+            if (r == T)
+                h = box_weight<MODE> (h, w1);
+            else if (r == B)
+                h = box_weight<MODE> (h, w2);
+            box_add<MODE> (vacc, h);
+            __syncwarp ();      /* everyone is done with this slot before it is refilled */
+        }
+
+        const BoxPx<MODE> fin = box_scale<MODE> (vacc, d.span_mul_y);
+        if (store)
+        {
+            uint32_t packed;
+            if constexpr (S128)
+            {
+                Px<true> o;
+                o.w[0] = (uint64_t) fin.v[0] | ((uint64_t) fin.v[1] << 32);
+                o.w[1] = (uint64_t) fin.v[2] | ((uint64_t) fin.v[3] << 32);
+                packed = pack_px<true> (o, d, P.luts);
+            }
+            else
+            {
+                /* fin holds the pixel's four bytes in source order */
+                const uint32_t bytes = fin.v[0] | (fin.v[1] << 8);
+                const uint32_t alpha = d.in_alpha_idx == 0xff ? 0xffu : (bytes >> P.alpha_shift) & 0xff;
+                const uint32_t cols = bytes >> P.col_shift;
+                Px<false> o;
+                o.w[0] = (uint64_t) alpha | ((uint64_t) (cols & 0xff) << 16) | ((uint64_t) ((cols >> 8) & 0xff) << 32)
+                         | ((uint64_t) ((cols >> 16) & 0xff) << 48);
+                packed = pack_px<false> (o, d, P.luts);
+            }
+            uint8_t *o8 = P.dst + (size_t) img * P.dst_image_stride + (size_t) yl * P.dst_pitch + (size_t) x * d.bpp_out;
+            store_raw_px (o8, packed, d.bpp_out);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ *
  * Host-side dispatch                                                                         *
  * ------------------------------------------------------------------------------------------ */
 
@@ -1348,10 +1655,30 @@ mag_eligible (const SmolLaunch &L)
     return taps_eligible (L) && L.d.h_out > L.d.h_in && L.d.h_halvings == 0;
 }
 
+static bool
+box_eligible (const SmolLaunch &L)
+{
+    const SmolJobDesc &d = L.d;
+
+    if (d.h_kind != SMOL_AXIS_BOX || d.v_kind != SMOL_AXIS_BOX || d.bpp_in != 4)
+        return false;
+    if (d.mid == SMOL_MID_P8 && d.storage128)
+        return false;                   /* ratio > 255 without linear light: general kernel */
+    if (d.w_in / d.w_out >= 512)
+        return false;                   /* a warp's row segment must fit its staging buffer */
+    if ((uint64_t) d.w_out * L.n_rows * L.n_images >= 0x7fffffffull)
+        return false;                   /* 32-bit work item index */
+    return aligned16 (L.src) && (L.src_pitch & 15) == 0 && (L.src_image_stride & 15) == 0;
+}
+
 extern "C" int
 smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
 {
     const bool half_ok = half_eligible (*launch);
+    const bool box_ok = box_eligible (*launch);
+
+    if (forced == SMOL_KERNEL_BOX)
+        return box_ok ? SMOL_KERNEL_BOX : SMOL_KERNEL_GENERAL;
     const bool taps_ok = taps_eligible (*launch);
     const bool mag_ok = mag_eligible (*launch);
 
@@ -1368,6 +1695,8 @@ smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
         return SMOL_KERNEL_GENERAL;
     if (half_ok)
         return SMOL_KERNEL_HALF2X;
+    if (box_ok)
+        return SMOL_KERNEL_BOX;
     if (mag_ok)
         return SMOL_KERNEL_MAG;
     if (taps_ok)
@@ -1696,6 +2025,109 @@ launch_mag (const SmolLaunch &L, cudaStream_t stream)
     return launch_mag_fmt<4, 4, false, false, false> (M, grid, smem, stream);
 }
 
+template <int MODE>
+static cudaError_t
+launch_box_mode (const BoxParams &P, dim3 grid, size_t smem, cudaStream_t stream)
+{
+    if (smem > 48 * 1024)
+    {
+        cudaError_t err = cudaFuncSetAttribute (smol_box_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (err != cudaSuccess)
+            return err;
+    }
+    return launch_pdl (smol_box_kernel<MODE>, P, grid, dim3 (256), smem, stream);
+}
+
+static cudaError_t
+launch_box (const SmolLaunch &L, cudaStream_t stream)
+{
+    const SmolJobDesc &d = L.d;
+    BoxParams P;
+
+    P.d = d;
+    P.src = L.src; P.dst = L.dst;
+    P.src_pitch = L.src_pitch; P.dst_pitch = L.dst_pitch;
+    P.src_image_stride = L.src_image_stride; P.dst_image_stride = L.dst_image_stride;
+    P.tab_x = L.tab_x; P.tab_y = L.tab_y; P.luts = L.luts;
+    P.first_row = L.first_row; P.n_rows = L.n_rows; P.n_images = L.n_images;
+    P.alpha_shift = d.in_alpha_idx * 8;
+    P.col_shift = d.in_col0 * 8;
+
+    int mode;
+    if (d.mid == SMOL_MID_P8)
+        mode = d.in_unassoc ? BM_P8_U : BM_P8_P;
+    else if (d.mid == SMOL_MID_P8L)
+        mode = d.in_unassoc ? BM_P8L_U : BM_P8L_P;
+    else
+        mode = d.mid == SMOL_MID_P16 ? BM_P16_U : BM_P16L_U;
+
+    const void *fn;
+    switch (mode)
+    {
+        case BM_P8_P:   fn = (const void *) smol_box_kernel<BM_P8_P>; break;
+        case BM_P8_U:   fn = (const void *) smol_box_kernel<BM_P8_U>; break;
+        case BM_P8L_P:  fn = (const void *) smol_box_kernel<BM_P8L_P>; break;
+        case BM_P8L_U:  fn = (const void *) smol_box_kernel<BM_P8L_U>; break;
+        case BM_P16_U:  fn = (const void *) smol_box_kernel<BM_P16_U>; break;
+        default:        fn = (const void *) smol_box_kernel<BM_P16L_U>; break;
+    }
+
+    /* Lanes per column (G).  Long spans want several lanes per column (8..16 source pixels per
+     * lane per row); beyond that G only grows to create enough work items: load balance is at
+     * warp granularity, so with r = items / resident warps the efficiency is r / ceil (r). */
+    static int tune_g = -1;
+    if (tune_g < 0)
+    {
+        const char *e = getenv ("SMOL_BOX_G_LOG2");
+        tune_g = e ? atoi (e) : 99;
+    }
+    const uint32_t ratio = d.w_in / d.w_out;
+    uint32_t glog = 0;
+    while (glog < 5 && ratio >= (16u << glog))
+        glog++;
+
+    size_t smem = 0;
+    uint32_t per_sm = 1;
+    for (;; glog++)
+    {
+        if (tune_g != 99)
+            glog = (uint32_t) tune_g;
+        const uint32_t cols = 32u >> glog;
+        P.lanes_per_col_log2 = glog;
+        P.x_tiles = (d.w_out + cols - 1) / cols;
+        /* staging buffer: the widest segment an item can need, + alignment slack */
+        const uint64_t seg_px = ((uint64_t) cols * d.w_in + d.w_out - 1) / d.w_out + 3;
+        P.seg_bytes = (uint32_t) ((seg_px * 4 + 32 + 15) & ~(uint64_t) 15);
+        smem = (size_t) 8 * 2 * P.seg_bytes;
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, 256, smem) != cudaSuccess || occ < 1)
+            occ = 1;
+        per_sm = (uint32_t) occ;
+        const double rounds = (double) P.x_tiles * L.n_rows * L.n_images / ((double) num_sms () * per_sm * 8);
+        const double eff = rounds / (double) ((uint64_t) rounds + ((double) (uint64_t) rounds < rounds ? 1 : 0));
+        if (tune_g != 99 || glog >= 3 || rounds >= 4.0 || eff >= 0.85)
+            break;
+    }
+
+    const uint64_t n_items = (uint64_t) P.x_tiles * L.n_rows * L.n_images;
+    uint64_t blocks = (n_items + 7) / 8;
+    if (blocks > (uint64_t) num_sms () * per_sm)
+        blocks = (uint64_t) num_sms () * per_sm;
+    dim3 grid ((unsigned) blocks);
+
+    switch (mode)
+    {
+        case BM_P8_P:   return launch_box_mode<BM_P8_P> (P, grid, smem, stream);
+        case BM_P8_U:   return launch_box_mode<BM_P8_U> (P, grid, smem, stream);
+        case BM_P8L_P:  return launch_box_mode<BM_P8L_P> (P, grid, smem, stream);
+        case BM_P8L_U:  return launch_box_mode<BM_P8L_U> (P, grid, smem, stream);
+        case BM_P16_U:  return launch_box_mode<BM_P16_U> (P, grid, smem, stream);
+        default:        return launch_box_mode<BM_P16L_U> (P, grid, smem, stream);
+    }
+}
+
 template <bool S128, bool HBOX, bool VBOX>
 static cudaError_t
 launch_general (const SmolLaunch &L, cudaStream_t stream)
@@ -1760,6 +2192,8 @@ smol_cuda_launch (const SmolLaunch *launch, int kernel_id, void *stream_p, const
 
     if (kernel_id == SMOL_KERNEL_HALF2X && half_eligible (L))
         return (int) launch_half (L, stream);
+    if (kernel_id == SMOL_KERNEL_BOX && box_eligible (L))
+        return (int) launch_box (L, stream);
     if (kernel_id == SMOL_KERNEL_MAG && mag_eligible (L))
         return (int) launch_mag (L, stream);
     if (kernel_id == SMOL_KERNEL_TAPS_DIRECT && taps_eligible (L))
