@@ -1331,6 +1331,8 @@ struct BoxParams
     uint32_t x_tiles;               /* items per output row */
     uint32_t seg_bytes;             /* bytes per staging buffer (multiple of 16) */
     uint32_t alpha_shift, col_shift;/* bit positions in the packed source pixel */
+    uint32_t sel_alpha, sel_c0, sel_c1, sel_c2;     /* PRMT selectors: that byte -> bits 0..7, zeros above */
+    uint32_t acc_fits_24;           /* every accumulator lane stays below 2^24: one-instruction normalisation */
 };
 
 __device__ __forceinline__ void cp_async_16 (uint32_t smem_addr, const void *gptr, uint32_t src_bytes)
@@ -1381,9 +1383,8 @@ box_unpack (uint32_t raw, const BoxParams &P, const uint32_t *__restrict__ sm_in
     }
     else
     {
-        const uint32_t alpha = (raw >> P.alpha_shift) & 0xff;
-        const uint32_t cols = raw >> P.col_shift;
-        uint32_t c[3] = { cols & 0xff, (cols >> 8) & 0xff, (cols >> 16) & 0xff };
+        const uint32_t alpha = __byte_perm (raw, 0, P.sel_alpha);
+        uint32_t c[3] = { __byte_perm (raw, 0, P.sel_c0), __byte_perm (raw, 0, P.sel_c1), __byte_perm (raw, 0, P.sel_c2) };
 
         if constexpr (MODE == BM_P8L_P || MODE == BM_P8L_U)
         {
@@ -1432,23 +1433,35 @@ template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_weight (const Box
     return r;
 }
 
-/* scale_64bpp / scale_128bpp_half (generic:1231-1261), lane by lane */
-template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_scale (const BoxPx<MODE> &acc, uint32_t mul)
+/* scale_64bpp / scale_128bpp_half (generic:1231-1261), lane by lane.
+ * (acc * mul + 2^23) >> 24 == high word of ((acc << 8) * mul + 2^31) when acc < 2^24: one
+ * wide multiply-add instead of a 64-bit add and shift. */
+template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_scale (const BoxPx<MODE> &acc, uint32_t mul, bool fits24)
 {
     BoxPx<MODE> r;
     if constexpr (MODE >= BM_P8L_P)
     {
+        if (fits24)
+        {
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            r.v[i] = (uint32_t) (((uint64_t) acc.v[i] * mul + (1u << 23)) >> 24) & 0xffffu;
+            for (int i = 0; i < 4; i++)
+                r.v[i] = (uint32_t) (((uint64_t) (acc.v[i] << 8) * mul + 0x80000000ull) >> 32) & 0xffffu;
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                r.v[i] = (uint32_t) (((uint64_t) acc.v[i] * mul + (1u << 23)) >> 24) & 0xffffu;
+        }
     }
     else
     {
 #pragma unroll
         for (int i = 0; i < 2; i++)
         {
-            const uint32_t lo = (uint32_t) (((uint64_t) (acc.v[i] & 0xffffu) * mul + (1u << 23)) >> 24) & 0xffu;
-            const uint32_t hi = (uint32_t) (((uint64_t) (acc.v[i] >> 16) * mul + (1u << 23)) >> 24) & 0xffu;
+            /* 16-bit lanes: always below 2^24 */
+            const uint32_t lo = (uint32_t) (((uint64_t) ((acc.v[i] & 0xffffu) << 8) * mul + 0x80000000ull) >> 32) & 0xffu;
+            const uint32_t hi = (uint32_t) (((uint64_t) ((acc.v[i] >> 16) << 8) * mul + 0x80000000ull) >> 32) & 0xffu;
             r.v[i] = lo | (hi << 16);
         }
     }
@@ -1456,7 +1469,7 @@ template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_scale (const BoxP
 }
 
 template <int MODE>
-__global__ void __launch_bounds__ (256)
+__global__ void __launch_bounds__ (256, 5)
 smol_box_kernel (const BoxParams P)
 {
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
@@ -1515,31 +1528,47 @@ smol_box_kernel (const BoxParams P)
 
         const uint8_t *src = P.src + (size_t) img * P.src_image_stride + win0;
 
-        auto prefetch = [&] (uint32_t r, uint32_t slot)
+        /* this lane's first three chunks of the window are the same for every row: work out
+         * their validity once (longer windows take the generic loop) */
+        uint32_t cvalid[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
         {
-            const uint8_t *grow = src + (size_t) r * P.src_pitch;
-            const uint32_t sbase = bufs_addr + slot * P.seg_bytes;
-            for (uint32_t k = lane; k < n_chunks; k += 32)
+            const uint32_t k = lane + 32 * c, ofs = win0 + 16 * k;
+            cvalid[c] = k < n_chunks ? (ofs < row_bytes ? min (16u, row_bytes - ofs) : 0u) : 0xffffffffu;
+        }
+        const uint8_t *grow = src + (size_t) T * P.src_pitch + 16 * lane;
+
+        auto prefetch = [&] (uint32_t slot)
+        {
+            /* copies the row `grow` points at, then advances it to the next row */
+            const uint32_t sbase = bufs_addr + slot * P.seg_bytes + 16 * lane;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                if (cvalid[c] != 0xffffffffu)
+                    /* past the row's end: zero-fill only (source size 0), address kept inside the row */
+                    cp_async_16 (sbase + 512 * c, cvalid[c] ? grow + 512 * c : grow - 16 * lane, cvalid[c]);
+            for (uint32_t k = lane + 96; k < n_chunks; k += 32)
             {
                 const uint32_t ofs = win0 + 16 * k;
                 const uint32_t valid = ofs < row_bytes ? min (16u, row_bytes - ofs) : 0u;
-                /* past the row's end: zero-fill only (source size 0), address kept inside the row */
-                cp_async_16 (sbase + 16 * k, valid ? grow + 16 * k : grow, valid);
+                cp_async_16 (sbase + 16 * (k - lane), valid ? grow + 16 * (k - lane) : grow - 16 * lane, valid);
             }
             cp_async_commit ();
+            grow += P.src_pitch;
         };
 
         BoxPx<MODE> vacc;
 #pragma unroll
         for (int i = 0; i < (S128 ? 4 : 2); i++) vacc.v[i] = 0;
 
-        prefetch (T, 0);
+        prefetch (0);
         for (uint32_t r = T; r <= r_end; r++)
         {
             const uint32_t slot = (r - T) & 1;
             if (r < r_end)
             {
-                prefetch (r + 1, slot ^ 1);
+                prefetch (slot ^ 1);
                 cp_async_wait<1> ();
             }
             else
@@ -1566,7 +1595,7 @@ smol_box_kernel (const BoxParams P)
                     acc.v[i] += __shfl_xor_sync (0xffffffffu, acc.v[i], m);
             }
 
-            BoxPx<MODE> h = box_scale<MODE> (acc, d.span_mul_x);
+            BoxPx<MODE> h = box_scale<MODE> (acc, d.span_mul_x, P.acc_fits_24 != 0);
             if (r == T)
                 h = box_weight<MODE> (h, w1);
             else if (r == B)
@@ -1575,7 +1604,7 @@ smol_box_kernel (const BoxParams P)
             __syncwarp ();      /* everyone is done with this slot before it is refilled */
         }
 
-        const BoxPx<MODE> fin = box_scale<MODE> (vacc, d.span_mul_y);
+        const BoxPx<MODE> fin = box_scale<MODE> (vacc, d.span_mul_y, P.acc_fits_24 != 0);
         if (store)
         {
             uint32_t packed;
@@ -2052,6 +2081,18 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     P.first_row = L.first_row; P.n_rows = L.n_rows; P.n_images = L.n_images;
     P.alpha_shift = d.in_alpha_idx * 8;
     P.col_shift = d.in_col0 * 8;
+    P.sel_alpha = 0x4440u | d.in_alpha_idx;
+    P.sel_c0 = 0x4440u | d.in_col0;
+    P.sel_c1 = 0x4440u | (d.in_col0 + 1u);
+    P.sel_c2 = 0x4440u | (d.in_col0 + 2u);
+    {
+        /* largest lane value after unpack x the longest span (+ 2 edge pixels) on either axis */
+        const uint64_t lane_max = d.mid == SMOL_MID_P8 ? 255 : d.mid == SMOL_MID_P8L ? 2047
+                                  : d.mid == SMOL_MID_P16 ? 0xff80 : 2047 * 255;
+        const uint64_t span_x = d.w_in / d.w_out + 2, span_y = d.h_in / d.h_out + 2;
+        const uint64_t h_max = lane_max * span_x, v_max = (d.mid == SMOL_MID_P8 && !d.storage128 ? 255 : 65535) * span_y;
+        P.acc_fits_24 = h_max < (1u << 24) && v_max < (1u << 24);
+    }
 
     int mode;
     if (d.mid == SMOL_MID_P8)
@@ -2073,8 +2114,8 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     }
 
     /* Lanes per column (G).  Long spans want several lanes per column (8..16 source pixels per
-     * lane per row); beyond that G only grows to create enough work items: load balance is at
-     * warp granularity, so with r = items / resident warps the efficiency is r / ceil (r). */
+     * lane per row).  Every extra lane repeats the per-row overhead (edge pixels, normalisation),
+     * so beyond that G only grows while there are fewer work items than resident warps. */
     static int tune_g = -1;
     if (tune_g < 0)
     {
@@ -2106,8 +2147,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
             occ = 1;
         per_sm = (uint32_t) occ;
         const double rounds = (double) P.x_tiles * L.n_rows * L.n_images / ((double) num_sms () * per_sm * 8);
-        const double eff = rounds / (double) ((uint64_t) rounds + ((double) (uint64_t) rounds < rounds ? 1 : 0));
-        if (tune_g != 99 || glog >= 3 || rounds >= 4.0 || eff >= 0.85)
+        if (tune_g != 99 || glog >= 5 || rounds >= 1.0)
             break;
     }
 
