@@ -28,7 +28,8 @@
 
 #define SMOL_MAX_DEVICES 16
 #define SMOL_MAX_LANES 16
-#define SMOL_TAB_CACHE_MAX 96
+#define SMOL_TAB_CACHE_MAX 192
+#define SMOL_PLAN_CACHE_MAX 64
 
 #define SMOL_EXPORT __attribute__ ((visibility ("default")))
 
@@ -432,9 +433,14 @@ typedef struct
 }
 TabEntry;
 
+#define SMOL_MAX_BANDS 8
+
 typedef struct
 {
-    cudaStream_t stream;
+    cudaStream_t stream;                /* kernels (and everything, for small jobs) */
+    cudaStream_t s_h2d, s_d2h;          /* copy streams of the banded pipeline */
+    cudaEvent_t ev_up[SMOL_MAX_BANDS], ev_done[SMOL_MAX_BANDS];
+    int pipeline_ready;
     void *d_in, *d_out;
     size_t d_in_cap, d_out_cap;
     int busy;
@@ -624,6 +630,108 @@ lane_reserve (void **buf, size_t *cap, size_t need)
  * Context                                                                                    *
  * ------------------------------------------------------------------------------------------ */
 
+/* Plans are immutable and depend only on (types, dimensions, sRGB flag), so they are shared:
+ * a small LRU cache makes repeated smol_scale_simple / smol_scale_new calls on the same geometry
+ * (a stream of video frames, a batch of same-sized thumbnails) skip table construction and keeps
+ * their device tables resident. */
+typedef struct
+{
+    int used;
+    SmolPixelType type_in, type_out;
+    uint32_t w_in, h_in, w_out, h_out;
+    uint8_t with_srgb;
+    int refs;
+    uint64_t stamp;
+    JobPlan plan;
+    TabEntry *tab_x[SMOL_MAX_DEVICES], *tab_y[SMOL_MAX_DEVICES];
+}
+SharedPlan;
+
+static SharedPlan *g_plans[SMOL_PLAN_CACHE_MAX];
+static uint64_t g_plan_clock;
+
+static void
+shared_plan_drop_locked (SharedPlan *sp)
+{
+    int i;
+
+    for (i = 0; i < SMOL_MAX_DEVICES; i++)
+    {
+        if (sp->tab_x[i])
+            sp->tab_x[i]->refs--;
+        if (sp->tab_y[i])
+            sp->tab_y[i]->refs--;
+    }
+    job_plan_clear (&sp->plan);
+    free (sp);
+}
+
+static SharedPlan *
+shared_plan_acquire (SmolPixelType type_in, uint32_t w_in, uint32_t h_in,
+                     SmolPixelType type_out, uint32_t w_out, uint32_t h_out, uint8_t with_srgb)
+{
+    SharedPlan *sp = NULL;
+    int i, free_slot = -1, victim = -1;
+
+    with_srgb = with_srgb ? 1 : 0;
+    pthread_mutex_lock (&g_lock);
+    for (i = 0; i < SMOL_PLAN_CACHE_MAX; i++)
+    {
+        SharedPlan *c = g_plans[i];
+
+        if (!c)
+        {
+            if (free_slot < 0)
+                free_slot = i;
+            continue;
+        }
+        if (c->w_in == w_in && c->h_in == h_in && c->w_out == w_out && c->h_out == h_out
+            && c->type_in == type_in && c->type_out == type_out && c->with_srgb == with_srgb)
+        {
+            sp = c;
+            break;
+        }
+        if (c->refs == 0 && (victim < 0 || c->stamp < g_plans[victim]->stamp))
+            victim = i;
+    }
+    if (!sp)
+    {
+        if (free_slot < 0 && victim >= 0)
+        {
+            shared_plan_drop_locked (g_plans[victim]);
+            g_plans[victim] = NULL;
+            free_slot = victim;
+        }
+        sp = calloc (1, sizeof (*sp));
+        if (!sp)
+            smol_fatal ("out of memory", NULL);
+        sp->type_in = type_in; sp->type_out = type_out;
+        sp->w_in = w_in; sp->h_in = h_in; sp->w_out = w_out; sp->h_out = h_out;
+        sp->with_srgb = with_srgb;
+        job_plan_init (&sp->plan, type_in, w_in, h_in, type_out, w_out, h_out, with_srgb);
+        if (free_slot >= 0)
+        {
+            sp->used = 1;               /* cached */
+            g_plans[free_slot] = sp;
+        }
+        /* else: every slot is pinned by a live context; this plan lives and dies with its context */
+    }
+    sp->refs++;
+    sp->stamp = ++g_plan_clock;
+    pthread_mutex_unlock (&g_lock);
+    return sp;
+}
+
+static void
+shared_plan_release (SharedPlan *sp)
+{
+    pthread_mutex_lock (&g_lock);
+    sp->refs--;
+    if (sp->refs == 0 && !sp->used)
+        shared_plan_drop_locked (sp);
+    pthread_mutex_unlock (&g_lock);
+}
+
 struct SmolScaleCtx
 {
     const char *pixels_in;
@@ -633,11 +741,7 @@ struct SmolScaleCtx
     SmolPostRowFunc *post_row_func;
     void *user_data;
 
-    JobPlan plan;
-
-    /* lazily acquired device-resident tables, one pair per device */
-    pthread_mutex_t lock;
-    TabEntry *tab_x[SMOL_MAX_DEVICES], *tab_y[SMOL_MAX_DEVICES];
+    SharedPlan *sp;
 };
 
 static SmolScaleCtx *
@@ -654,6 +758,8 @@ ctx_new (const void *pixels_in, SmolPixelType pixel_type_in,
     if (width_in == 0 || height_in == 0 || width_out == 0 || height_out == 0
         || width_in > 65535 || height_in > 65535 || width_out > 65535 || height_out > 65535)
         smol_fatal ("image dimensions must be in [1, 65535]", NULL);
+    (void) type_info (pixel_type_in);
+    (void) type_info (pixel_type_out);
 
     ctx->pixels_in = pixels_in;
     ctx->pixels_out = pixels_out;
@@ -663,28 +769,15 @@ ctx_new (const void *pixels_in, SmolPixelType pixel_type_in,
     ctx->pixel_type_out = pixel_type_out;
     ctx->post_row_func = post_row_func;
     ctx->user_data = user_data;
-    pthread_mutex_init (&ctx->lock, NULL);
-    job_plan_init (&ctx->plan, pixel_type_in, width_in, height_in,
-                   pixel_type_out, width_out, height_out, with_srgb);
+    ctx->sp = shared_plan_acquire (pixel_type_in, width_in, height_in,
+                                   pixel_type_out, width_out, height_out, with_srgb);
     return ctx;
 }
 
 static void
 ctx_free (SmolScaleCtx *ctx)
 {
-    int i;
-
-    pthread_mutex_lock (&g_lock);
-    for (i = 0; i < SMOL_MAX_DEVICES; i++)
-    {
-        if (ctx->tab_x[i])
-            ctx->tab_x[i]->refs--;
-        if (ctx->tab_y[i])
-            ctx->tab_y[i]->refs--;
-    }
-    pthread_mutex_unlock (&g_lock);
-    pthread_mutex_destroy (&ctx->lock);
-    job_plan_clear (&ctx->plan);
+    shared_plan_release (ctx->sp);
     free (ctx);
 }
 
@@ -692,21 +785,30 @@ ctx_free (SmolScaleCtx *ctx)
 static void
 ctx_device_tables (SmolScaleCtx *ctx, int dev, const uint32_t **tx, const uint32_t **ty, const SmolDeviceLuts **luts)
 {
-    pthread_mutex_lock (&ctx->lock);
-    if (!ctx->tab_x[dev])
+    SharedPlan *sp = ctx->sp;
+    TabEntry *ex = __atomic_load_n (&sp->tab_x[dev], __ATOMIC_ACQUIRE);
+    TabEntry *ey = __atomic_load_n (&sp->tab_y[dev], __ATOMIC_ACQUIRE);
+
+    if (!ex || !ey)
     {
         DeviceState *ds;
 
         pthread_mutex_lock (&g_lock);
         ds = device_state_locked (dev);
-        ctx->tab_x[dev] = tab_acquire_locked (ds, &ctx->plan.ax);
-        ctx->tab_y[dev] = tab_acquire_locked (ds, &ctx->plan.ay);
+        if (!sp->tab_y[dev])
+        {
+            ex = tab_acquire_locked (ds, &sp->plan.ax);
+            ey = tab_acquire_locked (ds, &sp->plan.ay);
+            __atomic_store_n (&sp->tab_x[dev], ex, __ATOMIC_RELEASE);
+            __atomic_store_n (&sp->tab_y[dev], ey, __ATOMIC_RELEASE);
+        }
+        ex = sp->tab_x[dev];
+        ey = sp->tab_y[dev];
         pthread_mutex_unlock (&g_lock);
     }
-    *tx = ctx->tab_x[dev]->dev;
-    *ty = ctx->tab_y[dev]->dev;
+    *tx = ex->dev;
+    *ty = ey->dev;
     *luts = g_dev[dev].luts;
-    pthread_mutex_unlock (&ctx->lock);
 }
 
 /* ------------------------------------------------------------------------------------------ *
@@ -790,7 +892,7 @@ static void
 do_rows (const SmolScaleCtx *cctx, void *outrows_dest, uint32_t first_row, uint32_t n_rows)
 {
     SmolScaleCtx *ctx = (SmolScaleCtx *) cctx;
-    const SmolJobDesc *d = &ctx->plan.d;
+    const SmolJobDesc *d = &ctx->sp->plan.d;
     const size_t in_row_bytes = (size_t) d->w_in * d->bpp_in;
     const size_t out_row_bytes = (size_t) d->w_out * d->bpp_out;
     PtrClass pc_in, pc_out;
@@ -803,10 +905,14 @@ do_rows (const SmolScaleCtx *cctx, void *outrows_dest, uint32_t first_row, uint3
     if ((uint64_t) first_row + n_rows > d->h_out)
         smol_fatal ("row range outside the output image", NULL);
 
-    pthread_mutex_lock (&g_lock);
-    if (device_count_locked () <= 0)
+    if (__atomic_load_n (&g_device_count, __ATOMIC_ACQUIRE) < 0)
+    {
+        pthread_mutex_lock (&g_lock);
+        (void) device_count_locked ();
+        pthread_mutex_unlock (&g_lock);
+    }
+    if (g_device_count <= 0)
         smol_fatal ("no usable CUDA device (this library has no CPU fallback)", NULL);
-    pthread_mutex_unlock (&g_lock);
 
     pc_in = classify_pointer (ctx->pixels_in);
     pc_out = classify_pointer (outrows_dest);
@@ -842,7 +948,11 @@ do_rows (const SmolScaleCtx *cctx, void *outrows_dest, uint32_t first_row, uint3
         Lane *lane = lane_acquire (dev);
         cudaStream_t s = lane->stream;
 
-        plan_source_rows (&ctx->plan, first_row, n_rows, &r0, &nr);
+        plan_source_rows (&ctx->sp->plan, first_row, n_rows, &r0, &nr);
+
+        const size_t in_pitch = align16 (in_row_bytes), out_pitch = align16 (out_row_bytes);
+        size_t staged_bytes = 0;
+        uint32_t n_bands = 1, rows_per_band, b;
 
         if (pc_in.is_device)
         {
@@ -851,18 +961,12 @@ do_rows (const SmolScaleCtx *cctx, void *outrows_dest, uint32_t first_row, uint3
         }
         else
         {
-            const size_t pitch = align16 (in_row_bytes);
-
-            lane_reserve (&lane->d_in, &lane->d_in_cap, pitch * nr + 16);
-            copy_rows_async (lane->d_in, pitch,
-                             ctx->pixels_in + (size_t) r0 * ctx->rowstride_in, ctx->rowstride_in,
-                             in_row_bytes, nr, cudaMemcpyHostToDevice, s);
-            __atomic_add_fetch (&g_stat_h2d, in_row_bytes * nr, __ATOMIC_RELAXED);
+            lane_reserve (&lane->d_in, &lane->d_in_cap, in_pitch * nr + 16);
             /* the kernel addresses rows from row 0 of the image; only rows [r0, r0 + nr) are read */
-            L.src = (const uint8_t *) lane->d_in - (size_t) r0 * pitch;
-            L.src_pitch = (uint32_t) pitch;
+            L.src = (const uint8_t *) lane->d_in - (size_t) r0 * in_pitch;
+            L.src_pitch = (uint32_t) in_pitch;
+            staged_bytes += in_row_bytes * nr;
         }
-
         if (pc_out.is_device)
         {
             L.dst = (uint8_t *) outrows_dest;
@@ -870,22 +974,97 @@ do_rows (const SmolScaleCtx *cctx, void *outrows_dest, uint32_t first_row, uint3
         }
         else
         {
-            const size_t pitch = align16 (out_row_bytes);
-
-            lane_reserve (&lane->d_out, &lane->d_out_cap, pitch * n_rows + 16);
+            lane_reserve (&lane->d_out, &lane->d_out_cap, out_pitch * n_rows + 16);
             L.dst = (uint8_t *) lane->d_out;
-            L.dst_pitch = (uint32_t) pitch;
+            L.dst_pitch = (uint32_t) out_pitch;
+            staged_bytes += out_row_bytes * n_rows;
         }
 
-        launch_checked (&L, s);
-
-        if (!pc_out.is_device)
+        /* Large host-memory jobs run as a pipeline of row bands: while band b is being scaled,
+         * band b + 1's source rows are already crossing PCIe and band b - 1's output rows are on
+         * their way back (H2D and D2H overlap: the link is full duplex).  Bands share the staged
+         * source image, so each source row is uploaded exactly once. */
+        if (staged_bytes >= ((size_t) 4 << 20) && n_rows >= 2 * SMOL_MAX_BANDS)
         {
-            copy_rows_async (outrows_dest, ctx->rowstride_out, lane->d_out, L.dst_pitch,
-                             out_row_bytes, n_rows, cudaMemcpyDeviceToHost, s);
-            __atomic_add_fetch (&g_stat_d2h, out_row_bytes * n_rows, __ATOMIC_RELAXED);
+            n_bands = (uint32_t) (staged_bytes >> 22);
+            if (n_bands > SMOL_MAX_BANDS)
+                n_bands = SMOL_MAX_BANDS;
+            if (n_bands < 2)
+                n_bands = 2;
         }
-        CK (cudaStreamSynchronize (s));
+        rows_per_band = (n_rows + n_bands - 1) / n_bands;
+
+        if (n_bands > 1 && !lane->pipeline_ready)
+        {
+            CK (cudaStreamCreateWithFlags (&lane->s_h2d, cudaStreamNonBlocking));
+            CK (cudaStreamCreateWithFlags (&lane->s_d2h, cudaStreamNonBlocking));
+            for (b = 0; b < SMOL_MAX_BANDS; b++)
+            {
+                CK (cudaEventCreateWithFlags (&lane->ev_up[b], cudaEventDisableTiming));
+                CK (cudaEventCreateWithFlags (&lane->ev_done[b], cudaEventDisableTiming));
+            }
+            lane->pipeline_ready = 1;
+        }
+
+        {
+            const uint8_t *dst_base = L.dst;
+            uint32_t uploaded_end = r0;     /* source rows [r0, uploaded_end) are on the device */
+            cudaStream_t s_up = n_bands > 1 ? lane->s_h2d : s;
+            cudaStream_t s_down = n_bands > 1 ? lane->s_d2h : s;
+
+            for (b = 0; b < n_bands; b++)
+            {
+                const uint32_t band_first = first_row + b * rows_per_band;
+                uint32_t band_rows, br0, bnr;
+
+                if (band_first >= first_row + n_rows)
+                    break;
+                band_rows = first_row + n_rows - band_first;
+                if (band_rows > rows_per_band)
+                    band_rows = rows_per_band;
+
+                if (!pc_in.is_device)
+                {
+                    plan_source_rows (&ctx->sp->plan, band_first, band_rows, &br0, &bnr);
+                    if (br0 + bnr > uploaded_end)
+                    {
+                        const uint32_t from = uploaded_end, cnt = br0 + bnr - uploaded_end;
+
+                        copy_rows_async ((char *) lane->d_in + (size_t) (from - r0) * in_pitch, in_pitch,
+                                         ctx->pixels_in + (size_t) from * ctx->rowstride_in, ctx->rowstride_in,
+                                         in_row_bytes, cnt, cudaMemcpyHostToDevice, s_up);
+                        __atomic_add_fetch (&g_stat_h2d, in_row_bytes * cnt, __ATOMIC_RELAXED);
+                        uploaded_end = br0 + bnr;
+                    }
+                    if (n_bands > 1)
+                    {
+                        CK (cudaEventRecord (lane->ev_up[b], s_up));
+                        CK (cudaStreamWaitEvent (s, lane->ev_up[b], 0));
+                    }
+                }
+
+                L.first_row = band_first;
+                L.n_rows = band_rows;
+                L.dst = (uint8_t *) dst_base + (size_t) (band_first - first_row) * L.dst_pitch;
+                launch_checked (&L, s);
+
+                if (!pc_out.is_device)
+                {
+                    if (n_bands > 1)
+                    {
+                        CK (cudaEventRecord (lane->ev_done[b], s));
+                        CK (cudaStreamWaitEvent (s_down, lane->ev_done[b], 0));
+                    }
+                    copy_rows_async ((char *) outrows_dest + (size_t) (band_first - first_row) * ctx->rowstride_out,
+                                     ctx->rowstride_out, L.dst, L.dst_pitch,
+                                     out_row_bytes, band_rows, cudaMemcpyDeviceToHost, s_down);
+                    __atomic_add_fetch (&g_stat_d2h, out_row_bytes * band_rows, __ATOMIC_RELAXED);
+                }
+            }
+            if (n_bands > 1)
+                CK (cudaStreamSynchronize (s_down));
+            CK (cudaStreamSynchronize (s));
+        }
 
         if (ctx->post_row_func)
         {
@@ -1051,7 +1230,7 @@ smol_cuda_scale_images (const void *pixels_in, size_t image_stride_in,
         CK (cudaSetDevice (dev));
 
     memset (&L, 0, sizeof (L));
-    L.d = ctx->plan.d;
+    L.d = ctx->sp->plan.d;
     L.src_pitch = rowstride_in;
     L.dst_pitch = rowstride_out;
     L.src_image_stride = image_stride_in;
@@ -1113,7 +1292,7 @@ smol_cuda_band_source_rows (const SmolScaleCtx *scale_ctx,
                             uint32_t first_outrow, uint32_t n_outrows,
                             uint32_t *first_inrow, uint32_t *n_inrows)
 {
-    plan_source_rows (&scale_ctx->plan, first_outrow, n_outrows, first_inrow, n_inrows);
+    plan_source_rows (&scale_ctx->sp->plan, first_outrow, n_outrows, first_inrow, n_inrows);
 }
 
 SMOL_EXPORT void
