@@ -245,6 +245,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel", type=int, default=0, help="force a kernel family (testing)")
+    ap.add_argument("--shard", default="frames", choices=["frames", "rows"],
+                    help="multi-GPU partitioning: frames (weak scaling, default) or output row bands of every "
+                         "frame (strong scaling; BASELINE configs 3 and 4)")
     ap.add_argument("--batched", action="store_true",
                     help="submit all frames of a step in one launch (smol_cuda_scale_images); default for cfg5")
     args = ap.parse_args()
@@ -284,8 +287,18 @@ def main():
     stream = torch.cuda.Stream(device=device)
     batched = cfg_name == "cfg5" or args.batched
 
+    from smolscale_b200 import sharding
+    band_first, band_rows = sharding.row_band(ho, rank, world) if args.shard == "rows" else (0, ho)
+
     def enqueue_step():
-        if batched:
+        if args.shard == "rows":
+            # every rank renders its own output row band of every frame (smol_scale_batch_full on a
+            # shared-geometry context); it reads only that band's source rows + filter halo
+            for f in range(frames):
+                ctx = sb.ScaleCtx(d_in.data_ptr() + f * in_bytes, ti, wi, hi, si, None, to, wo, ho, so, srgb)
+                ctx.batch_full(d_out.data_ptr() + f * out_bytes + band_first * so, band_first, band_rows)
+                ctx.destroy()
+        elif batched:
             sb.scale_images(d_in.data_ptr(), in_bytes, ti, wi, hi, si, d_out.data_ptr(), out_bytes, to, wo, ho, so,
                             srgb, frames)
         else:
@@ -348,7 +361,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
-    value = world * frames * wo * ho / 1e6 / (ms_per_step / 1e3)
+    strong = args.shard == "rows"
+    value = (1 if strong else world) * frames * wo * ho / 1e6 / (ms_per_step / 1e3)
 
     # ---- correctness guard: one frame of the timed output against the oracle (rank 0) ----
     check = None
@@ -358,8 +372,8 @@ def main():
             f = frames - 1
             src = d_in[f * in_bytes:(f + 1) * in_bytes].cpu().numpy()
             got = d_out[f * out_bytes:(f + 1) * out_bytes].cpu().numpy()
-            y0 = ho // 2
-            rows = min(4, ho - y0)
+            y0 = band_first + band_rows // 2
+            rows = min(4, band_first + band_rows - y0)
             want = oracle.restatement().scale_rows(src, ti, wi, hi, si, to, wo, ho, y0, rows, so, srgb)
             check = bool(np.array_equal(want, got[y0 * so:y0 * so + want.size]))
         except Exception as e:
@@ -407,19 +421,23 @@ def main():
     peak, peak_src = measured_peak_gbs()
     kernel_ms = elapsed_ms / (args.steps * launches_per_step)
     alg_per_launch = alg_bytes * (frames if batched else 1)
+    if strong:
+        alg_per_launch = alg_bytes / world
     achieved = alg_per_launch / (kernel_ms * 1e-3) / 1e9
     plan = sb.plan_query(ti, wi, hi, to, wo, ho, srgb)
 
     line = {
         "metric": "output Mpix/s", "value": round(value, 2), "unit": "Mpix/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
         "config": {"workload": desc, "config": cfg_name, "frames_per_step_per_gpu": frames,
                    "types": "%s->%s" % (TYPE_NAMES[ti], TYPE_NAMES[to]), "srgb": srgb,
                    "l2": "inputs larger than L2: %d distinct frames = %.0f MB in + %.0f MB out per step"
                          % (frames, frames * in_bytes / 1e6, frames * out_bytes / 1e6),
                    "launch": "cuda graph replay" if graph is not None else "direct stream-ordered launches",
-                   "kernel": plan["kernel_name"], "parallelism": "frames sharded across %d GPU(s), no collective" % world},
+                   "kernel": plan["kernel_name"], "parallelism": ("output row bands of every frame sharded across %d GPU(s), no collective" if strong
+                                   else "frames sharded across %d GPU(s), no collective") % world},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": round(kernel_ms, 6)},
