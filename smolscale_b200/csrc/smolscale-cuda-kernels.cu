@@ -1332,6 +1332,8 @@ struct BoxParams
     uint32_t seg_bytes;             /* bytes per staging buffer (multiple of 16) */
     uint32_t alpha_shift, col_shift;/* bit positions in the packed source pixel */
     uint32_t sel_alpha, sel_c0, sel_c1, sel_c2;     /* PRMT selectors: that byte -> bits 0..7, zeros above */
+    uint32_t sel_ac0, sel_ac1, sel_ac2;             /* PRMT selectors: (alpha << 8) | colour byte */
+    const uint16_t *unpack_tab;                     /* TAB variants: 65536-entry composite unpack table */
     uint32_t acc_fits_24;           /* every accumulator lane stays below 2^24: one-instruction normalisation */
 };
 
@@ -1352,11 +1354,29 @@ template <int N> __device__ __forceinline__ void cp_async_wait ()
  * 64bpp modes: v[0] = bytes 0 and 2, v[1] = bytes 1 and 3 of the source pixel (16-bit lanes). */
 template <int MODE> struct BoxPx { uint32_t v[MODE >= BM_P8L_P ? 4 : 2]; };
 
-template <int MODE>
+/* LUTM: how the data tables are held in shared memory.
+ *   0: one copy each (gathers suffer bank conflicts on random data)
+ *   1: the 64K-entry composite table (fewest instructions, conflicts remain)
+ *   2: 32 lane-private copies, word (index * 32 + lane): every lane always hits its own bank,
+ *      so the gathers are conflict-free whatever the data */
+template <int MODE, int LUTM>
 __device__ __forceinline__ BoxPx<MODE>
-box_unpack (uint32_t raw, const BoxParams &P, const uint32_t *__restrict__ sm_inv8, const uint32_t *__restrict__ sm_from)
+box_unpack (uint32_t raw, const BoxParams &P, const uint32_t *__restrict__ sm_inv8, const uint32_t *__restrict__ sm_from,
+            const uint16_t *__restrict__ sm_tab)
 {
     BoxPx<MODE> r;
+    constexpr int LSH = LUTM == 2 ? 5 : 0;      /* replicated tables: sm_inv8 / sm_from already point at this lane's column */
+
+    if constexpr (LUTM == 1)
+    {
+        /* one shared-memory lookup per channel: the whole unpremultiply -> from_srgb ->
+         * premultiply chain was folded into a 64K-entry table indexed by (alpha, value) */
+        r.v[0] = __byte_perm (raw, 0, P.sel_alpha);
+        r.v[1] = sm_tab[__byte_perm (raw, 0, P.sel_ac0)];
+        r.v[2] = sm_tab[__byte_perm (raw, 0, P.sel_ac1)];
+        r.v[3] = sm_tab[__byte_perm (raw, 0, P.sel_ac2)];
+        return r;
+    }
 
     if constexpr (MODE == BM_P8_P)
     {
@@ -1392,7 +1412,7 @@ box_unpack (uint32_t raw, const BoxParams &P, const uint32_t *__restrict__ sm_in
             if constexpr (MODE == BM_P8L_P)
             {
                 /* unpremultiply (generic:227-236): sm_inv8 = inv_div_p8 << 3, result = byte 2 */
-                const uint32_t inv8 = sm_inv8[alpha];
+                const uint32_t inv8 = sm_inv8[alpha << LSH];
 #pragma unroll
                 for (int i = 0; i < 3; i++)
                     c[i] = __byte_perm (c[i] * inv8, 0, 0x4442);
@@ -1400,7 +1420,7 @@ box_unpack (uint32_t raw, const BoxParams &P, const uint32_t *__restrict__ sm_in
 #pragma unroll
             for (int i = 0; i < 3; i++)
             {
-                const uint32_t lin = sm_from[c[i]];                 /* generic:185-199 */
+                const uint32_t lin = sm_from[c[i] << LSH];          /* generic:185-199 */
                 c[i] = (lin * m + (m - 1)) >> 11;                   /* ((lin + 1) * m - 1) >> 11 <= 2040, generic:261-269 */
             }
             r.v[0] = alpha;
@@ -1409,7 +1429,7 @@ box_unpack (uint32_t raw, const BoxParams &P, const uint32_t *__restrict__ sm_in
         {
 #pragma unroll
             for (int i = 0; i < 3; i++)
-                c[i] = (MODE == BM_P16L_U ? sm_from[c[i]] : c[i]) * alpha;  /* generic:616-660, :708-752 */
+                c[i] = (MODE == BM_P16L_U ? sm_from[c[i] << LSH] : c[i]) * alpha;  /* generic:616-660, :708-752 */
             r.v[0] = (alpha << 8) | 0x80;
         }
         r.v[1] = c[0]; r.v[2] = c[1]; r.v[3] = c[2];
@@ -1468,28 +1488,64 @@ template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_scale (const BoxP
     return r;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__ (256, 5)
+/* LUTM = 1: one big CTA per SM (128 KB composite table + the warps' staging buffers);
+ * LUTM = 2: 512-thread CTAs with lane-replicated LUTs; LUTM = 0: 256-thread CTAs, plain LUTs. */
+template <int MODE, int LUTM>
+__global__ void __launch_bounds__ (LUTM == 1 ? 1024 : LUTM == 2 ? 512 : 256, LUTM == 1 ? 1 : LUTM == 2 ? 2 : 5)
 smol_box_kernel (const BoxParams P)
 {
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
-    __shared__ uint32_t sm_inv8[256];
-    __shared__ uint32_t sm_from[256];
+    __shared__ uint32_t sm_inv8_plain[LUTM == 0 ? 256 : 1];
+    __shared__ uint32_t sm_from_plain[LUTM == 0 ? 256 : 1];
     constexpr bool S128 = MODE >= BM_P8L_P;
+    constexpr bool TAB = LUTM == 1;
+    constexpr bool NEED_INV = MODE == BM_P8L_P;
+    constexpr bool NEED_FROM = MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U;
+    constexpr uint32_t REP_BYTES = LUTM == 2 ? ((NEED_INV ? 32768u : 0u) + (NEED_FROM ? 32768u : 0u)) : 0u;
+    constexpr uint32_t TAB_BYTES = TAB ? 65536 * 2 : REP_BYTES;
     const SmolJobDesc &d = P.d;
+    const uint16_t *sm_tab = reinterpret_cast<const uint16_t *> (sm_dyn);
+    const uint32_t *sm_inv8 = sm_inv8_plain, *sm_from = sm_from_plain;
 
     pdl_launch_dependents ();
-    if constexpr (MODE == BM_P8L_P)
-        sm_inv8[threadIdx.x] = P.luts->inv_div_p8[threadIdx.x] << 3;
-    if constexpr (MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U)
-        sm_from[threadIdx.x] = P.luts->from_srgb[threadIdx.x];
+    if constexpr (TAB)
+    {
+        /* library-owned constant data: may be fetched before the dependency wait */
+        const uint32_t tab_addr = (uint32_t) __cvta_generic_to_shared (sm_dyn);
+        for (uint32_t i = threadIdx.x; i < TAB_BYTES / 16; i += blockDim.x)
+            cp_async_16 (tab_addr + 16 * i, reinterpret_cast<const uint8_t *> (P.unpack_tab) + 16 * i, 16);
+        cp_async_commit ();
+        cp_async_wait<0> ();
+    }
+    else if constexpr (LUTM == 2)
+    {
+        /* word (index * 32 + lane) of each replicated table */
+        uint32_t *rep_from = reinterpret_cast<uint32_t *> (sm_dyn);
+        uint32_t *rep_inv = rep_from + (NEED_FROM ? 8192 : 0);
+        for (uint32_t i = threadIdx.x; i < 8192; i += blockDim.x)
+        {
+            if constexpr (NEED_FROM)
+                rep_from[i] = P.luts->from_srgb[i >> 5];
+            if constexpr (NEED_INV)
+                rep_inv[i] = P.luts->inv_div_p8[i >> 5] << 3;
+        }
+        sm_from = rep_from + (threadIdx.x & 31);
+        sm_inv8 = rep_inv + (threadIdx.x & 31);
+    }
+    else
+    {
+        if constexpr (NEED_INV)
+            sm_inv8_plain[threadIdx.x] = P.luts->inv_div_p8[threadIdx.x] << 3;
+        if constexpr (NEED_FROM)
+            sm_from_plain[threadIdx.x] = P.luts->from_srgb[threadIdx.x];
+    }
     __syncthreads ();
     pdl_wait ();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t G = 1u << P.lanes_per_col_log2, g = lane & (G - 1);
     const uint32_t cols_per_item = 32u >> P.lanes_per_col_log2;
-    uint8_t *bufs = sm_dyn + (size_t) warp * 2 * P.seg_bytes;
+    uint8_t *bufs = sm_dyn + TAB_BYTES + (size_t) warp * 2 * P.seg_bytes;
     const uint32_t bufs_addr = (uint32_t) __cvta_generic_to_shared (bufs);
     const uint32_t row_bytes = d.w_in * 4;
 
@@ -1582,12 +1638,12 @@ smol_box_kernel (const BoxParams P)
 
             /* whole pixels hL + 1 .. hR - 1, interleaved over the G lanes of the column */
             for (uint32_t j = hL + 1 + g; j < hR; j += G)
-                box_add<MODE> (acc, box_unpack<MODE> (px[j], P, sm_inv8, sm_from));
+                box_add<MODE> (acc, box_unpack<MODE, LUTM> (px[j], P, sm_inv8, sm_from, sm_tab));
             /* edge pixels: lane 0 of the column takes the left one, the last lane the right one */
             if (g == 0)
-                box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE> (px[hL], P, sm_inv8, sm_from), wl));
+                box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE, LUTM> (px[hL], P, sm_inv8, sm_from, sm_tab), wl));
             if (g == G - 1 && wr > 0)
-                box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE> (px[hR], P, sm_inv8, sm_from), wr));
+                box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE, LUTM> (px[hR], P, sm_inv8, sm_from, sm_tab), wr));
             for (uint32_t m = G >> 1; m; m >>= 1)
             {
 #pragma unroll
@@ -2054,19 +2110,6 @@ launch_mag (const SmolLaunch &L, cudaStream_t stream)
     return launch_mag_fmt<4, 4, false, false, false> (M, grid, smem, stream);
 }
 
-template <int MODE>
-static cudaError_t
-launch_box_mode (const BoxParams &P, dim3 grid, size_t smem, cudaStream_t stream)
-{
-    if (smem > 48 * 1024)
-    {
-        cudaError_t err = cudaFuncSetAttribute (smol_box_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (err != cudaSuccess)
-            return err;
-    }
-    return launch_pdl (smol_box_kernel<MODE>, P, grid, dim3 (256), smem, stream);
-}
-
 static cudaError_t
 launch_box (const SmolLaunch &L, cudaStream_t stream)
 {
@@ -2085,6 +2128,10 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     P.sel_c0 = 0x4440u | d.in_col0;
     P.sel_c1 = 0x4440u | (d.in_col0 + 1u);
     P.sel_c2 = 0x4440u | (d.in_col0 + 2u);
+    P.sel_ac0 = 0x4400u | ((uint32_t) d.in_alpha_idx << 4) | d.in_col0;
+    P.sel_ac1 = 0x4400u | ((uint32_t) d.in_alpha_idx << 4) | (d.in_col0 + 1u);
+    P.sel_ac2 = 0x4400u | ((uint32_t) d.in_alpha_idx << 4) | (d.in_col0 + 2u);
+    P.unpack_tab = d.in_unassoc ? L.p8l_from_u : L.p8l_from_p;
     {
         /* largest lane value after unpack x the longest span (+ 2 edge pixels) on either axis */
         const uint64_t lane_max = d.mid == SMOL_MID_P8 ? 255 : d.mid == SMOL_MID_P8L ? 2047
@@ -2102,33 +2149,44 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     else
         mode = d.mid == SMOL_MID_P16 ? BM_P16_U : BM_P16L_U;
 
+    static int tune_g = -1, tune_lut = -1;
+    if (tune_g < 0)
+    {
+        const char *e = getenv ("SMOL_BOX_G_LOG2"), *t = getenv ("SMOL_BOX_LUTM");
+        tune_g = e ? atoi (e) : 99;
+        tune_lut = t ? atoi (t) : 2;
+    }
+    /* table placement (see box_unpack): modes without gathers need none */
+    const bool has_lut = mode == BM_P8L_P || mode == BM_P8L_U || mode == BM_P16L_U;
+    int lutm = has_lut ? tune_lut : 0;
+    if (lutm == 1 && d.mid != SMOL_MID_P8L)
+        lutm = 2;
+
+#define BOX_KERNEL_FOR(M) (lutm == 1 ? (const void *) smol_box_kernel<M, 1> : lutm == 2 ? (const void *) smol_box_kernel<M, 2> : (const void *) smol_box_kernel<M, 0>)
     const void *fn;
     switch (mode)
     {
-        case BM_P8_P:   fn = (const void *) smol_box_kernel<BM_P8_P>; break;
-        case BM_P8_U:   fn = (const void *) smol_box_kernel<BM_P8_U>; break;
-        case BM_P8L_P:  fn = (const void *) smol_box_kernel<BM_P8L_P>; break;
-        case BM_P8L_U:  fn = (const void *) smol_box_kernel<BM_P8L_U>; break;
-        case BM_P16_U:  fn = (const void *) smol_box_kernel<BM_P16_U>; break;
-        default:        fn = (const void *) smol_box_kernel<BM_P16L_U>; break;
+        case BM_P8_P:   fn = (const void *) smol_box_kernel<BM_P8_P, 0>; break;
+        case BM_P8_U:   fn = (const void *) smol_box_kernel<BM_P8_U, 0>; break;
+        case BM_P8L_P:  fn = BOX_KERNEL_FOR (BM_P8L_P); break;
+        case BM_P8L_U:  fn = BOX_KERNEL_FOR (BM_P8L_U); break;
+        case BM_P16_U:  fn = (const void *) smol_box_kernel<BM_P16_U, 0>; break;
+        default:        fn = lutm == 2 ? (const void *) smol_box_kernel<BM_P16L_U, 2> : (const void *) smol_box_kernel<BM_P16L_U, 0>; break;
     }
+#undef BOX_KERNEL_FOR
 
     /* Lanes per column (G).  Long spans want several lanes per column (8..16 source pixels per
      * lane per row).  Every extra lane repeats the per-row overhead (edge pixels, normalisation),
      * so beyond that G only grows while there are fewer work items than resident warps. */
-    static int tune_g = -1;
-    if (tune_g < 0)
-    {
-        const char *e = getenv ("SMOL_BOX_G_LOG2");
-        tune_g = e ? atoi (e) : 99;
-    }
     const uint32_t ratio = d.w_in / d.w_out;
     uint32_t glog = 0;
     while (glog < 5 && ratio >= (16u << glog))
         glog++;
 
+    const size_t lut_bytes = lutm == 1 ? 131072
+                             : lutm == 2 ? (mode == BM_P8L_P ? 65536 : 32768) : 0;
     size_t smem = 0;
-    uint32_t per_sm = 1;
+    uint32_t per_sm = 1, warps_per_cta = lutm == 2 ? 16 : 8;
     for (;; glog++)
     {
         if (tune_g != 99)
@@ -2139,33 +2197,44 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         /* staging buffer: the widest segment an item can need, + alignment slack */
         const uint64_t seg_px = ((uint64_t) cols * d.w_in + d.w_out - 1) / d.w_out + 3;
         P.seg_bytes = (uint32_t) ((seg_px * 4 + 32 + 15) & ~(uint64_t) 15);
-        smem = (size_t) 8 * 2 * P.seg_bytes;
+        if (lutm == 1)
+        {
+            /* one CTA per SM: as many warps as fit beside the 128 KB table */
+            const size_t room = 220 * 1024 - lut_bytes;
+            warps_per_cta = (uint32_t) (room / (2 * (size_t) P.seg_bytes));
+            warps_per_cta = warps_per_cta > 32 ? 32 : warps_per_cta < 4 ? 4 : warps_per_cta;
+        }
+        smem = lut_bytes + (size_t) warps_per_cta * 2 * P.seg_bytes;
         if (smem > 48 * 1024)
-            cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, 256, smem) != cudaSuccess || occ < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, (int) warps_per_cta * 32, smem) != cudaSuccess || occ < 1)
             occ = 1;
         per_sm = (uint32_t) occ;
-        const double rounds = (double) P.x_tiles * L.n_rows * L.n_images / ((double) num_sms () * per_sm * 8);
+        const double rounds = (double) P.x_tiles * L.n_rows * L.n_images / ((double) num_sms () * per_sm * warps_per_cta);
         if (tune_g != 99 || glog >= 5 || rounds >= 1.0)
             break;
     }
 
     const uint64_t n_items = (uint64_t) P.x_tiles * L.n_rows * L.n_images;
-    uint64_t blocks = (n_items + 7) / 8;
+    uint64_t blocks = (n_items + warps_per_cta - 1) / warps_per_cta;
     if (blocks > (uint64_t) num_sms () * per_sm)
         blocks = (uint64_t) num_sms () * per_sm;
-    dim3 grid ((unsigned) blocks);
+    dim3 grid ((unsigned) blocks), block (warps_per_cta * 32);
 
+#define BOX_LAUNCH(M, LM) launch_pdl (smol_box_kernel<M, LM>, P, grid, block, smem, stream)
+#define BOX_LAUNCH_LUT(M) (lutm == 1 ? BOX_LAUNCH (M, 1) : lutm == 2 ? BOX_LAUNCH (M, 2) : BOX_LAUNCH (M, 0))
     switch (mode)
     {
-        case BM_P8_P:   return launch_box_mode<BM_P8_P> (P, grid, smem, stream);
-        case BM_P8_U:   return launch_box_mode<BM_P8_U> (P, grid, smem, stream);
-        case BM_P8L_P:  return launch_box_mode<BM_P8L_P> (P, grid, smem, stream);
-        case BM_P8L_U:  return launch_box_mode<BM_P8L_U> (P, grid, smem, stream);
-        case BM_P16_U:  return launch_box_mode<BM_P16_U> (P, grid, smem, stream);
-        default:        return launch_box_mode<BM_P16L_U> (P, grid, smem, stream);
+        case BM_P8_P:   return BOX_LAUNCH (BM_P8_P, 0);
+        case BM_P8_U:   return BOX_LAUNCH (BM_P8_U, 0);
+        case BM_P8L_P:  return BOX_LAUNCH_LUT (BM_P8L_P);
+        case BM_P8L_U:  return BOX_LAUNCH_LUT (BM_P8L_U);
+        case BM_P16_U:  return BOX_LAUNCH (BM_P16_U, 0);
+        default:        return lutm == 2 ? BOX_LAUNCH (BM_P16L_U, 2) : BOX_LAUNCH (BM_P16L_U, 0);
     }
+#undef BOX_LAUNCH_LUT
+#undef BOX_LAUNCH
 }
 
 template <bool S128, bool HBOX, bool VBOX>

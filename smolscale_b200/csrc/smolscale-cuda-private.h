@@ -85,6 +85,10 @@ typedef struct
     uint32_t n_images;
     const uint32_t *tab_x, *tab_y;      /* device */
     const SmolDeviceLuts *luts;         /* device */
+    /* device, 65536 x uint16 each, index (alpha << 8) | c: the whole 8-bit -> premultiplied
+     * 11-bit linear unpack chain of one channel (reference generic:555-568 / :591-614) from a
+     * premultiplied resp. unassociated source, precomputed once per device from the LUTs */
+    const uint16_t *p8l_from_p, *p8l_from_u;
     uint32_t first_row, n_rows;         /* output rows to produce */
     /* launch shape chosen by the host */
     uint32_t lanes_per_col;             /* general kernel: threads cooperating on one output column (power of two) */

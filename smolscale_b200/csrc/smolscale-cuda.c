@@ -451,6 +451,7 @@ typedef struct
 {
     int ready;
     SmolDeviceLuts *luts;
+    uint16_t *p8l_from_p, *p8l_from_u;
     TabEntry tabs[SMOL_TAB_CACHE_MAX];
     uint64_t clock;
     Lane lanes[SMOL_MAX_LANES];
@@ -516,6 +517,31 @@ device_state_locked (int dev)
         CK (cudaMalloc ((void **) &ds->luts, sizeof (*h)));
         CK (cudaMemcpy (ds->luts, h, sizeof (*h), cudaMemcpyHostToDevice));
         free (h);
+        {
+            /* Composite per-channel unpack tables for linear light, index (alpha << 8) | c:
+             *   premultiplied source (reference generic:555-568): unpremultiply with the p8 table,
+             *   from_srgb, premultiply to 11 bits;  unassociated source (generic:591-614): the
+             *   last two steps only.  Pure functions of the six LUTs above. */
+            uint16_t *tp = malloc (65536 * sizeof (uint16_t)), *tu = malloc (65536 * sizeof (uint16_t));
+            uint32_t a, c;
+
+            if (!tp || !tu)
+                smol_fatal ("out of memory", NULL);
+            for (a = 0; a < 256; a++)
+                for (c = 0; c < 256; c++)
+                {
+                    const uint32_t m = (a << 3) + 1;
+                    const uint32_t u = ((c * smol_lut_inv_div_p8[a]) >> 13) & 0xff;
+                    tp[(a << 8) | c] = (uint16_t) ((((smol_lut_from_srgb[u] + 1u) * m - 1u) >> 11) & 0x7ff);
+                    tu[(a << 8) | c] = (uint16_t) ((((smol_lut_from_srgb[c] + 1u) * m - 1u) >> 11) & 0x7ff);
+                }
+            CK (cudaMalloc ((void **) &ds->p8l_from_p, 65536 * sizeof (uint16_t)));
+            CK (cudaMalloc ((void **) &ds->p8l_from_u, 65536 * sizeof (uint16_t)));
+            CK (cudaMemcpy (ds->p8l_from_p, tp, 65536 * sizeof (uint16_t), cudaMemcpyHostToDevice));
+            CK (cudaMemcpy (ds->p8l_from_u, tu, 65536 * sizeof (uint16_t), cudaMemcpyHostToDevice));
+            free (tp);
+            free (tu);
+        }
         ds->ready = 1;
     }
     return ds;
@@ -783,8 +809,10 @@ ctx_free (SmolScaleCtx *ctx)
 
 /* Device must be current. */
 static void
-ctx_device_tables (SmolScaleCtx *ctx, int dev, const uint32_t **tx, const uint32_t **ty, const SmolDeviceLuts **luts)
+ctx_device_tables (SmolScaleCtx *ctx, int dev, SmolLaunch *L)
 {
+    const uint32_t **tx = &L->tab_x, **ty = &L->tab_y;
+    const SmolDeviceLuts **luts = &L->luts;
     SharedPlan *sp = ctx->sp;
     TabEntry *ex = __atomic_load_n (&sp->tab_x[dev], __ATOMIC_ACQUIRE);
     TabEntry *ey = __atomic_load_n (&sp->tab_y[dev], __ATOMIC_ACQUIRE);
@@ -809,6 +837,8 @@ ctx_device_tables (SmolScaleCtx *ctx, int dev, const uint32_t **tx, const uint32
     *tx = ex->dev;
     *ty = ey->dev;
     *luts = g_dev[dev].luts;
+    L->p8l_from_p = g_dev[dev].p8l_from_p;
+    L->p8l_from_u = g_dev[dev].p8l_from_u;
 }
 
 /* ------------------------------------------------------------------------------------------ *
@@ -932,7 +962,7 @@ do_rows (const SmolScaleCtx *cctx, void *outrows_dest, uint32_t first_row, uint3
     L.n_images = 1;
     L.first_row = first_row;
     L.n_rows = n_rows;
-    ctx_device_tables (ctx, dev, &L.tab_x, &L.tab_y, &L.luts);
+    ctx_device_tables (ctx, dev, &L);
 
     if (pc_in.is_device && pc_out.is_device && !ctx->post_row_func)
     {
@@ -1237,7 +1267,7 @@ smol_cuda_scale_images (const void *pixels_in, size_t image_stride_in,
     L.dst_image_stride = image_stride_out;
     L.first_row = 0;
     L.n_rows = height_out;
-    ctx_device_tables (ctx, dev, &L.tab_x, &L.tab_y, &L.luts);
+    ctx_device_tables (ctx, dev, &L);
 
     /* grid.z carries the image index and is limited to 65535 */
     for (done = 0; done < n_images; done += 65535)
