@@ -1083,6 +1083,192 @@ smol_taps_kernel (const TapsParams P)
     }
 }
 
+/* Specialised taps kernel for the no-halving case (HH = VH = 0: every plain bilinear resize
+ * between 1:2 and any magnification, and copy / one), formats resolved at compile time:
+ * BI / BO bytes per pixel in / out, IU / OU unassociated alpha in / out, AF alpha is byte 0 of a
+ * 32bpp source pixel (else byte 3).  Same thread mapping as smol_taps_kernel; the arithmetic
+ * uses the PRMT folds: a horizontal tap is 2 multiply-adds + 1 PRMT per word, a vertical tap +
+ * repack is 4 multiply-adds + 1 PRMT per pixel. */
+struct Taps0Params
+{
+    TapsParams t;
+    uint32_t acc_prmt_sel;          /* (acc_a, acc_b) high bytes -> destination byte order */
+    uint32_t src_u32_ok;            /* 32bpp source rows are 4-byte aligned */
+};
+
+template <int BI, bool IU, bool AF>
+__device__ __forceinline__ Px16 taps0_fetch (const uint8_t *row, uint32_t x, bool u32_ok)
+{
+    const uint8_t *p = row + (size_t) x * BI;
+    uint32_t raw;
+    if (BI == 4 && u32_ok)
+        raw = __ldg (reinterpret_cast<const uint32_t *> (p));
+    else
+    {
+        raw = (uint32_t) __ldg (p) | ((uint32_t) __ldg (p + 1) << 8) | ((uint32_t) __ldg (p + 2) << 16);
+        raw |= BI == 4 ? ((uint32_t) __ldg (p + 3) << 24) : 0xff000000u;
+    }
+    Px16 r;
+    r.a = raw & 0x00ff00ffu;
+    r.b = (raw >> 8) & 0x00ff00ffu;
+    if constexpr (IU)
+    {
+        /* premultiply: ((c + 1) * (alpha + 1) - 1) >> 8, alpha lane untouched (generic:238-244) */
+        if constexpr (AF)
+        {
+            const uint32_t alpha = raw & 0xff, m = alpha + 1;
+            r.a = (((((r.a & 0x00ff0000u) + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff0000u) | alpha;
+            r.b = (((r.b + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff00ffu;
+        }
+        else
+        {
+            const uint32_t alpha = raw >> 24, m = alpha + 1;
+            r.a = (((r.a + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff00ffu;
+            r.b = (((((r.b & 0x000000ffu) + 0x00010001u) * m - 0x00010001u) >> 8) & 0x000000ffu) | (alpha << 16);
+        }
+    }
+    return r;
+}
+
+template <int BI, int BO, bool IU, bool OU, bool AF>
+__global__ void __launch_bounds__ (256)
+smol_taps0_kernel (const Taps0Params T)
+{
+    __shared__ uint32_t sm_inv[256];
+    const TapsParams &P = T.t;
+
+    pdl_launch_dependents ();
+    if constexpr (OU)
+    {
+        for (uint32_t i = threadIdx.y * blockDim.x + threadIdx.x; i < 256; i += blockDim.x * blockDim.y)
+            sm_inv[i] = __ldg (&P.inv_div_p8[i]) << 3;
+        __syncthreads ();
+    }
+
+    const uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const uint32_t strip = blockIdx.y * blockDim.y + threadIdx.y;
+    const uint32_t yl0 = strip * P.rows_per_thread;
+    if (x >= P.w_out || yl0 >= P.n_rows)
+        return;
+    const uint32_t yl1 = min (yl0 + P.rows_per_thread, P.n_rows);
+    const uint32_t n_px = min (4u, P.w_out - x);
+
+    /* this thread's four horizontal taps never change */
+    uint32_t op[4], oq[4], Fx[4];
+#pragma unroll
+    for (int o = 0; o < 4; o++)
+    {
+        const uint32_t e = __ldg (&P.tab_x[min (x + o, P.w_out - 1)]);
+        op[o] = SMOL_TAB_OFS (e);
+        oq[o] = min (op[o] + 1, P.w_in - 1);
+        Fx[o] = SMOL_TAB_F (e);
+    }
+
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
+    uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl0 * P.dst_pitch + (size_t) x * BO;
+    const bool fast_store = n_px == 4 && (reinterpret_cast<uintptr_t> (dst) & (BO == 4 ? 15 : 3)) == 0
+                            && (P.dst_pitch & (BO == 4 ? 15 : 3)) == 0;
+    const bool u32_ok = T.src_u32_ok != 0;
+
+    pdl_wait ();
+
+    auto hrow = [&] (uint32_t r, Px16 out[4])
+    {
+        const uint8_t *row = src + (size_t) r * P.src_pitch;
+#pragma unroll
+        for (int o = 0; o < 4; o++)
+        {
+            const Px16 p = taps0_fetch<BI, IU, AF> (row, op[o], u32_ok);
+            const Px16 q = taps0_fetch<BI, IU, AF> (row, oq[o], u32_ok);
+            const uint32_t F = Fx[o], G = 256u - F;
+            out[o].a = __byte_perm (p.a * F + q.a * G, 0, 0x4341);     /* (acc >> 8) & 0x00ff00ff */
+            out[o].b = __byte_perm (p.b * F + q.b * G, 0, 0x4341);
+        }
+    };
+
+    uint32_t idx0 = 0xffffffffu, idx1 = 0xffffffffu;
+    Px16 row0[4], row1[4];
+#pragma unroll
+    for (int o = 0; o < 4; o++)
+        row0[o].a = row0[o].b = row1[o].a = row1[o].b = 0;
+
+    for (uint32_t yl = yl0; yl < yl1; yl++, dst += P.dst_pitch)
+    {
+        const uint32_t e = __ldg (&P.tab_y[P.first_row + yl]);
+        const uint32_t r0 = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e), G = 256u - F;
+        const uint32_t r1 = min (r0 + 1, P.h_in - 1);
+
+        /* two-row cache (generic:1648-1682); F == 256 needs only the top row, F == 0 only the bottom */
+        if (F != 0 && r0 != idx0)
+        {
+            if (r0 == idx1)
+            {
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+                {
+                    const Px16 t = row0[o]; row0[o] = row1[o]; row1[o] = t;
+                }
+                idx1 = idx0;
+            }
+            else
+                hrow (r0, row0);
+            idx0 = r0;
+        }
+        if (F != 256 && r1 != idx1)
+        {
+            if (r1 == idx0)
+            {
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+                    row1[o] = row0[o];
+            }
+            else
+                hrow (r1, row1);
+            idx1 = r1;
+        }
+
+        uint32_t out[4];
+#pragma unroll
+        for (int o = 0; o < 4; o++)
+        {
+            /* an unused operand is multiplied by zero (its cache slot may be stale) */
+            const uint32_t ta = F != 0 ? row0[o].a : 0, tb = F != 0 ? row0[o].b : 0;
+            const uint32_t ba = F != 256 ? row1[o].a : 0, bb = F != 256 ? row1[o].b : 0;
+            const uint32_t acc_a = ta * F + ba * G, acc_b = tb * F + bb * G;
+            if constexpr (OU)
+            {
+                uint32_t v = __byte_perm (acc_a, acc_b, 0x7351);      /* source byte order */
+                v = half_unpremul<AF> (v, sm_inv);
+                out[o] = __byte_perm (v, 0, P.prmt_sel);
+            }
+            else
+                out[o] = __byte_perm (acc_a, acc_b, T.acc_prmt_sel);
+        }
+
+        if constexpr (BO == 4)
+        {
+            if (fast_store)
+                *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
+            else
+                for (uint32_t o = 0; o < n_px; o++)
+                    store_raw_px (dst + 4 * o, out[o], 4);
+        }
+        else
+        {
+            if (fast_store)
+            {
+                uint32_t *d32 = reinterpret_cast<uint32_t *> (dst);
+                d32[0] = __byte_perm (out[0], out[1], 0x4210);
+                d32[1] = __byte_perm (out[1], out[2], 0x5421);
+                d32[2] = __byte_perm (out[2], out[3], 0x6542);
+            }
+            else
+                for (uint32_t o = 0; o < n_px; o++)
+                    store_raw_px (dst + 3 * o, out[o], 3);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ *
  * "mag" kernel: vertical magnification (h_out > h_in; BASELINE config 4), bilinear / copy / one *
  * horizontally, 8-bit premultiplied intermediate.                                              *
@@ -1975,6 +2161,16 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
         rpt >>= 1;
     if (d.h_in <= d.h_out && rpt < 4)
         rpt = 4;                        /* magnification: row reuse matters more than thread count */
+    {
+        static int tune_rpt = -1;
+        if (tune_rpt < 0)
+        {
+            const char *e = getenv ("SMOL_TAPS_RPT");
+            tune_rpt = e ? atoi (e) : 0;
+        }
+        if (tune_rpt > 0)
+            rpt = (uint32_t) tune_rpt;
+    }
     P.rows_per_thread = rpt;
 
     uint32_t bx = 32;
@@ -1986,6 +2182,40 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
         by = strips;
     dim3 block (bx, by);
     dim3 grid ((unsigned) ((x_threads + bx - 1) / bx), (strips + by - 1) / by, L.n_images);
+
+    if (d.h_halvings == 0 && d.v_halvings == 0)
+    {
+        Taps0Params T;
+        static const uint32_t acc_byte[4] = { 1, 5, 3, 7 };
+        uint32_t sel = 0;
+
+        T.t = P;
+        for (int j = 0; j < 4; j++)
+            sel |= acc_byte[(P.prmt_sel >> (4 * j)) & 3] << (4 * j);
+        T.acc_prmt_sel = sel;
+        T.src_u32_ok = (reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
+                       && (L.src_image_stride & 3) == 0;
+        const bool af = d.in_alpha_idx == 0;
+#define TAPS0(BI, BO, IU, OU, AF) launch_pdl (smol_taps0_kernel<BI, BO, IU, OU, AF>, T, grid, block, 0, stream)
+        if (d.bpp_in == 3)
+        {
+            if (d.bpp_out == 3)     return TAPS0 (3, 3, false, false, false);
+            if (d.out_unassoc)      return TAPS0 (3, 4, false, true, false);
+            return TAPS0 (3, 4, false, false, false);
+        }
+        if (d.in_unassoc)
+        {
+            if (d.bpp_out == 3)
+                return af ? TAPS0 (4, 3, true, false, true) : TAPS0 (4, 3, true, false, false);
+            return af ? TAPS0 (4, 4, true, false, true) : TAPS0 (4, 4, true, false, false);
+        }
+        if (d.bpp_out == 3)
+            return TAPS0 (4, 3, false, false, false);
+        if (d.out_unassoc)
+            return af ? TAPS0 (4, 4, false, true, true) : TAPS0 (4, 4, false, true, false);
+        return TAPS0 (4, 4, false, false, false);
+#undef TAPS0
+    }
 
     if (d.h_halvings == 0)
         return launch_taps_h<0> (P, d.v_halvings, grid, block, stream);
