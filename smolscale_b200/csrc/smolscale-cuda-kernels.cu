@@ -288,6 +288,43 @@ __device__ __forceinline__ void store_raw_px (uint8_t *o, uint32_t v, uint32_t b
         o[3] = (uint8_t) (v >> 24);
 }
 
+/* Cold path: n_px (< 4 or unaligned destination) pixels stored one at a time.  The loop is kept
+ * rolled on purpose: a rolled loop stays a real branch, so the hot path does not have to issue its
+ * instructions predicated off. */
+__device__ __forceinline__ void store_px_slow (uint8_t *dst, const uint32_t out[4], uint32_t n_px, uint32_t bpp)
+{
+#pragma unroll 1
+    for (uint32_t o = 0; o < n_px; o++)
+    {
+        const uint32_t v = o == 0 ? out[0] : o == 1 ? out[1] : o == 2 ? out[2] : out[3];
+        store_raw_px (dst + (size_t) bpp * o, v, bpp);
+    }
+}
+
+/* Four finished pixels to a 4-byte-aligned destination row: one 128-bit store when the address
+ * allows, else 32-bit stores (32bpp); three 32-bit stores (24bpp). */
+template <int BO>
+__device__ __forceinline__ void store_px4_aligned (uint8_t *dst, const uint32_t out[4])
+{
+    if constexpr (BO == 4)
+    {
+        if ((reinterpret_cast<uintptr_t> (dst) & 15) == 0)
+            *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
+        else
+        {
+            uint32_t *d32 = reinterpret_cast<uint32_t *> (dst);
+            d32[0] = out[0]; d32[1] = out[1]; d32[2] = out[2]; d32[3] = out[3];
+        }
+    }
+    else
+    {
+        uint32_t *d32 = reinterpret_cast<uint32_t *> (dst);
+        d32[0] = __byte_perm (out[0], out[1], 0x4210);
+        d32[1] = __byte_perm (out[1], out[2], 0x5421);
+        d32[2] = __byte_perm (out[2], out[3], 0x6542);
+    }
+}
+
 __device__ __forceinline__ uint4 ldg_nc_v4 (const void *p)
 {
     uint4 r;
@@ -1096,12 +1133,12 @@ struct Taps0Params
     uint32_t src_u32_ok;            /* 32bpp source rows are 4-byte aligned */
 };
 
-template <int BI, bool IU, bool AF>
-__device__ __forceinline__ Px16 taps0_fetch (const uint8_t *row, uint32_t x, bool u32_ok)
+template <int BI, bool IU, bool AF, bool U32OK>
+__device__ __forceinline__ Px16 taps0_fetch (const uint8_t *row, uint32_t x)
 {
     const uint8_t *p = row + (size_t) x * BI;
     uint32_t raw;
-    if (BI == 4 && u32_ok)
+    if constexpr (BI == 4 && U32OK)
         raw = __ldg (reinterpret_cast<const uint32_t *> (p));
     else
     {
@@ -1130,7 +1167,9 @@ __device__ __forceinline__ Px16 taps0_fetch (const uint8_t *row, uint32_t x, boo
     return r;
 }
 
-template <int BI, int BO, bool IU, bool OU, bool AF>
+/* FASTIO: 32bpp source rows and all destination rows are 4-byte aligned; resolved at compile
+ * time so the byte-wise fallbacks cost nothing on the fast path. */
+template <int BI, int BO, bool IU, bool OU, bool AF, bool FASTIO>
 __global__ void __launch_bounds__ (256)
 smol_taps0_kernel (const Taps0Params T)
 {
@@ -1166,75 +1205,34 @@ smol_taps0_kernel (const Taps0Params T)
 
     const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
     uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl0 * P.dst_pitch + (size_t) x * BO;
-    const bool fast_store = n_px == 4 && (reinterpret_cast<uintptr_t> (dst) & (BO == 4 ? 15 : 3)) == 0
-                            && (P.dst_pitch & (BO == 4 ? 15 : 3)) == 0;
-    const bool u32_ok = T.src_u32_ok != 0;
+    const bool fast_store = FASTIO && n_px == 4;
 
     pdl_wait ();
 
     auto hrow = [&] (uint32_t r, Px16 out[4])
     {
-        const uint8_t *row = src + (size_t) r * P.src_pitch;
+        const uint8_t *row = src + (size_t) min (r, P.h_in - 1) * P.src_pitch;
 #pragma unroll
         for (int o = 0; o < 4; o++)
         {
-            const Px16 p = taps0_fetch<BI, IU, AF> (row, op[o], u32_ok);
-            const Px16 q = taps0_fetch<BI, IU, AF> (row, oq[o], u32_ok);
+            const Px16 p = taps0_fetch<BI, IU, AF, FASTIO> (row, op[o]);
+            const Px16 q = taps0_fetch<BI, IU, AF, FASTIO> (row, oq[o]);
             const uint32_t F = Fx[o], G = 256u - F;
             out[o].a = __byte_perm (p.a * F + q.a * G, 0, 0x4341);     /* (acc >> 8) & 0x00ff00ff */
             out[o].b = __byte_perm (p.b * F + q.b * G, 0, 0x4341);
         }
     };
 
-    uint32_t idx0 = 0xffffffffu, idx1 = 0xffffffffu;
-    Px16 row0[4], row1[4];
-#pragma unroll
-    for (int o = 0; o < 4; o++)
-        row0[o].a = row0[o].b = row1[o].a = row1[o].b = 0;
-
-    for (uint32_t yl = yl0; yl < yl1; yl++, dst += P.dst_pitch)
+    /* one output row from the two cached source rows; F = 256 / F = 0 (copy, one, table tails)
+     * come out exact from the same formula, so there are no special cases */
+    auto emit = [&] (const Px16 top[4], const Px16 bot[4], uint32_t F)
     {
-        const uint32_t e = __ldg (&P.tab_y[P.first_row + yl]);
-        const uint32_t r0 = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e), G = 256u - F;
-        const uint32_t r1 = min (r0 + 1, P.h_in - 1);
-
-        /* two-row cache (generic:1648-1682); F == 256 needs only the top row, F == 0 only the bottom */
-        if (F != 0 && r0 != idx0)
-        {
-            if (r0 == idx1)
-            {
-#pragma unroll
-                for (int o = 0; o < 4; o++)
-                {
-                    const Px16 t = row0[o]; row0[o] = row1[o]; row1[o] = t;
-                }
-                idx1 = idx0;
-            }
-            else
-                hrow (r0, row0);
-            idx0 = r0;
-        }
-        if (F != 256 && r1 != idx1)
-        {
-            if (r1 == idx0)
-            {
-#pragma unroll
-                for (int o = 0; o < 4; o++)
-                    row1[o] = row0[o];
-            }
-            else
-                hrow (r1, row1);
-            idx1 = r1;
-        }
-
+        const uint32_t G = 256u - F;
         uint32_t out[4];
 #pragma unroll
         for (int o = 0; o < 4; o++)
         {
-            /* an unused operand is multiplied by zero (its cache slot may be stale) */
-            const uint32_t ta = F != 0 ? row0[o].a : 0, tb = F != 0 ? row0[o].b : 0;
-            const uint32_t ba = F != 256 ? row1[o].a : 0, bb = F != 256 ? row1[o].b : 0;
-            const uint32_t acc_a = ta * F + ba * G, acc_b = tb * F + bb * G;
+            const uint32_t acc_a = top[o].a * F + bot[o].a * G, acc_b = top[o].b * F + bot[o].b * G;
             if constexpr (OU)
             {
                 uint32_t v = __byte_perm (acc_a, acc_b, 0x7351);      /* source byte order */
@@ -1244,28 +1242,63 @@ smol_taps0_kernel (const Taps0Params T)
             else
                 out[o] = __byte_perm (acc_a, acc_b, T.acc_prmt_sel);
         }
-
-        if constexpr (BO == 4)
-        {
-            if (fast_store)
-                *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
-            else
-                for (uint32_t o = 0; o < n_px; o++)
-                    store_raw_px (dst + 4 * o, out[o], 4);
-        }
+        if (fast_store)
+            store_px4_aligned<BO> (dst, out);
         else
+            store_px_slow (dst, out, n_px, BO);
+        dst += P.dst_pitch;
+    };
+
+    /* Walk the strip with the two source rows ping-ponging between register sets A and B (the
+     * reference's two-row cache, generic:1648-1682, without ever moving a row): in phase A the
+     * top row is in A and the bottom one in B, in phase B the other way round. */
+    const uint32_t *ty = P.tab_y + P.first_row;
+    uint32_t yl = yl0;
+    uint32_t e = __ldg (&ty[yl]);
+    uint32_t r = SMOL_TAB_OFS (e);
+    Px16 A[4], B[4];
+    hrow (r, A);
+    hrow (r + 1, B);
+
+    for (;;)
+    {
+        /* phase A */
+        do
         {
-            if (fast_store)
-            {
-                uint32_t *d32 = reinterpret_cast<uint32_t *> (dst);
-                d32[0] = __byte_perm (out[0], out[1], 0x4210);
-                d32[1] = __byte_perm (out[1], out[2], 0x5421);
-                d32[2] = __byte_perm (out[2], out[3], 0x6542);
-            }
-            else
-                for (uint32_t o = 0; o < n_px; o++)
-                    store_raw_px (dst + 3 * o, out[o], 3);
+            emit (A, B, SMOL_TAB_F (e));
+            if (++yl >= yl1)
+                return;
+            e = __ldg (&ty[yl]);
         }
+        while (SMOL_TAB_OFS (e) == r);
+        if (SMOL_TAB_OFS (e) != r + 1)
+        {
+            r = SMOL_TAB_OFS (e);
+            hrow (r, A);
+            hrow (r + 1, B);
+            continue;
+        }
+        r++;
+        hrow (r + 1, A);
+
+        /* phase B */
+        do
+        {
+            emit (B, A, SMOL_TAB_F (e));
+            if (++yl >= yl1)
+                return;
+            e = __ldg (&ty[yl]);
+        }
+        while (SMOL_TAB_OFS (e) == r);
+        if (SMOL_TAB_OFS (e) != r + 1)
+        {
+            r = SMOL_TAB_OFS (e);
+            hrow (r, A);
+            hrow (r + 1, B);
+            continue;
+        }
+        r++;
+        hrow (r + 1, B);
     }
 }
 
@@ -1298,7 +1331,7 @@ struct MagParams
 
 /* Format traits resolved at compile time: BI / BO bytes per pixel in / out, IU / OU unassociated
  * alpha in / out, AF alpha is the first byte of a 32bpp source pixel (else the last). */
-template <int BI, int BO, bool IU, bool OU, bool AF>
+template <int BI, int BO, bool IU, bool OU, bool AF, bool FASTIO>
 __global__ void __launch_bounds__ (256)
 smol_mag_kernel (const MagParams M)
 {
@@ -1346,7 +1379,7 @@ smol_mag_kernel (const MagParams M)
             {
                 const uint8_t *p = row + c * BI;
                 uint32_t raw;
-                if (BI == 4 && M.src_u32_ok)
+                if constexpr (BI == 4 && FASTIO)
                     raw = __ldg (reinterpret_cast<const uint32_t *> (p));
                 else
                 {
@@ -1418,8 +1451,7 @@ smol_mag_kernel (const MagParams M)
     const uint32_t n_px = min (4u, x1 - x);
     const uint32_t *ha = sm_ha + 4 * g, *hb = sm_hb + 4 * g;
     uint8_t *dst = dst_img + (size_t) (yl0 + ry_begin) * P.dst_pitch + (size_t) x * BO;
-    const bool fast_store = n_px == 4 && (reinterpret_cast<uintptr_t> (dst) & (BO == 4 ? 15 : 3)) == 0
-                            && (P.dst_pitch & (BO == 4 ? 15 : 3)) == 0;
+    const bool fast_store = FASTIO && n_px == 4;
     uint32_t ry = ry_begin;
     uint32_t e = ry < ry_end ? sm_ty[ry] : 0;
     while (ry < ry_end)
@@ -1452,27 +1484,10 @@ smol_mag_kernel (const MagParams M)
                     out[o] = __byte_perm (acc_a[o], acc_b[o], M.acc_prmt_sel);
             }
 
-            if constexpr (BO == 4)
-            {
-                if (fast_store)
-                    *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
-                else
-                    for (uint32_t o = 0; o < n_px; o++)
-                        store_raw_px (dst + 4 * o, out[o], 4);
-            }
+            if (fast_store)
+                store_px4_aligned<BO> (dst, out);
             else
-            {
-                if (fast_store)
-                {
-                    uint32_t *d32 = reinterpret_cast<uint32_t *> (dst);
-                    d32[0] = __byte_perm (out[0], out[1], 0x4210);
-                    d32[1] = __byte_perm (out[1], out[2], 0x5421);
-                    d32[2] = __byte_perm (out[2], out[3], 0x6542);
-                }
-                else
-                    for (uint32_t o = 0; o < n_px; o++)
-                        store_raw_px (dst + 3 * o, out[o], 3);
-            }
+                store_px_slow (dst, out, n_px, BO);
 
             ry++;
             dst += P.dst_pitch;
@@ -2193,10 +2208,13 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
         for (int j = 0; j < 4; j++)
             sel |= acc_byte[(P.prmt_sel >> (4 * j)) & 3] << (4 * j);
         T.acc_prmt_sel = sel;
-        T.src_u32_ok = (reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
-                       && (L.src_image_stride & 3) == 0;
+        T.src_u32_ok = d.bpp_in == 3 || ((reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
+                                         && (L.src_image_stride & 3) == 0);
         const bool af = d.in_alpha_idx == 0;
-#define TAPS0(BI, BO, IU, OU, AF) launch_pdl (smol_taps0_kernel<BI, BO, IU, OU, AF>, T, grid, block, 0, stream)
+        const bool fastio = T.src_u32_ok && (reinterpret_cast<uintptr_t> (L.dst) & 3) == 0
+                            && (L.dst_pitch & 3) == 0 && (L.dst_image_stride & 3) == 0;
+#define TAPS0(BI, BO, IU, OU, AF) (fastio ? launch_pdl (smol_taps0_kernel<BI, BO, IU, OU, AF, true>, T, grid, block, 0, stream) \
+                                          : launch_pdl (smol_taps0_kernel<BI, BO, IU, OU, AF, false>, T, grid, block, 0, stream))
         if (d.bpp_in == 3)
         {
             if (d.bpp_out == 3)     return TAPS0 (3, 3, false, false, false);
@@ -2243,18 +2261,27 @@ taps_params_init (TapsParams &P, const SmolLaunch &L)
     P.prmt_sel = byte_order_selector (d);
 }
 
-template <int BI, int BO, bool IU, bool OU, bool AF>
+template <int BI, int BO, bool IU, bool OU, bool AF, bool FASTIO>
 static cudaError_t
-launch_mag_fmt (const MagParams &M, dim3 grid, size_t smem, cudaStream_t stream)
+launch_mag_fmt_io (const MagParams &M, dim3 grid, size_t smem, cudaStream_t stream)
 {
     if (smem > 48 * 1024)
     {
-        cudaError_t err = cudaFuncSetAttribute (smol_mag_kernel<BI, BO, IU, OU, AF>,
+        cudaError_t err = cudaFuncSetAttribute (smol_mag_kernel<BI, BO, IU, OU, AF, FASTIO>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (err != cudaSuccess)
             return err;
     }
-    return launch_pdl (smol_mag_kernel<BI, BO, IU, OU, AF>, M, grid, dim3 (256), smem, stream);
+    return launch_pdl (smol_mag_kernel<BI, BO, IU, OU, AF, FASTIO>, M, grid, dim3 (256), smem, stream);
+}
+
+template <int BI, int BO, bool IU, bool OU, bool AF>
+static cudaError_t
+launch_mag_fmt (const MagParams &M, dim3 grid, size_t smem, cudaStream_t stream)
+{
+    /* src_u32_ok doubles as "fast I/O": set by launch_mag only if the destination is aligned too */
+    return M.src_u32_ok ? launch_mag_fmt_io<BI, BO, IU, OU, AF, true> (M, grid, smem, stream)
+                        : launch_mag_fmt_io<BI, BO, IU, OU, AF, false> (M, grid, smem, stream);
 }
 
 static cudaError_t
@@ -2304,8 +2331,10 @@ launch_mag (const SmolLaunch &L, cudaStream_t stream)
         M.u_cw *= 2;
         M.u_cw_log2++;
     }
-    M.src_u32_ok = (reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
-                   && (L.src_image_stride & 3) == 0;
+    M.src_u32_ok = (d.bpp_in == 3 || ((reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
+                                      && (L.src_image_stride & 3) == 0))
+                   && (reinterpret_cast<uintptr_t> (L.dst) & 3) == 0
+                   && (L.dst_pitch & 3) == 0 && (L.dst_image_stride & 3) == 0;
 
     /* (acc_a, acc_b) -> destination bytes: source byte s lives in byte 1 (s = 0), 5 (s = 1),
      * 3 (s = 2), 7 (s = 3) of the PRMT operand pair */
