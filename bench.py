@@ -62,6 +62,25 @@ def alpha_index(t):
     return 3 if (t & 3) < 2 else 0
 
 
+def ncu_traffic_bytes(cfg_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this config's kernel, from the
+    committed `ncu --set full` capture summary (profiles/rNN_ncu_full_<cfg>.txt; newest round wins)."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_%s.txt" % cfg_name))):
+        best = path
+    if not best:
+        return None, None
+    total = 0.0
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in open(best):
+        m = re.match(r"\s*dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+        if m:
+            total += float(m.group(2)) * unit.get(m.group(3), 1.0)
+    return int(total), os.path.relpath(best, ROOT)
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -425,6 +444,9 @@ def main():
         alg_per_launch = alg_bytes / world
     achieved = alg_per_launch / (kernel_ms * 1e-3) / 1e9
     plan = sb.plan_query(ti, wi, hi, to, wo, ho, srgb)
+    traffic, traffic_src = ncu_traffic_bytes(cfg_name)
+    if traffic is not None and batched:
+        traffic = None      # the capture is of the per-frame launch
 
     line = {
         "metric": "output Mpix/s", "value": round(value, 2), "unit": "Mpix/s",
@@ -439,7 +461,8 @@ def main():
                    "kernel": plan["kernel_name"], "parallelism": ("output row bands of every frame sharded across %d GPU(s), no collective" if strong
                                    else "frames sharded across %d GPU(s), no collective") % world},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": round(kernel_ms, 6)},
         "e2e": e2e,
         "gpu_launches": int(gpu_launches),
