@@ -1691,7 +1691,7 @@ template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_scale (const BoxP
 
 /* LUTM = 1: one big CTA per SM (128 KB composite table + the warps' staging buffers);
  * LUTM = 2: 512-thread CTAs with lane-replicated LUTs; LUTM = 0: 256-thread CTAs, plain LUTs. */
-template <int MODE, int LUTM>
+template <int MODE, int LUTM, int BI>
 __global__ void __launch_bounds__ (LUTM == 1 ? 1024 : LUTM == 2 ? 512 : 256, LUTM == 1 ? 1 : LUTM == 2 ? 2 : 5)
 smol_box_kernel (const BoxParams P)
 {
@@ -1748,7 +1748,7 @@ smol_box_kernel (const BoxParams P)
     const uint32_t cols_per_item = 32u >> P.lanes_per_col_log2;
     uint8_t *bufs = sm_dyn + TAB_BYTES + (size_t) warp * 2 * P.seg_bytes;
     const uint32_t bufs_addr = (uint32_t) __cvta_generic_to_shared (bufs);
-    const uint32_t row_bytes = d.w_in * 4;
+    const uint32_t row_bytes = d.w_in * BI;
 
     const uint32_t items_per_image = P.x_tiles * P.n_rows;
     const uint32_t n_items = items_per_image * P.n_images;
@@ -1773,8 +1773,8 @@ smol_box_kernel (const BoxParams P)
         /* segment of the source rows the whole item reads, as an aligned byte window */
         const uint32_t sx0 = SMOL_TAB_OFS (__ldg (&P.tab_x[x_first]));
         const uint32_t sx1 = SMOL_TAB_OFS (__ldg (&P.tab_x[x_last + 1]));
-        const uint32_t win0 = (sx0 * 4) & ~15u;
-        const uint32_t n_chunks = (((sx1 + 1) * 4 + 15) & ~15u) - win0 >> 4;
+        const uint32_t win0 = (sx0 * BI) & ~15u;
+        const uint32_t n_chunks = (((sx1 + 1) * BI + 15) & ~15u) - win0 >> 4;
 
         /* vertical span (generic:2112-2161 / :2198-2260) */
         const uint32_t ey0 = __ldg (&P.tab_y[y]), ey1 = __ldg (&P.tab_y[y + 1]);
@@ -1832,19 +1832,31 @@ smol_box_kernel (const BoxParams P)
                 cp_async_wait<0> ();
             __syncwarp ();
 
-            const uint32_t *px = reinterpret_cast<const uint32_t *> (bufs + slot * P.seg_bytes) - (win0 >> 2);
+            const uint32_t *words = reinterpret_cast<const uint32_t *> (bufs + slot * P.seg_bytes);
+            /* source pixel j of this row: 32bpp straight from the window; 24bpp as a funnel shift
+             * over the two words that hold its three bytes, alpha byte forced to 0xff */
+            auto fetch = [&] (uint32_t j) -> uint32_t
+            {
+                if constexpr (BI == 4)
+                    return words[j - (win0 >> 2)];
+                else
+                {
+                    const uint32_t b = j * 3 - win0;
+                    return __funnelshift_r (words[b >> 2], words[(b >> 2) + 1], (b & 3) * 8) | 0xff000000u;
+                }
+            };
             BoxPx<MODE> acc;
 #pragma unroll
             for (int i = 0; i < (S128 ? 4 : 2); i++) acc.v[i] = 0;
 
             /* whole pixels hL + 1 .. hR - 1, interleaved over the G lanes of the column */
             for (uint32_t j = hL + 1 + g; j < hR; j += G)
-                box_add<MODE> (acc, box_unpack<MODE, LUTM> (px[j], P, sm_inv8, sm_from, sm_tab));
+                box_add<MODE> (acc, box_unpack<MODE, LUTM> (fetch (j), P, sm_inv8, sm_from, sm_tab));
             /* edge pixels: lane 0 of the column takes the left one, the last lane the right one */
             if (g == 0)
-                box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE, LUTM> (px[hL], P, sm_inv8, sm_from, sm_tab), wl));
+                box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE, LUTM> (fetch (hL), P, sm_inv8, sm_from, sm_tab), wl));
             if (g == G - 1 && wr > 0)
-                box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE, LUTM> (px[hR], P, sm_inv8, sm_from, sm_tab), wr));
+                box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE, LUTM> (fetch (hR), P, sm_inv8, sm_from, sm_tab), wr));
             for (uint32_t m = G >> 1; m; m >>= 1)
             {
 #pragma unroll
@@ -1876,7 +1888,7 @@ smol_box_kernel (const BoxParams P)
             {
                 /* fin holds the pixel's four bytes in source order */
                 const uint32_t bytes = fin.v[0] | (fin.v[1] << 8);
-                const uint32_t alpha = d.in_alpha_idx == 0xff ? 0xffu : (bytes >> P.alpha_shift) & 0xff;
+                const uint32_t alpha = (bytes >> P.alpha_shift) & 0xff;
                 const uint32_t cols = bytes >> P.col_shift;
                 Px<false> o;
                 o.w[0] = (uint64_t) alpha | ((uint64_t) (cols & 0xff) << 16) | ((uint64_t) ((cols >> 8) & 0xff) << 32)
@@ -1946,7 +1958,7 @@ box_eligible (const SmolLaunch &L)
 {
     const SmolJobDesc &d = L.d;
 
-    if (d.h_kind != SMOL_AXIS_BOX || d.v_kind != SMOL_AXIS_BOX || d.bpp_in != 4)
+    if (d.h_kind != SMOL_AXIS_BOX || d.v_kind != SMOL_AXIS_BOX)
         return false;
     if (d.mid == SMOL_MID_P8 && d.storage128)
         return false;                   /* ratio > 255 without linear light: general kernel */
@@ -2381,15 +2393,17 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     P.src_image_stride = L.src_image_stride; P.dst_image_stride = L.dst_image_stride;
     P.tab_x = L.tab_x; P.tab_y = L.tab_y; P.luts = L.luts;
     P.first_row = L.first_row; P.n_rows = L.n_rows; P.n_images = L.n_images;
-    P.alpha_shift = d.in_alpha_idx * 8;
+    /* a 24bpp source pixel is fetched with a forced 0xff in byte 3 */
+    const uint32_t alpha_idx = d.in_alpha_idx == 0xff ? 3u : d.in_alpha_idx;
+    P.alpha_shift = alpha_idx * 8;
     P.col_shift = d.in_col0 * 8;
-    P.sel_alpha = 0x4440u | d.in_alpha_idx;
+    P.sel_alpha = 0x4440u | alpha_idx;
     P.sel_c0 = 0x4440u | d.in_col0;
     P.sel_c1 = 0x4440u | (d.in_col0 + 1u);
     P.sel_c2 = 0x4440u | (d.in_col0 + 2u);
-    P.sel_ac0 = 0x4400u | ((uint32_t) d.in_alpha_idx << 4) | d.in_col0;
-    P.sel_ac1 = 0x4400u | ((uint32_t) d.in_alpha_idx << 4) | (d.in_col0 + 1u);
-    P.sel_ac2 = 0x4400u | ((uint32_t) d.in_alpha_idx << 4) | (d.in_col0 + 2u);
+    P.sel_ac0 = 0x4400u | (alpha_idx << 4) | d.in_col0;
+    P.sel_ac1 = 0x4400u | (alpha_idx << 4) | (d.in_col0 + 1u);
+    P.sel_ac2 = 0x4400u | (alpha_idx << 4) | (d.in_col0 + 2u);
     P.unpack_tab = d.in_unassoc ? L.p8l_from_u : L.p8l_from_p;
     {
         /* largest lane value after unpack x the longest span (+ 2 edge pixels) on either axis */
@@ -2421,18 +2435,21 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     if (lutm == 1 && d.mid != SMOL_MID_P8L)
         lutm = 2;
 
-#define BOX_KERNEL_FOR(M) (lutm == 1 ? (const void *) smol_box_kernel<M, 1> : lutm == 2 ? (const void *) smol_box_kernel<M, 2> : (const void *) smol_box_kernel<M, 0>)
+    const bool bi3 = d.bpp_in == 3;     /* 24bpp sources are never unassociated: modes P8_P / P8L_P only */
+#define BOX_KERNEL_FOR(M) (lutm == 1 ? (const void *) smol_box_kernel<M, 1, 4> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 4> : (const void *) smol_box_kernel<M, 0, 4>)
+#define BOX_KERNEL_FOR3(M) (lutm == 1 ? (const void *) smol_box_kernel<M, 1, 3> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 3> : (const void *) smol_box_kernel<M, 0, 3>)
     const void *fn;
     switch (mode)
     {
-        case BM_P8_P:   fn = (const void *) smol_box_kernel<BM_P8_P, 0>; break;
-        case BM_P8_U:   fn = (const void *) smol_box_kernel<BM_P8_U, 0>; break;
-        case BM_P8L_P:  fn = BOX_KERNEL_FOR (BM_P8L_P); break;
+        case BM_P8_P:   fn = bi3 ? (const void *) smol_box_kernel<BM_P8_P, 0, 3> : (const void *) smol_box_kernel<BM_P8_P, 0, 4>; break;
+        case BM_P8_U:   fn = (const void *) smol_box_kernel<BM_P8_U, 0, 4>; break;
+        case BM_P8L_P:  fn = bi3 ? BOX_KERNEL_FOR3 (BM_P8L_P) : BOX_KERNEL_FOR (BM_P8L_P); break;
         case BM_P8L_U:  fn = BOX_KERNEL_FOR (BM_P8L_U); break;
-        case BM_P16_U:  fn = (const void *) smol_box_kernel<BM_P16_U, 0>; break;
-        default:        fn = lutm == 2 ? (const void *) smol_box_kernel<BM_P16L_U, 2> : (const void *) smol_box_kernel<BM_P16L_U, 0>; break;
+        case BM_P16_U:  fn = (const void *) smol_box_kernel<BM_P16_U, 0, 4>; break;
+        default:        fn = lutm == 2 ? (const void *) smol_box_kernel<BM_P16L_U, 2, 4> : (const void *) smol_box_kernel<BM_P16L_U, 0, 4>; break;
     }
 #undef BOX_KERNEL_FOR
+#undef BOX_KERNEL_FOR3
 
     /* Lanes per column (G).  Long spans want several lanes per column (8..16 source pixels per
      * lane per row).  Every extra lane repeats the per-row overhead (edge pixels, normalisation),
@@ -2455,7 +2472,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         P.x_tiles = (d.w_out + cols - 1) / cols;
         /* staging buffer: the widest segment an item can need, + alignment slack */
         const uint64_t seg_px = ((uint64_t) cols * d.w_in + d.w_out - 1) / d.w_out + 3;
-        P.seg_bytes = (uint32_t) ((seg_px * 4 + 32 + 15) & ~(uint64_t) 15);
+        P.seg_bytes = (uint32_t) ((seg_px * d.bpp_in + 32 + 15) & ~(uint64_t) 15);
         if (lutm == 1)
         {
             /* one CTA per SM: as many warps as fit beside the 128 KB table */
@@ -2481,16 +2498,16 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         blocks = (uint64_t) num_sms () * per_sm;
     dim3 grid ((unsigned) blocks), block (warps_per_cta * 32);
 
-#define BOX_LAUNCH(M, LM) launch_pdl (smol_box_kernel<M, LM>, P, grid, block, smem, stream)
-#define BOX_LAUNCH_LUT(M) (lutm == 1 ? BOX_LAUNCH (M, 1) : lutm == 2 ? BOX_LAUNCH (M, 2) : BOX_LAUNCH (M, 0))
+#define BOX_LAUNCH(M, LM, B) launch_pdl (smol_box_kernel<M, LM, B>, P, grid, block, smem, stream)
+#define BOX_LAUNCH_LUT(M, B) (lutm == 1 ? BOX_LAUNCH (M, 1, B) : lutm == 2 ? BOX_LAUNCH (M, 2, B) : BOX_LAUNCH (M, 0, B))
     switch (mode)
     {
-        case BM_P8_P:   return BOX_LAUNCH (BM_P8_P, 0);
-        case BM_P8_U:   return BOX_LAUNCH (BM_P8_U, 0);
-        case BM_P8L_P:  return BOX_LAUNCH_LUT (BM_P8L_P);
-        case BM_P8L_U:  return BOX_LAUNCH_LUT (BM_P8L_U);
-        case BM_P16_U:  return BOX_LAUNCH (BM_P16_U, 0);
-        default:        return lutm == 2 ? BOX_LAUNCH (BM_P16L_U, 2) : BOX_LAUNCH (BM_P16L_U, 0);
+        case BM_P8_P:   return bi3 ? BOX_LAUNCH (BM_P8_P, 0, 3) : BOX_LAUNCH (BM_P8_P, 0, 4);
+        case BM_P8_U:   return BOX_LAUNCH (BM_P8_U, 0, 4);
+        case BM_P8L_P:  return bi3 ? BOX_LAUNCH_LUT (BM_P8L_P, 3) : BOX_LAUNCH_LUT (BM_P8L_P, 4);
+        case BM_P8L_U:  return BOX_LAUNCH_LUT (BM_P8L_U, 4);
+        case BM_P16_U:  return BOX_LAUNCH (BM_P16_U, 0, 4);
+        default:        return lutm == 2 ? BOX_LAUNCH (BM_P16L_U, 2, 4) : BOX_LAUNCH (BM_P16L_U, 0, 4);
     }
 #undef BOX_LAUNCH_LUT
 #undef BOX_LAUNCH
