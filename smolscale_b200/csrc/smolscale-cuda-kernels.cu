@@ -1302,6 +1302,107 @@ smol_taps0_kernel (const Taps0Params T)
     }
 }
 
+/* Bilinear with halvings (reference BILINEAR_1H / _2H on either axis: every 2:1 .. 8:1
+ * reduction that is not an exact power of two), 8-bit premultiplied intermediate, formats
+ * resolved at compile time, 4-byte-aligned rows.  One thread per OUTPUT pixel: a downscale has
+ * few output pixels and many taps each, so parallelism comes from the output grid and there is
+ * next to no reuse between neighbouring outputs to exploit.  The thread sums 2^vh vertical
+ * samples, each a tap between two horizontally filtered source rows (two-entry register cache:
+ * consecutive samples usually share a row), each of those the sum of 2^hh horizontal taps. */
+template <int BI, int BO, bool IU, bool OU, bool AF>
+__global__ void __launch_bounds__ (256)
+smol_tapsn_kernel (const Taps0Params T, uint32_t hh, uint32_t vh)
+{
+    __shared__ uint32_t sm_inv[256];
+    const TapsParams &P = T.t;
+
+    pdl_launch_dependents ();
+    if constexpr (OU)
+    {
+        for (uint32_t i = threadIdx.y * blockDim.x + threadIdx.x; i < 256; i += blockDim.x * blockDim.y)
+            sm_inv[i] = __ldg (&P.inv_div_p8[i]) << 3;
+        __syncthreads ();
+    }
+
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t yl = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= P.w_out || yl >= P.n_rows)
+        return;
+
+    const uint32_t n_h = 1u << hh, n_v = 1u << vh;
+    const uint32_t *tx = P.tab_x + (x << hh);
+    const uint32_t *ty = P.tab_y + ((P.first_row + yl) << vh);
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
+
+    pdl_wait ();
+
+    auto hval = [&] (uint32_t r) -> Px16
+    {
+        const uint8_t *row = src + (size_t) r * P.src_pitch;
+        uint32_t acc_a = 0, acc_b = 0;
+#pragma unroll 1
+        for (uint32_t k = 0; k < n_h; k++)
+        {
+            const uint32_t e = __ldg (&tx[k]);
+            const uint32_t ofs = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e), G = 256u - F;
+            const Px16 p = taps0_fetch<BI, IU, AF, true> (row, ofs);
+            const Px16 q = taps0_fetch<BI, IU, AF, true> (row, min (ofs + 1, P.w_in - 1));
+            acc_a += __byte_perm (p.a * F + q.a * G, 0, 0x4341);       /* ((..) >> 8) & 0x00ff00ff */
+            acc_b += __byte_perm (p.b * F + q.b * G, 0, 0x4341);
+        }
+        Px16 h;
+        h.a = (acc_a >> hh) & 0x00ff00ffu;
+        h.b = (acc_b >> hh) & 0x00ff00ffu;
+        return h;
+    };
+
+    uint32_t idx0 = 0xffffffffu, idx1 = 0xffffffffu;
+    Px16 c0, c1;
+    c0.a = c0.b = c1.a = c1.b = 0;
+    uint32_t acc_a = 0, acc_b = 0;
+
+#pragma unroll 1
+    for (uint32_t kv = 0; kv < n_v; kv++)
+    {
+        const uint32_t e = __ldg (&ty[kv]);
+        const uint32_t r0 = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e), G = 256u - F;
+        const uint32_t r1 = min (r0 + 1, P.h_in - 1);
+
+        if (r0 != idx0)
+        {
+            if (r0 == idx1)
+            {
+                const Px16 t = c0; c0 = c1; c1 = t;
+                idx1 = idx0;
+            }
+            else
+                c0 = hval (r0);
+            idx0 = r0;
+        }
+        if (r1 != idx1)
+        {
+            c1 = hval (r1);
+            idx1 = r1;
+        }
+        acc_a += __byte_perm (c0.a * F + c1.a * G, 0, 0x4341);
+        acc_b += __byte_perm (c0.b * F + c1.b * G, 0, 0x4341);
+    }
+
+    const uint32_t fa = (acc_a >> vh) & 0x00ff00ffu, fb = (acc_b >> vh) & 0x00ff00ffu;
+    uint32_t v = fa | (fb << 8);                                         /* source byte order */
+    if constexpr (OU)
+        v = half_unpremul<AF> (v, sm_inv);
+    v = __byte_perm (v, 0, P.prmt_sel);
+
+    uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl * P.dst_pitch + (size_t) x * BO;
+    if constexpr (BO == 4)
+        *reinterpret_cast<uint32_t *> (dst) = v;
+    else
+    {
+        dst[0] = (uint8_t) v; dst[1] = (uint8_t) (v >> 8); dst[2] = (uint8_t) (v >> 16);
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ *
  * "mag" kernel: vertical magnification (h_out > h_in; BASELINE config 4), bilinear / copy / one *
  * horizontally, 8-bit premultiplied intermediate.                                              *
@@ -2037,6 +2138,25 @@ launch_pdl (Kernel kernel, const Params &P, dim3 grid, dim3 block, size_t smem, 
     return cudaLaunchKernelEx (&cfg, kernel, P);
 }
 
+template <typename Kernel, typename... Args>
+static cudaError_t
+launch_pdl_args (Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr;
+
+    memset (&cfg, 0, sizeof (cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx (&cfg, kernel, args...);
+}
+
 template <int HH, int VH>
 static cudaError_t
 launch_half_hv (const HalfParams &P, int pack, dim3 grid, dim3 block, cudaStream_t stream)
@@ -2245,6 +2365,50 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
             return af ? TAPS0 (4, 4, false, true, true) : TAPS0 (4, 4, false, true, false);
         return TAPS0 (4, 4, false, false, false);
 #undef TAPS0
+    }
+
+    {
+        /* halvings on either axis: one thread per output pixel, compile-time formats (needs
+         * 4-byte-aligned rows; anything else takes the runtime-format kernel below) */
+        Taps0Params T;
+        T.t = P;
+        T.acc_prmt_sel = 0;
+        T.src_u32_ok = d.bpp_in == 3 || ((reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
+                                         && (L.src_image_stride & 3) == 0);
+        const bool dst_ok = d.bpp_out == 3 || ((reinterpret_cast<uintptr_t> (L.dst) & 3) == 0 && (L.dst_pitch & 3) == 0
+                                               && (L.dst_image_stride & 3) == 0);
+        if (T.src_u32_ok && dst_ok)
+        {
+            uint32_t nbx = 32;
+            while (nbx < 128 && nbx < d.w_out)
+                nbx *= 2;
+            uint32_t nby = 256 / nbx;
+            if (nby > L.n_rows)
+                nby = L.n_rows;
+            dim3 nblock (nbx, nby);
+            dim3 ngrid ((d.w_out + nbx - 1) / nbx, (L.n_rows + nby - 1) / nby, L.n_images);
+            const bool af = d.in_alpha_idx == 0;
+            const uint32_t hh = d.h_halvings, vh = d.v_halvings;
+#define TAPSN(BI, BO, IU, OU, AF) launch_pdl_args (smol_tapsn_kernel<BI, BO, IU, OU, AF>, ngrid, nblock, 0, stream, T, hh, vh)
+            if (d.bpp_in == 3)
+            {
+                if (d.bpp_out == 3)     return TAPSN (3, 3, false, false, false);
+                if (d.out_unassoc)      return TAPSN (3, 4, false, true, false);
+                return TAPSN (3, 4, false, false, false);
+            }
+            if (d.in_unassoc)
+            {
+                if (d.bpp_out == 3)
+                    return af ? TAPSN (4, 3, true, false, true) : TAPSN (4, 3, true, false, false);
+                return af ? TAPSN (4, 4, true, false, true) : TAPSN (4, 4, true, false, false);
+            }
+            if (d.bpp_out == 3)
+                return TAPSN (4, 3, false, false, false);
+            if (d.out_unassoc)
+                return af ? TAPSN (4, 4, false, true, true) : TAPSN (4, 4, false, true, false);
+            return TAPSN (4, 4, false, false, false);
+#undef TAPSN
+        }
     }
 
     if (d.h_halvings == 0)
