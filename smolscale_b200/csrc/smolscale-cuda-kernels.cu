@@ -2003,12 +2003,131 @@ smol_box_kernel (const BoxParams P)
 }
 
 /* ------------------------------------------------------------------------------------------ *
+ * "taps128" kernel: bilinear / copy / one on both axes with a 128bpp intermediate -- linear      *
+ * light (P8L) and unassociated -> unassociated (P16 / P16L).  One thread per output pixel, four   *
+ * 32-bit lanes per pixel, the unpack chain shared with the box kernel (box_unpack), tables in     *
+ * shared memory as 32 lane-private copies so the gathers are conflict-free.                       *
+ * ------------------------------------------------------------------------------------------ */
+
+template <int MODE, int BI>
+__global__ void __launch_bounds__ (512, 2)
+smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u32_ok)
+{
+    extern __shared__ __align__ (16) uint8_t sm_dyn[];
+    constexpr bool NEED_INV = MODE == BM_P8L_P;
+    constexpr bool NEED_FROM = MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U;
+    const SmolJobDesc &d = P.d;
+    const uint32_t tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+
+    pdl_launch_dependents ();
+    uint32_t *rep_from = reinterpret_cast<uint32_t *> (sm_dyn);
+    uint32_t *rep_inv = rep_from + (NEED_FROM ? 8192 : 0);
+    for (uint32_t i = tid; i < 8192; i += nthr)
+    {
+        if constexpr (NEED_FROM)
+            rep_from[i] = P.luts->from_srgb[i >> 5];
+        if constexpr (NEED_INV)
+            rep_inv[i] = P.luts->inv_div_p8[i >> 5] << 3;
+    }
+    const uint32_t *sm_from = rep_from + (tid & 31), *sm_inv8 = rep_inv + (tid & 31);
+    __syncthreads ();
+
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t yl = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= d.w_out || yl >= P.n_rows)
+        return;
+
+    const uint32_t n_h = 1u << hh, n_v = 1u << vh;
+    const uint32_t *tx = P.tab_x + (x << hh);
+    const uint32_t *ty = P.tab_y + ((P.first_row + yl) << vh);
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
+
+    pdl_wait ();
+
+    auto fetch = [&] (const uint8_t *row, uint32_t j) -> BoxPx<MODE>
+    {
+        const uint8_t *p = row + (size_t) j * BI;
+        uint32_t raw;
+        if (BI == 4 && src_u32_ok)
+            raw = __ldg (reinterpret_cast<const uint32_t *> (p));
+        else
+        {
+            raw = (uint32_t) __ldg (p) | ((uint32_t) __ldg (p + 1) << 8) | ((uint32_t) __ldg (p + 2) << 16);
+            raw |= BI == 4 ? ((uint32_t) __ldg (p + 3) << 24) : 0xff000000u;
+        }
+        return box_unpack<MODE, 2> (raw, P, sm_inv8, sm_from, nullptr);
+    };
+
+    auto hval = [&] (uint32_t r) -> BoxPx<MODE>
+    {
+        const uint8_t *row = src + (size_t) r * P.src_pitch;
+        BoxPx<MODE> acc;
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc.v[i] = 0;
+#pragma unroll 1
+        for (uint32_t k = 0; k < n_h; k++)
+        {
+            const uint32_t e = __ldg (&tx[k]);
+            const uint32_t ofs = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e), G = 256u - F;
+            const BoxPx<MODE> p = fetch (row, ofs);
+            const BoxPx<MODE> q = fetch (row, min (ofs + 1, d.w_in - 1));
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                acc.v[i] += ((p.v[i] * F + q.v[i] * G) >> 8) & 0x00ffffffu;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc.v[i] = (acc.v[i] >> hh) & 0x00ffffffu;
+        return acc;
+    };
+
+    uint32_t idx0 = 0xffffffffu, idx1 = 0xffffffffu;
+    BoxPx<MODE> c0, c1, acc;
+#pragma unroll
+    for (int i = 0; i < 4; i++) c0.v[i] = c1.v[i] = acc.v[i] = 0;
+
+#pragma unroll 1
+    for (uint32_t kv = 0; kv < n_v; kv++)
+    {
+        const uint32_t e = __ldg (&ty[kv]);
+        const uint32_t r0 = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e), G = 256u - F;
+        const uint32_t r1 = min (r0 + 1, d.h_in - 1);
+
+        if (r0 != idx0)
+        {
+            if (r0 == idx1)
+            {
+                const BoxPx<MODE> t = c0; c0 = c1; c1 = t;
+                idx1 = idx0;
+            }
+            else
+                c0 = hval (r0);
+            idx0 = r0;
+        }
+        if (r1 != idx1)
+        {
+            c1 = hval (r1);
+            idx1 = r1;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            acc.v[i] += ((c0.v[i] * F + c1.v[i] * G) >> 8) & 0x00ffffffu;
+    }
+
+    Px<true> o;
+    o.w[0] = (uint64_t) ((acc.v[0] >> vh) & 0x00ffffffu) | ((uint64_t) ((acc.v[1] >> vh) & 0x00ffffffu) << 32);
+    o.w[1] = (uint64_t) ((acc.v[2] >> vh) & 0x00ffffffu) | ((uint64_t) ((acc.v[3] >> vh) & 0x00ffffffu) << 32);
+    const uint32_t packed = pack_px<true> (o, d, P.luts);
+    uint8_t *o8 = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl * P.dst_pitch + (size_t) x * d.bpp_out;
+    store_raw_px (o8, packed, d.bpp_out);
+}
+
+/* ------------------------------------------------------------------------------------------ *
  * Host-side dispatch                                                                         *
  * ------------------------------------------------------------------------------------------ */
 
 static const char *const kernel_names[SMOL_KERNEL_MAX] =
 {
-    "auto", "general", "taps_direct", "half2x", "box", "mag"
+    "auto", "general", "taps_direct", "half2x", "box", "mag", "taps128"
 };
 
 extern "C" const char *
@@ -2049,6 +2168,18 @@ taps_eligible (const SmolLaunch &L)
 }
 
 static bool
+taps128_eligible (const SmolLaunch &L)
+{
+    const SmolJobDesc &d = L.d;
+
+    /* one thread per output pixel pays off when outputs are few and taps many (a halving on
+     * either axis, i.e. more than 2:1); near 1:1 and on upscales the general kernel's per-column
+     * row cache avoids recomputing the costly unpack chain */
+    return d.h_kind == SMOL_AXIS_TAPS && d.v_kind == SMOL_AXIS_TAPS && d.storage128
+           && d.mid != SMOL_MID_P8 && (d.h_halvings > 0 || d.v_halvings > 0);
+}
+
+static bool
 mag_eligible (const SmolLaunch &L)
 {
     return taps_eligible (L) && L.d.h_out > L.d.h_in && L.d.h_halvings == 0;
@@ -2083,6 +2214,8 @@ smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
 
     if (forced == SMOL_KERNEL_MAG)
         return mag_ok ? SMOL_KERNEL_MAG : SMOL_KERNEL_GENERAL;
+    if (forced == SMOL_KERNEL_TAPS128)
+        return taps128_eligible (*launch) ? SMOL_KERNEL_TAPS128 : SMOL_KERNEL_GENERAL;
 
     if (forced == SMOL_KERNEL_GENERAL)
         return SMOL_KERNEL_GENERAL;
@@ -2096,6 +2229,8 @@ smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
         return SMOL_KERNEL_HALF2X;
     if (box_ok)
         return SMOL_KERNEL_BOX;
+    if (taps128_eligible (*launch) && (forced == SMOL_KERNEL_AUTO || forced == SMOL_KERNEL_TAPS128))
+        return SMOL_KERNEL_TAPS128;
     if (mag_ok)
         return SMOL_KERNEL_MAG;
     if (taps_ok)
@@ -2545,12 +2680,10 @@ launch_mag (const SmolLaunch &L, cudaStream_t stream)
     return launch_mag_fmt<4, 4, false, false, false> (M, grid, smem, stream);
 }
 
-static cudaError_t
-launch_box (const SmolLaunch &L, cudaStream_t stream)
+static void
+box_params_init (BoxParams &P, const SmolLaunch &L)
 {
     const SmolJobDesc &d = L.d;
-    BoxParams P;
-
     P.d = d;
     P.src = L.src; P.dst = L.dst;
     P.src_pitch = L.src_pitch; P.dst_pitch = L.dst_pitch;
@@ -2577,6 +2710,16 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         const uint64_t h_max = lane_max * span_x, v_max = (d.mid == SMOL_MID_P8 && !d.storage128 ? 255 : 65535) * span_y;
         P.acc_fits_24 = h_max < (1u << 24) && v_max < (1u << 24);
     }
+
+}
+
+static cudaError_t
+launch_box (const SmolLaunch &L, cudaStream_t stream)
+{
+    const SmolJobDesc &d = L.d;
+    BoxParams P;
+
+    box_params_init (P, L);
 
     int mode;
     if (d.mid == SMOL_MID_P8)
@@ -2677,6 +2820,40 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
 #undef BOX_LAUNCH
 }
 
+static void box_params_init (BoxParams &P, const SmolLaunch &L);
+
+static cudaError_t
+launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
+{
+    const SmolJobDesc &d = L.d;
+    BoxParams P;
+
+    box_params_init (P, L);
+    const uint32_t src_u32_ok = d.bpp_in == 3 || ((reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
+                                                  && (L.src_image_stride & 3) == 0);
+    const uint32_t hh = d.h_halvings, vh = d.v_halvings;
+    uint32_t bx = 32;
+    while (bx < 128 && bx < d.w_out)
+        bx *= 2;
+    uint32_t by = 512 / bx;
+    if (by > L.n_rows)
+        by = L.n_rows;
+    dim3 block (bx, by), grid ((d.w_out + bx - 1) / bx, (L.n_rows + by - 1) / by, L.n_images);
+
+#define T128(M, B, BYTES) (cudaFuncSetAttribute (smol_taps128_kernel<M, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), \
+                           launch_pdl_args (smol_taps128_kernel<M, B>, grid, block, (size_t) (BYTES), stream, P, hh, vh, src_u32_ok))
+    if (d.mid == SMOL_MID_P8L)
+    {
+        if (d.in_unassoc)
+            return T128 (BM_P8L_U, 4, 32768);
+        return d.bpp_in == 3 ? T128 (BM_P8L_P, 3, 65536) : T128 (BM_P8L_P, 4, 65536);
+    }
+    if (d.mid == SMOL_MID_P16)
+        return T128 (BM_P16_U, 4, 0);
+    return T128 (BM_P16L_U, 4, 32768);
+#undef T128
+}
+
 template <bool S128, bool HBOX, bool VBOX>
 static cudaError_t
 launch_general (const SmolLaunch &L, cudaStream_t stream)
@@ -2743,6 +2920,8 @@ smol_cuda_launch (const SmolLaunch *launch, int kernel_id, void *stream_p, const
         return (int) launch_half (L, stream);
     if (kernel_id == SMOL_KERNEL_BOX && box_eligible (L))
         return (int) launch_box (L, stream);
+    if (kernel_id == SMOL_KERNEL_TAPS128 && taps128_eligible (L))
+        return (int) launch_taps128 (L, stream);
     if (kernel_id == SMOL_KERNEL_MAG && mag_eligible (L))
         return (int) launch_mag (L, stream);
     if (kernel_id == SMOL_KERNEL_TAPS_DIRECT && taps_eligible (L))
