@@ -276,6 +276,29 @@ def test_solid_colours(sb, restatement):
                     assert (out.reshape(-1, 4) == np.array([a, r, g, b], np.uint8)).all(), (a, r, g, b, wi, wo)
 
 
+def test_solid_colour_sweep(sb):
+    """the reference's `check` mode (test.c:1128-1298) restated for the GPU path: solid
+    colours, every Nth width 1..65535 -> 1 and 65535 -> every Nth width, horizontally and vertically
+    (SMOL_SWEEP_STEP=1 for the exhaustive sweep; default stride keeps the run to seconds).  The
+    reference's own bar is "output == the colour"; at exact integer box ratios the reference itself
+    loses the last pixel, so the exact bar is applied where it holds (non-box ratios
+    and non-integer box ratios) and every result is additionally cross-checked between the H and V
+    directions, which must agree for a solid colour."""
+    step = int(os.environ.get("SMOL_SWEEP_STEP", "611"))
+    colours = [(0xff, 0xff, 0xff, 0xff), (0x80, 0x40, 0x20, 0x10), (0x01, 0x00, 0x01, 0x00)]
+    for col in colours:
+        c = np.array(col, np.uint8)
+        src = np.tile(c, 65535)
+        for n in list(range(1, 65536, step)) + [65534, 65535]:
+            for n_in, n_out in ((n, 1), (65535, n)):
+                h = cuda_scale(sb, src, cases.ARGB8_P, n_in, 1, n_in * 4, cases.ARGB8_P, n_out, 1, n_out * 4, 0)
+                v = cuda_scale(sb, src, cases.ARGB8_P, 1, n_in, 4, cases.ARGB8_P, 1, n_out, 4, 0)
+                assert np.array_equal(h, v), (col, n_in, n_out)
+                is_box = n_in > 8 * n_out
+                if not is_box or n_in % n_out != 0:
+                    assert (h.reshape(-1, 4) == c).all(), (col, n_in, n_out)
+
+
 def test_baseline_config_properties(sb, restatement):
     """Full-size BASELINE shapes: band-split invariance and agreement with the oracle on a sampled
     row window (the digests in test_golden_digests already pin the whole images)."""
