@@ -2002,6 +2002,67 @@ smol_box_kernel (const BoxParams P)
     }
 }
 
+/* Repack of a 128bpp intermediate pixel (four 32-bit lanes: alpha lane, c0, c1, c2) with 32-bit
+ * arithmetic.  The reference multiplies whole 64-bit words by the inverse-division entry and
+ * shifts (generic:271-318); every field it then keeps lies inside the LOW 32 bits of the lane's
+ * product (lanes are masked to 24 bits, table entries are at most 2^19, and the kept bits end at
+ * bit 29 at most), so a plain 32-bit multiply gives the same bits.  sm_to_srgb: the 2048-entry
+ * table in shared memory.  Returns the pixel's bytes in destination memory order. */
+template <int MODE>
+__device__ __forceinline__ uint32_t
+pack128_fast (const uint32_t lane[4], const SmolJobDesc &d, const SmolDeviceLuts *__restrict__ lut,
+              const uint8_t *__restrict__ sm_to_srgb)
+{
+    uint32_t a, c[3];
+
+    if constexpr (MODE == BM_P16_U || MODE == BM_P16L_U)
+        a = (lane[0] >> 8) & 0xff;                                       /* generic:1140, :1152 */
+    else
+        a = lane[0] & 0xff;                                              /* generic:1101 */
+
+    if constexpr (MODE == BM_P16_U)
+    {
+        const uint32_t inv = __ldg (&lut->inv_div_p16[a]);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            c[i] = __byte_perm (lane[i + 1] * inv, 0, 0x4442);           /* (v * inv) >> 16 & 0xff, generic:290-299 */
+    }
+    else if constexpr (MODE == BM_P16L_U)
+    {
+        const uint32_t inv = __ldg (&lut->inv_div_p16l[a]);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            c[i] = sm_to_srgb[((lane[i + 1] * inv) >> 19) & 0x7ff];      /* generic:309-318 */
+    }
+    else
+    {
+        /* P8L (generic:1096-1134, 24bpp :922-935 / :1010-1023) */
+        const uint32_t inv = __ldg (&lut->inv_div_p8l[a]);
+        const bool unpremul = !(d.bpp_out == 3 && d.pack24_direct);
+        const bool repremul = d.bpp_out == 4 && !d.out_unassoc;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            uint32_t v = lane[i + 1];
+            if (unpremul)
+                v = (v * inv) >> 10;
+            v = sm_to_srgb[v & 0x7ff];
+            if (repremul)
+                v = (((v + 1) * (a + 1) - 1) >> 8) & 0xff;
+            c[i] = v;
+        }
+    }
+
+    if (d.swap_rb)
+    {
+        const uint32_t t = c[0]; c[0] = c[2]; c[2] = t;
+    }
+    uint32_t out = (c[0] << (8 * d.out_col0)) | (c[1] << (8 * (d.out_col0 + 1))) | (c[2] << (8 * (d.out_col0 + 2)));
+    if (d.out_alpha_idx != 0xff)
+        out |= a << (8 * d.out_alpha_idx);
+    return out;
+}
+
 /* ------------------------------------------------------------------------------------------ *
  * "taps128" kernel: bilinear / copy / one on both axes with a 128bpp intermediate -- linear      *
  * light (P8L) and unassociated -> unassociated (P16 / P16L).  One thread per output pixel, four   *
@@ -2030,6 +2091,10 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
             rep_inv[i] = P.luts->inv_div_p8[i >> 5] << 3;
     }
     const uint32_t *sm_from = rep_from + (tid & 31), *sm_inv8 = rep_inv + (tid & 31);
+    __shared__ uint8_t sm_to_srgb[2048];
+    if constexpr (MODE != BM_P16_U)
+        for (uint32_t i = tid; i < 512; i += nthr)
+            reinterpret_cast<uint32_t *> (sm_to_srgb)[i] = reinterpret_cast<const uint32_t *> (P.luts->to_srgb)[i];
     __syncthreads ();
 
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2113,12 +2178,169 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
             acc.v[i] += ((c0.v[i] * F + c1.v[i] * G) >> 8) & 0x00ffffffu;
     }
 
-    Px<true> o;
-    o.w[0] = (uint64_t) ((acc.v[0] >> vh) & 0x00ffffffu) | ((uint64_t) ((acc.v[1] >> vh) & 0x00ffffffu) << 32);
-    o.w[1] = (uint64_t) ((acc.v[2] >> vh) & 0x00ffffffu) | ((uint64_t) ((acc.v[3] >> vh) & 0x00ffffffu) << 32);
-    const uint32_t packed = pack_px<true> (o, d, P.luts);
+    uint32_t fin[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) fin[i] = (acc.v[i] >> vh) & 0x00ffffffu;
+    const uint32_t packed = pack128_fast<MODE> (fin, d, P.luts, sm_to_srgb);
     uint8_t *o8 = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl * P.dst_pitch + (size_t) x * d.bpp_out;
     store_raw_px (o8, packed, d.bpp_out);
+}
+
+/* ------------------------------------------------------------------------------------------ *
+ * "tile128" kernel: bilinear without halvings / copy / one on both axes (anything from 1:2 to     *
+ * any magnification) with a 128bpp intermediate -- linear light and unassociated -> unassociated. *
+ * Same two-phase shared-memory tile as the mag kernel, because here the unpack chain is the       *
+ * expensive part and must run exactly once per source pixel:                                      *
+ *   1a. load + unpack the tile's source window once per source pixel (four 32-bit lanes);         *
+ *   1b. horizontal taps once per (source row, output column);                                     *
+ *   2.  vertical taps per output pixel, walking runs of rows that share a source row pair,        *
+ *       then the (format-generic) repack.                                                         *
+ * ------------------------------------------------------------------------------------------ */
+
+struct Tile128Params
+{
+    BoxParams b;
+    uint32_t tile_w, tile_w_log2, tile_h;
+    uint32_t u_pitch, u_cw, u_cw_log2, max_src_rows;
+    uint32_t src_u32_ok;
+};
+
+/* BO: destination bytes per pixel; 32bpp destinations need 4-byte-aligned rows. */
+template <int MODE, int BI, int BO>
+__global__ void __launch_bounds__ (512)
+smol_tile128_kernel (const Tile128Params M)
+{
+    extern __shared__ __align__ (16) uint8_t sm_dyn[];
+    __shared__ uint32_t sm_ty[64];
+    __shared__ uint32_t sm_inv8[256];
+    __shared__ uint32_t sm_from[256];
+    __shared__ uint8_t sm_to_srgb[2048];
+    constexpr bool NEED_INV = MODE == BM_P8L_P;
+    constexpr bool NEED_FROM = MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U;
+    const BoxParams &P = M.b;
+    const SmolJobDesc &d = P.d;
+    const uint32_t tid = threadIdx.x;
+
+    pdl_launch_dependents ();
+    /* one plain copy of each table per CTA: the gathers happen once per SOURCE pixel here, so
+     * their bank conflicts are cheaper than replicating 64 KB of tables into every tile's CTA */
+    if (tid < 256)
+    {
+        if constexpr (NEED_FROM)
+            sm_from[tid] = P.luts->from_srgb[tid];
+        if constexpr (NEED_INV)
+            sm_inv8[tid] = P.luts->inv_div_p8[tid] << 3;
+    }
+    if constexpr (MODE != BM_P16_U)
+        reinterpret_cast<uint32_t *> (sm_to_srgb)[tid] = reinterpret_cast<const uint32_t *> (P.luts->to_srgb)[tid];
+
+    const uint32_t x0 = blockIdx.x * M.tile_w;
+    const uint32_t x1 = min (x0 + M.tile_w, d.w_out);
+    const uint32_t yl0 = blockIdx.y * M.tile_h;
+    const uint32_t yl1 = min (yl0 + M.tile_h, P.n_rows);
+    const uint32_t tw = x1 - x0, th = yl1 - yl0;
+
+    const uint32_t c_lo = SMOL_TAB_OFS (__ldg (&P.tab_x[x0]));
+    const uint32_t c_hi = min (SMOL_TAB_OFS (__ldg (&P.tab_x[x1 - 1])) + 1, d.w_in - 1);
+    const uint32_t r_lo = SMOL_TAB_OFS (__ldg (&P.tab_y[P.first_row + yl0]));
+    const uint32_t r_hi = min (SMOL_TAB_OFS (__ldg (&P.tab_y[P.first_row + yl1 - 1])) + 1, d.h_in - 1);
+    const uint32_t n_cols = c_hi - c_lo + 1, n_rows = r_hi - r_lo + 1;
+    if (tid < th)
+        sm_ty[tid] = __ldg (&P.tab_y[P.first_row + yl0 + tid]);
+
+    uint4 *sm_u = reinterpret_cast<uint4 *> (sm_dyn);
+    uint4 *sm_h = sm_u + (size_t) M.max_src_rows * M.u_pitch;
+
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
+    __syncthreads ();
+    pdl_wait ();
+
+    /* phase 1a */
+    {
+        const uint32_t ct = tid & (M.u_cw - 1), rt = tid >> M.u_cw_log2, r_step = 512u >> M.u_cw_log2;
+        for (uint32_t r = rt; r < n_rows; r += r_step)
+        {
+            const uint8_t *row = src + (size_t) (r_lo + r) * P.src_pitch + (size_t) c_lo * BI;
+            for (uint32_t c = ct; c < n_cols; c += M.u_cw)
+            {
+                const uint8_t *p = row + c * BI;
+                uint32_t raw;
+                if (BI == 4 && M.src_u32_ok)
+                    raw = __ldg (reinterpret_cast<const uint32_t *> (p));
+                else
+                {
+                    raw = (uint32_t) __ldg (p) | ((uint32_t) __ldg (p + 1) << 8) | ((uint32_t) __ldg (p + 2) << 16);
+                    raw |= BI == 4 ? ((uint32_t) __ldg (p + 3) << 24) : 0xff000000u;
+                }
+                const BoxPx<MODE> u = box_unpack<MODE, 0> (raw, P, sm_inv8, sm_from, nullptr);
+                sm_u[r * M.u_pitch + c] = make_uint4 (u.v[0], u.v[1], u.v[2], u.v[3]);
+            }
+        }
+    }
+    __syncthreads ();
+
+    /* phase 1b */
+    {
+        const bool full = tw == M.tile_w;
+        const uint32_t xl = full ? (tid & (M.tile_w - 1)) : tid % tw;
+        const uint32_t r_step = full ? (512u >> M.tile_w_log2) : 512 / tw;
+        const uint32_t r_first = full ? (tid >> M.tile_w_log2) : tid / tw;
+        const uint32_t e = __ldg (&P.tab_x[x0 + xl]);
+        const uint32_t op = SMOL_TAB_OFS (e) - c_lo, oq = min (SMOL_TAB_OFS (e) + 1, d.w_in - 1) - c_lo;
+        const uint32_t F = SMOL_TAB_F (e), G = 256u - F;
+        if (r_step > 0)
+            for (uint32_t r = r_first; r < n_rows; r += r_step)
+            {
+                const uint4 p = sm_u[r * M.u_pitch + op], q = sm_u[r * M.u_pitch + oq];
+                uint4 h;
+                h.x = ((p.x * F + q.x * G) >> 8) & 0x00ffffffu;
+                h.y = ((p.y * F + q.y * G) >> 8) & 0x00ffffffu;
+                h.z = ((p.z * F + q.z * G) >> 8) & 0x00ffffffu;
+                h.w = ((p.w * F + q.w * G) >> 8) & 0x00ffffffu;
+                sm_h[r * M.tile_w + xl] = h;
+            }
+    }
+    __syncthreads ();
+
+    /* phase 2 */
+    const bool full = tw == M.tile_w;
+    const uint32_t n_runs = full ? (512u >> M.tile_w_log2) : 512 / tw;
+    const uint32_t xl = full ? (tid & (M.tile_w - 1)) : tid % tw;
+    const uint32_t run = full ? (tid >> M.tile_w_log2) : tid / tw;
+    if (run >= n_runs)
+        return;
+    const uint32_t rows_per_run = (th + n_runs - 1) / n_runs;
+    const uint32_t ry_begin = run * rows_per_run, ry_end = min (ry_begin + rows_per_run, th);
+    uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) (yl0 + ry_begin) * P.dst_pitch
+                   + (size_t) (x0 + xl) * BO;
+    const uint4 *hcol = sm_h + xl;
+
+    uint32_t ry = ry_begin;
+    uint32_t e = ry < ry_end ? sm_ty[ry] : 0;
+    while (ry < ry_end)
+    {
+        const uint32_t ofs = SMOL_TAB_OFS (e);
+        const uint32_t r0 = ofs - r_lo, r1 = min (ofs + 1, d.h_in - 1) - r_lo;
+        const uint4 t = hcol[r0 * M.tile_w], b = hcol[r1 * M.tile_w];
+
+        do
+        {
+            const uint32_t F = SMOL_TAB_F (e), G = 256u - F;
+            const uint32_t fin[4] = { ((t.x * F + b.x * G) >> 8) & 0x00ffffffu, ((t.y * F + b.y * G) >> 8) & 0x00ffffffu,
+                                      ((t.z * F + b.z * G) >> 8) & 0x00ffffffu, ((t.w * F + b.w * G) >> 8) & 0x00ffffffu };
+            const uint32_t v = pack128_fast<MODE> (fin, d, P.luts, sm_to_srgb);
+            if constexpr (BO == 4)
+                *reinterpret_cast<uint32_t *> (dst) = v;
+            else
+            {
+                dst[0] = (uint8_t) v; dst[1] = (uint8_t) (v >> 8); dst[2] = (uint8_t) (v >> 16);
+            }
+            ry++;
+            dst += P.dst_pitch;
+            e = sm_ty[min (ry, th - 1)];
+        }
+        while (ry < ry_end && SMOL_TAB_OFS (e) == ofs);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ *
@@ -2127,7 +2349,7 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
 
 static const char *const kernel_names[SMOL_KERNEL_MAX] =
 {
-    "auto", "general", "taps_direct", "half2x", "box", "mag", "taps128"
+    "auto", "general", "taps_direct", "half2x", "box", "mag", "taps128", "tile128"
 };
 
 extern "C" const char *
@@ -2180,6 +2402,17 @@ taps128_eligible (const SmolLaunch &L)
 }
 
 static bool
+tile128_eligible (const SmolLaunch &L)
+{
+    const SmolJobDesc &d = L.d;
+
+    return d.h_kind == SMOL_AXIS_TAPS && d.v_kind == SMOL_AXIS_TAPS && d.storage128
+           && d.mid != SMOL_MID_P8 && d.h_halvings == 0 && d.v_halvings == 0
+           && (d.bpp_out == 3 || ((reinterpret_cast<uintptr_t> (L.dst) & 3) == 0 && (L.dst_pitch & 3) == 0
+                                  && (L.dst_image_stride & 3) == 0));
+}
+
+static bool
 mag_eligible (const SmolLaunch &L)
 {
     return taps_eligible (L) && L.d.h_out > L.d.h_in && L.d.h_halvings == 0;
@@ -2216,6 +2449,8 @@ smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
         return mag_ok ? SMOL_KERNEL_MAG : SMOL_KERNEL_GENERAL;
     if (forced == SMOL_KERNEL_TAPS128)
         return taps128_eligible (*launch) ? SMOL_KERNEL_TAPS128 : SMOL_KERNEL_GENERAL;
+    if (forced == SMOL_KERNEL_TILE128)
+        return tile128_eligible (*launch) ? SMOL_KERNEL_TILE128 : SMOL_KERNEL_GENERAL;
 
     if (forced == SMOL_KERNEL_GENERAL)
         return SMOL_KERNEL_GENERAL;
@@ -2231,6 +2466,8 @@ smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
         return SMOL_KERNEL_BOX;
     if (taps128_eligible (*launch) && (forced == SMOL_KERNEL_AUTO || forced == SMOL_KERNEL_TAPS128))
         return SMOL_KERNEL_TAPS128;
+    if (tile128_eligible (*launch) && (forced == SMOL_KERNEL_AUTO || forced == SMOL_KERNEL_TILE128))
+        return SMOL_KERNEL_TILE128;
     if (mag_ok)
         return SMOL_KERNEL_MAG;
     if (taps_ok)
@@ -2854,6 +3091,61 @@ launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
 #undef T128
 }
 
+static cudaError_t
+launch_tile128 (const SmolLaunch &L, cudaStream_t stream)
+{
+    const SmolJobDesc &d = L.d;
+    Tile128Params M;
+
+    box_params_init (M.b, L);
+    M.src_u32_ok = d.bpp_in == 3 || ((reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
+                                     && (L.src_image_stride & 3) == 0);
+    const size_t lut_bytes = 0;
+    M.tile_w = 4;
+    M.tile_w_log2 = 2;
+    while (M.tile_w < 128 && M.tile_w < d.w_out)
+    {
+        M.tile_w *= 2;
+        M.tile_w_log2++;
+    }
+    M.tile_h = 32;
+    size_t smem;
+    for (;;)
+    {
+        const uint64_t cols = ((uint64_t) M.tile_w * d.w_in + d.w_out - 1) / d.w_out + 3;
+        const uint64_t rows = ((uint64_t) M.tile_h * d.h_in + d.h_out - 1) / d.h_out + 3;
+        M.u_pitch = (uint32_t) (cols < d.w_in ? cols : d.w_in);
+        M.max_src_rows = (uint32_t) (rows < d.h_in ? rows : d.h_in);
+        smem = lut_bytes + (size_t) M.max_src_rows * ((size_t) M.u_pitch + M.tile_w) * 16;
+        if (smem <= 100 * 1024 || M.tile_h <= 2)
+            break;
+        M.tile_h /= 2;
+    }
+    M.u_cw = 1;
+    M.u_cw_log2 = 0;
+    while (M.u_cw < 512 && M.u_cw < M.u_pitch)
+    {
+        M.u_cw *= 2;
+        M.u_cw_log2++;
+    }
+    dim3 grid ((d.w_out + M.tile_w - 1) / M.tile_w, (L.n_rows + M.tile_h - 1) / M.tile_h, L.n_images);
+
+#define TILE128_BO(MD, B, O) (cudaFuncSetAttribute (smol_tile128_kernel<MD, B, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), \
+                              launch_pdl (smol_tile128_kernel<MD, B, O>, M, grid, dim3 (512), smem, stream))
+#define TILE128(MD, B) (d.bpp_out == 3 ? TILE128_BO (MD, B, 3) : TILE128_BO (MD, B, 4))
+    if (d.mid == SMOL_MID_P8L)
+    {
+        if (d.in_unassoc)
+            return TILE128 (BM_P8L_U, 4);
+        return d.bpp_in == 3 ? TILE128 (BM_P8L_P, 3) : TILE128 (BM_P8L_P, 4);
+    }
+    if (d.mid == SMOL_MID_P16)
+        return TILE128 (BM_P16_U, 4);
+    return TILE128 (BM_P16L_U, 4);
+#undef TILE128
+#undef TILE128_BO
+}
+
 template <bool S128, bool HBOX, bool VBOX>
 static cudaError_t
 launch_general (const SmolLaunch &L, cudaStream_t stream)
@@ -2922,6 +3214,8 @@ smol_cuda_launch (const SmolLaunch *launch, int kernel_id, void *stream_p, const
         return (int) launch_box (L, stream);
     if (kernel_id == SMOL_KERNEL_TAPS128 && taps128_eligible (L))
         return (int) launch_taps128 (L, stream);
+    if (kernel_id == SMOL_KERNEL_TILE128 && tile128_eligible (L))
+        return (int) launch_tile128 (L, stream);
     if (kernel_id == SMOL_KERNEL_MAG && mag_eligible (L))
         return (int) launch_mag (L, stream);
     if (kernel_id == SMOL_KERNEL_TAPS_DIRECT && taps_eligible (L))

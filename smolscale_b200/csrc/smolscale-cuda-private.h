@@ -29,7 +29,8 @@ enum
     SMOL_KERNEL_HALF2X = 3,      /* exact 2^k:1 reductions (all F = 128), 32bpp in, packed-byte math */
     SMOL_KERNEL_BOX = 4,         /* box x box, tuned for large-span downscales */
     SMOL_KERNEL_MAG = 5,         /* vertical magnification: two-phase shared-memory tile */
-    SMOL_KERNEL_TAPS128 = 6,     /* bilinear / copy / one with a 128bpp intermediate (linear light, P16) */
+    SMOL_KERNEL_TAPS128 = 6,     /* bilinear with halvings, 128bpp intermediate (linear light, P16) */
+    SMOL_KERNEL_TILE128 = 7,     /* bilinear without halvings / copy / one, 128bpp intermediate */
     SMOL_KERNEL_MAX
 };
 

@@ -43,7 +43,8 @@ def test_golden_digests(sb):
     assert not bad, "CUDA output differs from the reference digests: %s" % bad[:10]
 
 
-@pytest.mark.parametrize("forced", [0, 1, 2, 4, 5, 6], ids=["auto", "general", "taps", "box", "mag", "taps128"])
+@pytest.mark.parametrize("forced", [0, 1, 2, 4, 5, 6, 7],
+                         ids=["auto", "general", "taps", "box", "mag", "taps128", "tile128"])
 def test_random_matrix_vs_oracle(sb, restatement, forced):
     """forced = 0: the dispatcher's choice; 1: everything through the general kernel;
     2 / 5: the direct taps / magnification kernel wherever eligible (general elsewhere)."""
