@@ -1169,8 +1169,13 @@ __device__ __forceinline__ Px16 taps0_fetch (const uint8_t *row, uint32_t x)
 
 /* FASTIO: 32bpp source rows and all destination rows are 4-byte aligned; resolved at compile
  * time so the byte-wise fallbacks cost nothing on the fast path. */
-template <int BI, int BO, bool IU, bool OU, bool AF, bool FASTIO>
-__global__ void __launch_bounds__ (256)
+#ifndef SMOL_TAPS0_MINBLOCKS
+#define SMOL_TAPS0_MINBLOCKS 5
+#endif
+/* PX: output pixels per thread.  4 gives 128-bit (or 3 x 32-bit) stores; 1 makes every load of a
+ * warp touch one contiguous run of source pixels (32bpp destinations only). */
+template <int BI, int BO, bool IU, bool OU, bool AF, bool FASTIO, int PX>
+__global__ void __launch_bounds__ (256, SMOL_TAPS0_MINBLOCKS)
 smol_taps0_kernel (const Taps0Params T)
 {
     __shared__ uint32_t sm_inv[256];
@@ -1184,18 +1189,18 @@ smol_taps0_kernel (const Taps0Params T)
         __syncthreads ();
     }
 
-    const uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
     const uint32_t strip = blockIdx.y * blockDim.y + threadIdx.y;
     const uint32_t yl0 = strip * P.rows_per_thread;
     if (x >= P.w_out || yl0 >= P.n_rows)
         return;
     const uint32_t yl1 = min (yl0 + P.rows_per_thread, P.n_rows);
-    const uint32_t n_px = min (4u, P.w_out - x);
+    const uint32_t n_px = min ((uint32_t) PX, P.w_out - x);
 
     /* this thread's four horizontal taps never change */
-    uint32_t op[4], oq[4], Fx[4];
+    uint32_t op[PX], oq[PX], Fx[PX];
 #pragma unroll
-    for (int o = 0; o < 4; o++)
+    for (int o = 0; o < PX; o++)
     {
         const uint32_t e = __ldg (&P.tab_x[min (x + o, P.w_out - 1)]);
         op[o] = SMOL_TAB_OFS (e);
@@ -1205,15 +1210,15 @@ smol_taps0_kernel (const Taps0Params T)
 
     const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
     uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl0 * P.dst_pitch + (size_t) x * BO;
-    const bool fast_store = FASTIO && n_px == 4;
+    const bool fast_store = FASTIO && n_px == PX;
 
     pdl_wait ();
 
-    auto hrow = [&] (uint32_t r, Px16 out[4])
+    auto hrow = [&] (uint32_t r, Px16 *out)
     {
         const uint8_t *row = src + (size_t) min (r, P.h_in - 1) * P.src_pitch;
 #pragma unroll
-        for (int o = 0; o < 4; o++)
+        for (int o = 0; o < PX; o++)
         {
             const Px16 p = taps0_fetch<BI, IU, AF, FASTIO> (row, op[o]);
             const Px16 q = taps0_fetch<BI, IU, AF, FASTIO> (row, oq[o]);
@@ -1225,12 +1230,12 @@ smol_taps0_kernel (const Taps0Params T)
 
     /* one output row from the two cached source rows; F = 256 / F = 0 (copy, one, table tails)
      * come out exact from the same formula, so there are no special cases */
-    auto emit = [&] (const Px16 top[4], const Px16 bot[4], uint32_t F)
+    auto emit = [&] (const Px16 *top, const Px16 *bot, uint32_t F)
     {
         const uint32_t G = 256u - F;
         uint32_t out[4];
 #pragma unroll
-        for (int o = 0; o < 4; o++)
+        for (int o = 0; o < PX; o++)
         {
             const uint32_t acc_a = top[o].a * F + bot[o].a * G, acc_b = top[o].b * F + bot[o].b * G;
             if constexpr (OU)
@@ -1242,7 +1247,9 @@ smol_taps0_kernel (const Taps0Params T)
             else
                 out[o] = __byte_perm (acc_a, acc_b, T.acc_prmt_sel);
         }
-        if (fast_store)
+        if constexpr (PX == 1)
+            *reinterpret_cast<uint32_t *> (dst) = out[0];       /* PX == 1 implies BO == 4 and FASTIO */
+        else if (fast_store)
             store_px4_aligned<BO> (dst, out);
         else
             store_px_slow (dst, out, n_px, BO);
@@ -1256,7 +1263,7 @@ smol_taps0_kernel (const Taps0Params T)
     uint32_t yl = yl0;
     uint32_t e = __ldg (&ty[yl]);
     uint32_t r = SMOL_TAB_OFS (e);
-    Px16 A[4], B[4];
+    Px16 A[PX], B[PX];
     hrow (r, A);
     hrow (r + 1, B);
 
@@ -2674,7 +2681,7 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
     /* strip height: long strips amortise the two-row cache (essential on upscales) but leave
      * fewer threads; keep at least ~2 resident waves of threads on the GPU */
     const uint64_t x_threads = (d.w_out + 3) / 4;
-    const uint64_t want_threads = (uint64_t) num_sms () * 2048 * 2;
+    const uint64_t want_threads = (uint64_t) num_sms () * 1536;
     uint32_t rpt = 16;
     while (rpt > 1 && x_threads * ((L.n_rows + rpt - 1) / rpt) * L.n_images < want_threads)
         rpt >>= 1;
@@ -2717,8 +2724,31 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
         const bool af = d.in_alpha_idx == 0;
         const bool fastio = T.src_u32_ok && (reinterpret_cast<uintptr_t> (L.dst) & 3) == 0
                             && (L.dst_pitch & 3) == 0 && (L.dst_image_stride & 3) == 0;
-#define TAPS0(BI, BO, IU, OU, AF) (fastio ? launch_pdl (smol_taps0_kernel<BI, BO, IU, OU, AF, true>, T, grid, block, 0, stream) \
-                                          : launch_pdl (smol_taps0_kernel<BI, BO, IU, OU, AF, false>, T, grid, block, 0, stream))
+        /* one pixel per thread (fully coalesced source reads) when the destination is 32bpp and
+         * rows are aligned; otherwise four (vector / 24bpp stores) */
+        static int tune_px = -1;
+        if (tune_px < 0)
+        {
+            const char *e = getenv ("SMOL_TAPS_PX");
+            tune_px = e ? atoi (e) : 4;
+        }
+        const bool px1 = fastio && d.bpp_out == 4 && tune_px == 1;
+        if (px1)
+        {
+            const uint64_t xt1 = d.w_out;
+            uint32_t bx1 = 32;
+            while (bx1 < 128 && bx1 < xt1)
+                bx1 *= 2;
+            uint32_t by1 = 256 / bx1;
+            if (by1 > strips)
+                by1 = strips;
+            block = dim3 (bx1, by1);
+            grid = dim3 ((unsigned) ((xt1 + bx1 - 1) / bx1), (strips + by1 - 1) / by1, L.n_images);
+        }
+#define TAPS0_PX(BI, BO, IU, OU, AF, PX) (fastio ? launch_pdl (smol_taps0_kernel<BI, BO, IU, OU, AF, true, PX>, T, grid, block, 0, stream) \
+                                                 : launch_pdl (smol_taps0_kernel<BI, BO, IU, OU, AF, false, PX>, T, grid, block, 0, stream))
+#define TAPS0(BI, BO, IU, OU, AF) (BO == 4 && px1 ? launch_pdl (smol_taps0_kernel<BI, 4, IU, OU, AF, true, 1>, T, grid, block, 0, stream) \
+                                                  : TAPS0_PX (BI, BO, IU, OU, AF, 4))
         if (d.bpp_in == 3)
         {
             if (d.bpp_out == 3)     return TAPS0 (3, 3, false, false, false);
@@ -2737,6 +2767,7 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
             return af ? TAPS0 (4, 4, false, true, true) : TAPS0 (4, 4, false, true, false);
         return TAPS0 (4, 4, false, false, false);
 #undef TAPS0
+#undef TAPS0_PX
     }
 
     {
