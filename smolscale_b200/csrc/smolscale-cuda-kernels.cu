@@ -1893,31 +1893,37 @@ smol_box_kernel (const BoxParams P)
 
         const uint8_t *src = P.src + (size_t) img * P.src_image_stride + win0;
 
-        /* this lane's first three chunks of the window are the same for every row: work out
-         * their validity once (longer windows take the generic loop) */
+        /* This lane's chunks of the window (lane, lane + 32, lane + 64; longer windows take the
+         * generic loop) are the same for every row: work out once how many bytes of each lie inside
+         * the row.  Chunks wholly past the row's end are skipped -- nothing ever reads them. */
         uint32_t cvalid[3];
 #pragma unroll
         for (int c = 0; c < 3; c++)
         {
             const uint32_t k = lane + 32 * c, ofs = win0 + 16 * k;
-            cvalid[c] = k < n_chunks ? (ofs < row_bytes ? min (16u, row_bytes - ofs) : 0u) : 0xffffffffu;
+            cvalid[c] = (k < n_chunks && ofs < row_bytes) ? min (16u, row_bytes - ofs) : 0u;
         }
         const uint8_t *grow = src + (size_t) T * P.src_pitch + 16 * lane;
+        const uint32_t sbuf = bufs_addr + 16 * lane;
 
         auto prefetch = [&] (uint32_t slot)
         {
             /* copies the row `grow` points at, then advances it to the next row */
-            const uint32_t sbase = bufs_addr + slot * P.seg_bytes + 16 * lane;
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                if (cvalid[c] != 0xffffffffu)
-                    /* past the row's end: zero-fill only (source size 0), address kept inside the row */
-                    cp_async_16 (sbase + 512 * c, cvalid[c] ? grow + 512 * c : grow - 16 * lane, cvalid[c]);
-            for (uint32_t k = lane + 96; k < n_chunks; k += 32)
+            const uint32_t sbase = sbuf + slot * P.seg_bytes;
+            if (cvalid[0])
+                cp_async_16 (sbase, grow, cvalid[0]);
+            if (cvalid[1])
+                cp_async_16 (sbase + 512, grow + 512, cvalid[1]);
+            if (cvalid[2])
+                cp_async_16 (sbase + 1024, grow + 1024, cvalid[2]);
+            if (n_chunks > 96)
             {
-                const uint32_t ofs = win0 + 16 * k;
-                const uint32_t valid = ofs < row_bytes ? min (16u, row_bytes - ofs) : 0u;
-                cp_async_16 (sbase + 16 * (k - lane), valid ? grow + 16 * (k - lane) : grow - 16 * lane, valid);
+                for (uint32_t k = lane + 96; k < n_chunks; k += 32)
+                {
+                    const uint32_t ofs = win0 + 16 * k;
+                    if (ofs < row_bytes)
+                        cp_async_16 (sbase + 16 * (k - lane), grow + 16 * (k - lane), min (16u, row_bytes - ofs));
+                }
             }
             cp_async_commit ();
             grow += P.src_pitch;
