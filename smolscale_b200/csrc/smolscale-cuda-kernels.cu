@@ -2850,7 +2850,7 @@ template <int BI, int BO, bool IU, bool OU, bool AF, bool FASTIO>
 static cudaError_t
 launch_mag_fmt_io (const MagParams &M, dim3 grid, size_t smem, cudaStream_t stream)
 {
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)        /* static shared memory counts against the 48 KB default too */
     {
         cudaError_t err = cudaFuncSetAttribute (smol_mag_kernel<BI, BO, IU, OU, AF, FASTIO>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -3062,7 +3062,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
             warps_per_cta = warps_per_cta > 32 ? 32 : warps_per_cta < 4 ? 4 : warps_per_cta;
         }
         smem = lut_bytes + (size_t) warps_per_cta * 2 * P.seg_bytes;
-        if (smem > 48 * 1024)
+        if (smem > 32 * 1024)        /* static shared memory counts against the 48 KB default too */
             cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, (int) warps_per_cta * 32, smem) != cudaSuccess || occ < 1)

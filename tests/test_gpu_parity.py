@@ -60,6 +60,27 @@ def test_random_matrix_vs_oracle(sb, restatement, forced):
         sb.force_kernel(0)
 
 
+REGRESSION_JOBS = [
+    # found by tools/soak.py: dynamic + static shared memory just above the 48 KB default limit
+    (cases.BGR8, 77, 37, 240, cases.RGBA8_U, 154, 41, 624, 0, "saturated"),
+]
+
+
+def test_regression_jobs(sb, restatement):
+    import torch
+    for job in REGRESSION_JOBS:
+        ti, wi, hi, si, to, wo, ho, so, srgb, mode = job
+        src = cases.make_image(ti, wi, hi, si, mode, seed=1)
+        want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
+        got = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, srgb)
+        assert np.array_equal(got, want), (job, "host")
+        d_in = torch.from_numpy(src).cuda()
+        d_out = torch.full((want.size,), 0xCD, dtype=torch.uint8, device="cuda")
+        sb.scale_simple(d_in, ti, wi, hi, si, d_out, to, wo, ho, so, srgb)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), want), (job, "device")
+
+
 def test_half_kernel_family(sb, restatement):
     """Exact 2^k:1 jobs: automatic dispatch (packed-byte kernel) == general kernel == oracle,
     with device pointers both 16-byte aligned (fast path) and misaligned (fallback)."""
