@@ -1644,11 +1644,20 @@ struct BoxParams
     uint32_t sel_ac0, sel_ac1, sel_ac2;             /* PRMT selectors: (alpha << 8) | colour byte */
     const uint16_t *unpack_tab;                     /* TAB variants: 65536-entry composite unpack table */
     uint32_t acc_fits_24;           /* every accumulator lane stays below 2^24: one-instruction normalisation */
+    /* LUTM = 3 (byte-addressed lane-replicated tables): PRMT selectors that build a table OFFSET
+     * straight from the source pixel: byte 0 = the lane's slot, byte 1 = the alpha / colour byte */
+    uint32_t sel_aaddr, sel_f0, sel_f1, sel_f2;
+    uint32_t mul8_x, mul8_y;        /* span_mul << 8 (span_mul < 2^24 on every box axis) */
+    uint32_t warps_lo;              /* warps whose staging buffers lie below the tables (window < 0x10000) */
 };
 
 __device__ __forceinline__ void cp_async_16 (uint32_t smem_addr, const void *gptr, uint32_t src_bytes)
 {
     asm volatile ("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_16_full (uint32_t smem_addr, const void *gptr)
+{
+    asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gptr) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit ()
 {
@@ -1797,10 +1806,101 @@ template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_scale (const BoxP
     return r;
 }
 
+/* LUTM = 3: unpack one source pixel and add it into the four accumulator lanes in one go, with
+ * byte-addressed lane-replicated tables (linear-light modes only).
+ *
+ * The tables sit at fixed addresses of the CTA's shared-memory WINDOW (not of the kernel's dynamic
+ * allocation), each on a 64 KB boundary:
+ *   from table at 0x10000:    entry u at 0x10000 + u * 256 + lane * 4   (32-bit: from_srgb[u] + 1 for the
+ *                             P8-LINEAR modes -- the premultiply wants lin + 1 --, from_srgb[u] for P16-LINEAR)
+ *   inverse table at 0x20000: entry a at 0x20000 + a * 256 + lane * 8   (64-bit: { inv_div_p8[a] << 3, 8 a + 1 })
+ * An entry's index is byte 1 of its address and the other three bytes are per-lane constants, so
+ * ONE PRMT turns "the register whose byte holds the index" into the load address -- no shift, no
+ * multiply-add, no base addition -- and every lane still reads its own bank whatever the data
+ * (conflict-free gathers).  The warps' staging buffers fill the space below 0x10000 and above the
+ * tables.
+ *
+ * Per channel of a premultiplied source pixel (generic:227-236, :185-199, :261-269):
+ *   u = ((c * inv8) >> 16) & 0xff; lin = from_srgb[u]; out = ((lin + 1) * (8 a + 1) - 1) >> 11
+ * which is PRMT (c), IMAD, PRMT (address), LDS, IMAD, LEA.HI (accumulate) here.
+ * WEIGHTED: the pixel is an edge of the span, each lane is scaled by w / 256 first (generic:1177-1192).
+ * from_y / inv_y: this lane's table addresses for index 0. */
+#define SMOL_BOX3_FROM_WIN 0x10000u
+#define SMOL_BOX3_INV_WIN  0x20000u
+
+__device__ __forceinline__ uint32_t lds_u32 (uint32_t addr)
+{
+    uint32_t v;
+    asm ("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64 (uint32_t addr)
+{
+    uint2 v;
+    asm ("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+/* staging-buffer read: ordered against the cp.async / __syncwarp around it */
+__device__ __forceinline__ uint32_t lds_u32_ordered (uint32_t addr)
+{
+    uint32_t v;
+    asm volatile ("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+template <int MODE, bool WEIGHTED>
+__device__ __forceinline__ void
+box3_accum (uint32_t raw, uint32_t w, uint32_t acc[4], const BoxParams &P, uint32_t from_y, uint32_t inv_y)
+{
+    static_assert (MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U, "linear-light modes only");
+    auto add = [&] (uint32_t &a, uint32_t v, int shift)
+    {
+        if constexpr (WEIGHTED)
+            a += ((v >> shift) * w) >> 8;
+        else
+            a += v >> shift;
+    };
+
+    if constexpr (MODE == BM_P8L_P)
+    {
+        const uint2 im = lds_u64 (__byte_perm (raw, inv_y, P.sel_aaddr));
+        const uint32_t c[3] = { __byte_perm (raw, 0, P.sel_c0), __byte_perm (raw, 0, P.sel_c1), __byte_perm (raw, 0, P.sel_c2) };
+        add (acc[0], im.y, 3);                                      /* alpha = (8 a + 1) >> 3 */
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            const uint32_t lin1 = lds_u32 (__byte_perm (c[i] * im.x, from_y, 0x7624));
+            add (acc[i + 1], lin1 * im.y - 1, 11);
+        }
+    }
+    else
+    {
+        const uint32_t alpha = __byte_perm (raw, 0, P.sel_alpha);
+        const uint32_t lin[3] = { lds_u32 (__byte_perm (raw, from_y, P.sel_f0)), lds_u32 (__byte_perm (raw, from_y, P.sel_f1)),
+                                  lds_u32 (__byte_perm (raw, from_y, P.sel_f2)) };
+        if constexpr (MODE == BM_P8L_U)
+        {
+            const uint32_t m = alpha * 8 + 1;
+            add (acc[0], alpha, 0);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                add (acc[i + 1], lin[i] * m - 1, 11);
+        }
+        else
+        {
+            add (acc[0], (alpha << 8) | 0x80, 0);                   /* generic:616-625 */
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                add (acc[i + 1], lin[i] * alpha, 0);
+        }
+    }
+}
+
 /* LUTM = 1: one big CTA per SM (128 KB composite table + the warps' staging buffers);
- * LUTM = 2: 512-thread CTAs with lane-replicated LUTs; LUTM = 0: 256-thread CTAs, plain LUTs. */
+ * LUTM = 2: 512-thread CTAs with lane-replicated LUTs; LUTM = 0: 256-thread CTAs, plain LUTs;
+ * LUTM = 3: one big CTA per SM, byte-addressed lane-replicated LUTs (see box3_accum). */
 template <int MODE, int LUTM, int BI>
-__global__ void __launch_bounds__ (LUTM == 1 ? 1024 : LUTM == 2 ? 512 : 256, LUTM == 1 ? 1 : LUTM == 2 ? 2 : 5)
+__global__ void __launch_bounds__ (LUTM == 1 || LUTM == 3 ? 1024 : LUTM == 2 ? 512 : 256, LUTM == 1 || LUTM == 3 ? 1 : LUTM == 2 ? 2 : 5)
 smol_box_kernel (const BoxParams P)
 {
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
@@ -1812,6 +1912,9 @@ smol_box_kernel (const BoxParams P)
     constexpr bool NEED_FROM = MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U;
     constexpr uint32_t REP_BYTES = LUTM == 2 ? ((NEED_INV ? 32768u : 0u) + (NEED_FROM ? 32768u : 0u)) : 0u;
     constexpr uint32_t TAB_BYTES = TAB ? 65536 * 2 : REP_BYTES;
+    /* LUTM = 3: first window address above the tables */
+    constexpr uint32_t WIN_HI = NEED_INV ? SMOL_BOX3_INV_WIN + 65536u : SMOL_BOX3_FROM_WIN + 65536u;
+    static_assert (LUTM != 3 || NEED_FROM, "byte-addressed tables: linear-light modes only");
     const SmolJobDesc &d = P.d;
     const uint16_t *sm_tab = reinterpret_cast<const uint16_t *> (sm_dyn);
     const uint32_t *sm_inv8 = sm_inv8_plain, *sm_from = sm_from_plain;
@@ -1841,6 +1944,22 @@ smol_box_kernel (const BoxParams P)
         sm_from = rep_from + (threadIdx.x & 31);
         sm_inv8 = rep_inv + (threadIdx.x & 31);
     }
+    else if constexpr (LUTM == 3)
+    {
+        /* layout: see box3_accum; window address -> offset inside the dynamic allocation */
+        const uint32_t dyn_win = (uint32_t) __cvta_generic_to_shared (sm_dyn) & 0x00ffffffu;
+        if (dyn_win > 0x480u)
+            __trap ();                  /* the host sized the low staging region for a start at or below 0x480 */
+        uint32_t *t_from = reinterpret_cast<uint32_t *> (sm_dyn + (SMOL_BOX3_FROM_WIN - dyn_win));
+        uint2 *t_inv = reinterpret_cast<uint2 *> (sm_dyn + (SMOL_BOX3_INV_WIN - dyn_win));
+        for (uint32_t i = threadIdx.x; i < 8192; i += blockDim.x)
+        {
+            const uint32_t e = i >> 5, l = i & 31;
+            t_from[e * 64 + l] = (uint32_t) P.luts->from_srgb[e] + (MODE == BM_P16L_U ? 0u : 1u);
+            if constexpr (NEED_INV)
+                t_inv[e * 32 + l] = make_uint2 (P.luts->inv_div_p8[e] << 3, e * 8 + 1);
+        }
+    }
     else
     {
         if constexpr (NEED_INV)
@@ -1855,6 +1974,13 @@ smol_box_kernel (const BoxParams P)
     const uint32_t G = 1u << P.lanes_per_col_log2, g = lane & (G - 1);
     const uint32_t cols_per_item = 32u >> P.lanes_per_col_log2;
     uint8_t *bufs = sm_dyn + TAB_BYTES + (size_t) warp * 2 * P.seg_bytes;
+    if constexpr (LUTM == 3)
+    {
+        /* staging buffers: the first warps_lo warps below the tables, the others above them */
+        const uint32_t dyn_win = (uint32_t) __cvta_generic_to_shared (sm_dyn) & 0x00ffffffu;
+        bufs = warp < P.warps_lo ? sm_dyn + (size_t) warp * 2 * P.seg_bytes
+                                 : sm_dyn + (WIN_HI - dyn_win) + (size_t) (warp - P.warps_lo) * 2 * P.seg_bytes;
+    }
     const uint32_t bufs_addr = (uint32_t) __cvta_generic_to_shared (bufs);
     const uint32_t row_bytes = d.w_in * BI;
 
@@ -1933,6 +2059,130 @@ smol_box_kernel (const BoxParams P)
 #pragma unroll
         for (int i = 0; i < (S128 ? 4 : 2); i++) vacc.v[i] = 0;
 
+        if constexpr (LUTM == 3)
+        {
+            /* Lean row loop for the byte-addressed tables: the window's chunks are copied whole
+             * when the window lies inside the row (all items but a row's last), the span is walked
+             * with a shared-memory byte offset, pixels are unpacked straight into the accumulators,
+             * and normalisation is one multiply-high per lane ((acc * mul + 2^23) >> 24 ==
+             * hi32 (acc * (mul << 8) + 2^31) for any 32-bit acc). */
+            const bool win_full = win0 + 16 * n_chunks <= row_bytes;
+            const uint32_t win_hi = bufs_addr & 0xff000000u;        /* the CTA's window */
+            const uint32_t from_y = win_hi | SMOL_BOX3_FROM_WIN | (lane * 4), inv_y = win_hi | SMOL_BOX3_INV_WIN | (lane * 8);
+            /* byte offsets into the staging buffer of the first whole pixel of this lane, of the
+             * span's end, and of the two edge pixels (32bpp; 24bpp goes through fetch3) */
+            const uint32_t o_first = (hL + 1 + g) * 4 - win0, o_end = hR * 4 - win0;
+            const uint32_t o_left = hL * 4 - win0;
+            uint32_t cur = 0;                                       /* byte offset of the slot in use: 0 or seg_bytes */
+
+            auto prefetch3 = [&] (uint32_t slot_ofs)
+            {
+                const uint32_t sbase = sbuf + slot_ofs;
+                if (win_full)
+                {
+                    if (cvalid[0])
+                        cp_async_16_full (sbase, grow);
+                    if (cvalid[1])
+                        cp_async_16_full (sbase + 512, grow + 512);
+                    if (cvalid[2])
+                        cp_async_16_full (sbase + 1024, grow + 1024);
+                }
+                else
+                {
+                    if (cvalid[0])
+                        cp_async_16 (sbase, grow, cvalid[0]);
+                    if (cvalid[1])
+                        cp_async_16 (sbase + 512, grow + 512, cvalid[1]);
+                    if (cvalid[2])
+                        cp_async_16 (sbase + 1024, grow + 1024, cvalid[2]);
+                }
+                if (n_chunks > 96)
+                {
+                    for (uint32_t k = lane + 96; k < n_chunks; k += 32)
+                    {
+                        const uint32_t ofs = win0 + 16 * k;
+                        if (ofs < row_bytes)
+                            cp_async_16 (sbase + 16 * (k - lane), grow + 16 * (k - lane), min (16u, row_bytes - ofs));
+                    }
+                }
+                cp_async_commit ();
+                grow += P.src_pitch;
+            };
+
+            prefetch3 (0);
+            for (uint32_t r = T; r <= r_end; r++)
+            {
+                if (r < r_end)
+                {
+                    prefetch3 (P.seg_bytes - cur);
+                    cp_async_wait<1> ();
+                }
+                else
+                    cp_async_wait<0> ();
+                __syncwarp ();
+
+                const uint32_t row = bufs_addr + cur;               /* window address of the staged segment */
+                auto fetch3 = [&] (uint32_t j) -> uint32_t
+                {
+                    const uint32_t b = j * 3 - win0, a = row + (b & ~3u);
+                    return __funnelshift_r (lds_u32_ordered (a), lds_u32_ordered (a + 4), (b & 3) * 8) | 0xff000000u;
+                };
+                uint32_t acc[4] = { 0, 0, 0, 0 };
+
+                if constexpr (BI == 4)
+                {
+                    for (uint32_t a = row + o_first, a_end = row + o_end; a < a_end; a += 4 * G)
+                        box3_accum<MODE, false> (lds_u32_ordered (a), 0, acc, P, from_y, inv_y);
+                    if (g == 0)
+                        box3_accum<MODE, true> (lds_u32_ordered (row + o_left), wl, acc, P, from_y, inv_y);
+                    if (g == G - 1 && wr > 0)
+                        box3_accum<MODE, true> (lds_u32_ordered (row + o_end), wr, acc, P, from_y, inv_y);
+                }
+                else
+                {
+                    for (uint32_t j = hL + 1 + g; j < hR; j += G)
+                        box3_accum<MODE, false> (fetch3 (j), 0, acc, P, from_y, inv_y);
+                    if (g == 0)
+                        box3_accum<MODE, true> (fetch3 (hL), wl, acc, P, from_y, inv_y);
+                    if (g == G - 1 && wr > 0)
+                        box3_accum<MODE, true> (fetch3 (hR), wr, acc, P, from_y, inv_y);
+                }
+                for (uint32_t m = G >> 1; m; m >>= 1)
+                {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        acc[i] += __shfl_xor_sync (0xffffffffu, acc[i], m);
+                }
+
+                /* scale_128bpp_half (generic:1247-1261): the 16-bit mask cannot bite in the
+                 * P8-LINEAR modes (lanes are averages of values below 2^11) */
+                uint32_t h[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                {
+                    h[i] = (uint32_t) (((uint64_t) acc[i] * P.mul8_x + 0x80000000ull) >> 32);
+                    if constexpr (MODE == BM_P16L_U)
+                        h[i] &= 0xffffu;
+                }
+                if (r == T || r == B)
+                {
+                    const uint32_t wrow = r == T ? w1 : w2;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        vacc.v[i] += (h[i] * wrow) >> 8;
+                }
+                else
+                {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        vacc.v[i] += h[i];
+                }
+                cur = P.seg_bytes - cur;
+                __syncwarp ();      /* everyone is done with this slot before it is refilled */
+            }
+        }
+        else
+        {
         prefetch (0);
         for (uint32_t r = T; r <= r_end; r++)
         {
@@ -1985,6 +2235,7 @@ smol_box_kernel (const BoxParams P)
                 h = box_weight<MODE> (h, w2);
             box_add<MODE> (vacc, h);
             __syncwarp ();      /* everyone is done with this slot before it is refilled */
+        }
         }
 
         const BoxPx<MODE> fin = box_scale<MODE> (vacc, d.span_mul_y, P.acc_fits_24 != 0);
@@ -2976,6 +3227,13 @@ box_params_init (BoxParams &P, const SmolLaunch &L)
     P.sel_ac1 = 0x4400u | (alpha_idx << 4) | (d.in_col0 + 1u);
     P.sel_ac2 = 0x4400u | (alpha_idx << 4) | (d.in_col0 + 2u);
     P.unpack_tab = d.in_unassoc ? L.p8l_from_u : L.p8l_from_p;
+    P.sel_aaddr = 0x7604u | (alpha_idx << 4);
+    P.sel_f0 = 0x7604u | ((uint32_t) d.in_col0 << 4);
+    P.sel_f1 = 0x7604u | ((d.in_col0 + 1u) << 4);
+    P.sel_f2 = 0x7604u | ((d.in_col0 + 2u) << 4);
+    P.warps_lo = 0;
+    P.mul8_x = d.span_mul_x << 8;
+    P.mul8_y = d.span_mul_y << 8;
     {
         /* largest lane value after unpack x the longest span (+ 2 edge pixels) on either axis */
         const uint64_t lane_max = d.mid == SMOL_MID_P8 ? 255 : d.mid == SMOL_MID_P8L ? 2047
@@ -3008,17 +3266,35 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     {
         const char *e = getenv ("SMOL_BOX_G_LOG2"), *t = getenv ("SMOL_BOX_LUTM");
         tune_g = e ? atoi (e) : 99;
-        tune_lut = t ? atoi (t) : 2;
+        tune_lut = t ? atoi (t) : 3;
     }
-    /* table placement (see box_unpack): modes without gathers need none */
+    /* table placement (see box_unpack / box3_accum): modes without gathers need none */
     const bool has_lut = mode == BM_P8L_P || mode == BM_P8L_U || mode == BM_P16L_U;
     int lutm = has_lut ? tune_lut : 0;
     if (lutm == 1 && d.mid != SMOL_MID_P8L)
         lutm = 2;
+    if (lutm == 3 && (d.span_mul_x >= (1u << 24) || d.span_mul_y >= (1u << 24)))
+        lutm = 2;                       /* the multiply-high normalisation wants span_mul << 8 in 32 bits */
+    if (lutm == 3)
+    {
+        /* the 64 KB-per-table layout must leave room for at least 8 warps' staging buffers
+         * (longest segments: the starting G of the loop below) */
+        const uint32_t ratio0 = d.w_in / d.w_out;
+        uint32_t glog0 = 0;
+        while (glog0 < 5 && ratio0 >= (16u << glog0))
+            glog0++;
+        if (tune_g != 99)
+            glog0 = (uint32_t) tune_g;
+        const uint64_t seg_px0 = ((uint64_t) (32u >> glog0) * d.w_in + d.w_out - 1) / d.w_out + 3;
+        const size_t per_warp0 = 2 * (size_t) ((seg_px0 * d.bpp_in + 32 + 15) & ~(uint64_t) 15);
+        const size_t win_hi0 = mode == BM_P8L_P ? 0x30000 : 0x20000;
+        if ((0x10000 - 0x480) / per_warp0 + (225 * 1024 - 64 - (win_hi0 - 0x400)) / per_warp0 < 8)
+            lutm = 2;
+    }
 
     const bool bi3 = d.bpp_in == 3;     /* 24bpp sources are never unassociated: modes P8_P / P8L_P only */
-#define BOX_KERNEL_FOR(M) (lutm == 1 ? (const void *) smol_box_kernel<M, 1, 4> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 4> : (const void *) smol_box_kernel<M, 0, 4>)
-#define BOX_KERNEL_FOR3(M) (lutm == 1 ? (const void *) smol_box_kernel<M, 1, 3> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 3> : (const void *) smol_box_kernel<M, 0, 3>)
+#define BOX_KERNEL_FOR(M) (lutm == 3 ? (const void *) smol_box_kernel<M, 3, 4> : lutm == 1 ? (const void *) smol_box_kernel<M, 1, 4> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 4> : (const void *) smol_box_kernel<M, 0, 4>)
+#define BOX_KERNEL_FOR3(M) (lutm == 3 ? (const void *) smol_box_kernel<M, 3, 3> : lutm == 1 ? (const void *) smol_box_kernel<M, 1, 3> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 3> : (const void *) smol_box_kernel<M, 0, 3>)
     const void *fn;
     switch (mode)
     {
@@ -3027,7 +3303,8 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         case BM_P8L_P:  fn = bi3 ? BOX_KERNEL_FOR3 (BM_P8L_P) : BOX_KERNEL_FOR (BM_P8L_P); break;
         case BM_P8L_U:  fn = BOX_KERNEL_FOR (BM_P8L_U); break;
         case BM_P16_U:  fn = (const void *) smol_box_kernel<BM_P16_U, 0, 4>; break;
-        default:        fn = lutm == 2 ? (const void *) smol_box_kernel<BM_P16L_U, 2, 4> : (const void *) smol_box_kernel<BM_P16L_U, 0, 4>; break;
+        default:        fn = lutm == 3 ? (const void *) smol_box_kernel<BM_P16L_U, 3, 4>
+                             : lutm == 2 ? (const void *) smol_box_kernel<BM_P16L_U, 2, 4> : (const void *) smol_box_kernel<BM_P16L_U, 0, 4>; break;
     }
 #undef BOX_KERNEL_FOR
 #undef BOX_KERNEL_FOR3
@@ -3041,6 +3318,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         glog++;
 
     const size_t lut_bytes = lutm == 1 ? 131072
+                             : lutm == 3 ? (mode == BM_P8L_P ? 131072 : 65536)
                              : lutm == 2 ? (mode == BM_P8L_P ? 65536 : 32768) : 0;
     size_t smem = 0;
     uint32_t per_sm = 1, warps_per_cta = lutm == 2 ? 16 : 8;
@@ -3056,12 +3334,28 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         P.seg_bytes = (uint32_t) ((seg_px * d.bpp_in + 32 + 15) & ~(uint64_t) 15);
         if (lutm == 1)
         {
-            /* one CTA per SM: as many warps as fit beside the 128 KB table */
+            /* one CTA per SM: as many warps as fit beside the tables */
             const size_t room = 220 * 1024 - lut_bytes;
             warps_per_cta = (uint32_t) (room / (2 * (size_t) P.seg_bytes));
             warps_per_cta = warps_per_cta > 32 ? 32 : warps_per_cta < 4 ? 4 : warps_per_cta;
         }
         smem = lut_bytes + (size_t) warps_per_cta * 2 * P.seg_bytes;
+        if (lutm == 3)
+        {
+            /* One CTA per SM.  The tables sit at window addresses 0x10000 (+ 0x20000); staging
+             * buffers go below them (the allocation starts a little above the 1 KB the system
+             * reserves) and above them, up to the 225 KB opted in to. */
+            const size_t per_warp = 2 * (size_t) P.seg_bytes;
+            const size_t win_hi = lut_bytes == 131072 ? 0x30000 : 0x20000;
+            const size_t dyn_max = 225 * 1024 - 64;
+            const size_t lo_room = 0x10000 - 0x480, hi_room = dyn_max - (win_hi - 0x400);
+            uint32_t lo = (uint32_t) (lo_room / per_warp), hi = (uint32_t) (hi_room / per_warp);
+            lo = lo > 32 ? 32 : lo;
+            hi = hi > 32 - lo ? 32 - lo : hi;
+            P.warps_lo = lo;
+            warps_per_cta = lo + hi;
+            smem = (win_hi - 0x400) + hi * per_warp;
+        }
         if (smem > 32 * 1024)        /* static shared memory counts against the 48 KB default too */
             cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         int occ = 0;
@@ -3080,7 +3374,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     dim3 grid ((unsigned) blocks), block (warps_per_cta * 32);
 
 #define BOX_LAUNCH(M, LM, B) launch_pdl (smol_box_kernel<M, LM, B>, P, grid, block, smem, stream)
-#define BOX_LAUNCH_LUT(M, B) (lutm == 1 ? BOX_LAUNCH (M, 1, B) : lutm == 2 ? BOX_LAUNCH (M, 2, B) : BOX_LAUNCH (M, 0, B))
+#define BOX_LAUNCH_LUT(M, B) (lutm == 3 ? BOX_LAUNCH (M, 3, B) : lutm == 1 ? BOX_LAUNCH (M, 1, B) : lutm == 2 ? BOX_LAUNCH (M, 2, B) : BOX_LAUNCH (M, 0, B))
     switch (mode)
     {
         case BM_P8_P:   return bi3 ? BOX_LAUNCH (BM_P8_P, 0, 3) : BOX_LAUNCH (BM_P8_P, 0, 4);
@@ -3088,7 +3382,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         case BM_P8L_P:  return bi3 ? BOX_LAUNCH_LUT (BM_P8L_P, 3) : BOX_LAUNCH_LUT (BM_P8L_P, 4);
         case BM_P8L_U:  return BOX_LAUNCH_LUT (BM_P8L_U, 4);
         case BM_P16_U:  return BOX_LAUNCH (BM_P16_U, 0, 4);
-        default:        return lutm == 2 ? BOX_LAUNCH (BM_P16L_U, 2, 4) : BOX_LAUNCH (BM_P16L_U, 0, 4);
+        default:        return lutm == 3 ? BOX_LAUNCH (BM_P16L_U, 3, 4) : lutm == 2 ? BOX_LAUNCH (BM_P16L_U, 2, 4) : BOX_LAUNCH (BM_P16L_U, 0, 4);
     }
 #undef BOX_LAUNCH_LUT
 #undef BOX_LAUNCH
