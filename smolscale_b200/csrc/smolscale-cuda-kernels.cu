@@ -1649,6 +1649,7 @@ struct BoxParams
     uint32_t sel_aaddr, sel_f0, sel_f1, sel_f2;
     uint32_t mul8_x, mul8_y;        /* span_mul << 8 (span_mul < 2^24 on every box axis) */
     uint32_t warps_lo;              /* warps whose staging buffers lie below the tables (window < 0x10000) */
+    uint32_t unroll2;               /* walk the span two pixels per trip */
 };
 
 __device__ __forceinline__ void cp_async_16 (uint32_t smem_addr, const void *gptr, uint32_t src_bytes)
@@ -1826,6 +1827,7 @@ template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_scale (const BoxP
  * WEIGHTED: the pixel is an edge of the span, each lane is scaled by w / 256 first (generic:1177-1192).
  * from_y / inv_y: this lane's table addresses for index 0. */
 #define SMOL_BOX3_FROM_WIN 0x10000u
+
 #define SMOL_BOX3_INV_WIN  0x20000u
 
 __device__ __forceinline__ uint32_t lds_u32 (uint32_t addr)
@@ -1848,6 +1850,15 @@ __device__ __forceinline__ uint32_t lds_u32_ordered (uint32_t addr)
     return v;
 }
 
+/* PRMT with a selector known to have bit 3 of every nibble clear (__byte_perm masks its selector
+ * with 0x7777 first, an extra instruction whenever the selector is a kernel parameter) */
+__device__ __forceinline__ uint32_t prmt_raw (uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm ("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 template <int MODE, bool WEIGHTED>
 __device__ __forceinline__ void
 box3_accum (uint32_t raw, uint32_t w, uint32_t acc[4], const BoxParams &P, uint32_t from_y, uint32_t inv_y)
@@ -1863,8 +1874,8 @@ box3_accum (uint32_t raw, uint32_t w, uint32_t acc[4], const BoxParams &P, uint3
 
     if constexpr (MODE == BM_P8L_P)
     {
-        const uint2 im = lds_u64 (__byte_perm (raw, inv_y, P.sel_aaddr));
-        const uint32_t c[3] = { __byte_perm (raw, 0, P.sel_c0), __byte_perm (raw, 0, P.sel_c1), __byte_perm (raw, 0, P.sel_c2) };
+        const uint2 im = lds_u64 (prmt_raw (raw, inv_y, P.sel_aaddr));
+        const uint32_t c[3] = { prmt_raw (raw, 0, P.sel_c0), prmt_raw (raw, 0, P.sel_c1), prmt_raw (raw, 0, P.sel_c2) };
         add (acc[0], im.y, 3);                                      /* alpha = (8 a + 1) >> 3 */
 #pragma unroll
         for (int i = 0; i < 3; i++)
@@ -1875,9 +1886,9 @@ box3_accum (uint32_t raw, uint32_t w, uint32_t acc[4], const BoxParams &P, uint3
     }
     else
     {
-        const uint32_t alpha = __byte_perm (raw, 0, P.sel_alpha);
-        const uint32_t lin[3] = { lds_u32 (__byte_perm (raw, from_y, P.sel_f0)), lds_u32 (__byte_perm (raw, from_y, P.sel_f1)),
-                                  lds_u32 (__byte_perm (raw, from_y, P.sel_f2)) };
+        const uint32_t alpha = prmt_raw (raw, 0, P.sel_alpha);
+        const uint32_t lin[3] = { lds_u32 (prmt_raw (raw, from_y, P.sel_f0)), lds_u32 (prmt_raw (raw, from_y, P.sel_f1)),
+                                  lds_u32 (prmt_raw (raw, from_y, P.sel_f2)) };
         if constexpr (MODE == BM_P8L_U)
         {
             const uint32_t m = alpha * 8 + 1;
@@ -2131,8 +2142,25 @@ smol_box_kernel (const BoxParams P)
 
                 if constexpr (BI == 4)
                 {
-                    for (uint32_t a = row + o_first, a_end = row + o_end; a < a_end; a += 4 * G)
-                        box3_accum<MODE, false> (lds_u32_ordered (a), 0, acc, P, from_y, inv_y);
+                    uint32_t a = row + o_first;
+                    const uint32_t a_end = row + o_end;
+                    if (P.unroll2)
+                    {
+                        /* two pixels per trip: two independent table chains in flight */
+                        for (; a + 4 * G < a_end; a += 8 * G)
+                        {
+                            const uint32_t raw0 = lds_u32_ordered (a), raw1 = lds_u32_ordered (a + 4 * G);
+                            box3_accum<MODE, false> (raw0, 0, acc, P, from_y, inv_y);
+                            box3_accum<MODE, false> (raw1, 0, acc, P, from_y, inv_y);
+                        }
+                        if (a < a_end)
+                            box3_accum<MODE, false> (lds_u32_ordered (a), 0, acc, P, from_y, inv_y);
+                    }
+                    else
+                    {
+                        for (; a < a_end; a += 4 * G)
+                            box3_accum<MODE, false> (lds_u32_ordered (a), 0, acc, P, from_y, inv_y);
+                    }
                     if (g == 0)
                         box3_accum<MODE, true> (lds_u32_ordered (row + o_left), wl, acc, P, from_y, inv_y);
                     if (g == G - 1 && wr > 0)
@@ -3232,6 +3260,7 @@ box_params_init (BoxParams &P, const SmolLaunch &L)
     P.sel_f1 = 0x7604u | ((d.in_col0 + 1u) << 4);
     P.sel_f2 = 0x7604u | ((d.in_col0 + 2u) << 4);
     P.warps_lo = 0;
+    P.unroll2 = 1;
     P.mul8_x = d.span_mul_x << 8;
     P.mul8_y = d.span_mul_y << 8;
     {
@@ -3261,10 +3290,13 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     else
         mode = d.mid == SMOL_MID_P16 ? BM_P16_U : BM_P16L_U;
 
-    static int tune_g = -1, tune_lut = -1;
+    static int tune_g = -1, tune_lut = -1, tune_wpc = 0, tune_unroll = 1;
     if (tune_g < 0)
     {
-        const char *e = getenv ("SMOL_BOX_G_LOG2"), *t = getenv ("SMOL_BOX_LUTM");
+        const char *e = getenv ("SMOL_BOX_G_LOG2"), *t = getenv ("SMOL_BOX_LUTM"), *w = getenv ("SMOL_BOX_WPC");
+        tune_wpc = w ? atoi (w) : 0;
+        const char *u = getenv ("SMOL_BOX_UNROLL");
+        tune_unroll = u ? atoi (u) : 1;
         tune_g = e ? atoi (e) : 99;
         tune_lut = t ? atoi (t) : 3;
     }
@@ -3292,6 +3324,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
             lutm = 2;
     }
 
+    P.unroll2 = tune_unroll != 0;
     const bool bi3 = d.bpp_in == 3;     /* 24bpp sources are never unassociated: modes P8_P / P8L_P only */
 #define BOX_KERNEL_FOR(M) (lutm == 3 ? (const void *) smol_box_kernel<M, 3, 4> : lutm == 1 ? (const void *) smol_box_kernel<M, 1, 4> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 4> : (const void *) smol_box_kernel<M, 0, 4>)
 #define BOX_KERNEL_FOR3(M) (lutm == 3 ? (const void *) smol_box_kernel<M, 3, 3> : lutm == 1 ? (const void *) smol_box_kernel<M, 1, 3> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 3> : (const void *) smol_box_kernel<M, 0, 3>)
@@ -3352,6 +3385,31 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
             uint32_t lo = (uint32_t) (lo_room / per_warp), hi = (uint32_t) (hi_room / per_warp);
             lo = lo > 32 ? 32 : lo;
             hi = hi > 32 - lo ? 32 - lo : hi;
+            /* Every work item costs the same and a warp takes ceil (items / warps) of them, so
+             * the kernel's length is quantised: among the warp counts that fit (down to 5/8 of
+             * the most) take the one that wastes the smallest share of its last round. */
+            {
+                const uint32_t w_max = lo + hi;
+                const uint64_t items = (uint64_t) ((d.w_out + cols - 1) / cols) * L.n_rows * L.n_images;
+                uint32_t best_w = w_max;
+                double best_eff = 0.0;
+                for (uint32_t w = w_max; w >= 8 && w * 8 >= w_max * 5; w--)
+                {
+                    const uint64_t slots = (uint64_t) num_sms () * w;
+                    const uint64_t rounds = (items + slots - 1) / slots;
+                    const double eff = (double) items / (double) (rounds * slots);
+                    if (eff > best_eff + 0.02)
+                    {
+                        best_eff = eff;
+                        best_w = w;
+                    }
+                }
+                if (tune_wpc > 0 && (uint32_t) tune_wpc <= w_max)
+                    best_w = (uint32_t) tune_wpc;
+                if (best_w < lo)
+                    lo = best_w;
+                hi = best_w - lo;
+            }
             P.warps_lo = lo;
             warps_per_cta = lo + hi;
             smem = (win_hi - 0x400) + hi * per_warp;
