@@ -95,6 +95,12 @@ SmolCudaStats;
 void smol_cuda_get_stats (SmolCudaStats *stats);
 void smol_cuda_reset_stats (void);
 
+/* Launches per kernel family since the last reset: fills counts[0..n) and, if `names` is not
+ * NULL, the families' static names; returns n (at most max_families).  The family recorded is the
+ * one that actually ran, after any fallback to the general kernel. */
+#define SMOL_CUDA_MAX_KERNEL_FAMILIES 16
+int smol_cuda_get_kernel_launches (uint64_t *counts, const char **names, int max_families);
+
 /* Forces a kernel family for testing (0 = automatic).  See SMOL_KERNEL_* in
  * smolscale-cuda-private.h; families that cannot run the job fall back to the general one. */
 void smol_cuda_force_kernel (int kernel_id);

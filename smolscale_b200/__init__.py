@@ -18,7 +18,7 @@ from . import _build
 
 __all__ = ["PixelType", "ScaleCtx", "scale_simple", "scale_images", "lib", "plan_query",
            "device_count", "set_stream", "set_device", "synchronize", "stats", "reset_stats",
-           "force_kernel", "bytes_per_pixel", "LIB_PATH"]
+           "force_kernel", "kernel_launches", "bytes_per_pixel", "LIB_PATH"]
 
 LIB_PATH = _build.LIB_PATH
 
@@ -68,7 +68,7 @@ EXPORTED_SYMBOLS = [
     "smol_scale_batch", "smol_scale_batch_full",
     "smol_cuda_device_count", "smol_cuda_set_device", "smol_cuda_set_stream", "smol_cuda_synchronize",
     "smol_cuda_scale_images", "smol_cuda_plan_query", "smol_cuda_band_source_rows",
-    "smol_cuda_get_stats", "smol_cuda_reset_stats", "smol_cuda_force_kernel",
+    "smol_cuda_get_stats", "smol_cuda_reset_stats", "smol_cuda_force_kernel", "smol_cuda_get_kernel_launches",
 ]
 
 _lib = None
@@ -114,6 +114,9 @@ def lib():
     L.smol_cuda_get_stats.argtypes = [ctypes.POINTER(Stats)]
     L.smol_cuda_reset_stats.argtypes = []
     L.smol_cuda_force_kernel.argtypes = [ctypes.c_int]
+    L.smol_cuda_get_kernel_launches.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_char_p),
+                                                ctypes.c_int]
+    L.smol_cuda_get_kernel_launches.restype = ctypes.c_int
     _lib = L
     return L
 
@@ -234,6 +237,14 @@ def stats():
     s = Stats()
     lib().smol_cuda_get_stats(ctypes.byref(s))
     return {name: getattr(s, name) for name, _ in Stats._fields_}
+
+
+def kernel_launches():
+    """Launches per kernel family since the last reset_stats(): {family name: count}."""
+    counts = (ctypes.c_uint64 * 16)()
+    names = (ctypes.c_char_p * 16)()
+    n = lib().smol_cuda_get_kernel_launches(counts, names, 16)
+    return {names[k].decode(): int(counts[k]) for k in range(n)}
 
 
 def reset_stats():

@@ -1606,6 +1606,242 @@ smol_mag_kernel (const MagParams M)
 }
 
 /* ------------------------------------------------------------------------------------------ *
+ * "magb" kernel: the magnification tile again, but BYTE-granular in its vertical stage          *
+ * (BASELINE config 4; any 24/32bpp pair whose output needs no per-pixel alpha operation).       *
+ *                                                                                              *
+ * Once the horizontal pass has put every channel in destination byte order, the vertical tap    *
+ * is the same operation on every BYTE of the output row -- pixel boundaries stop mattering.     *
+ * So the tile is tile_b output BYTES wide (a multiple of 16, not of the pixel size) and:        *
+ *   1. the source window is loaded (24bpp: four pixels = three aligned words per step) and      *
+ *      unpacked once per source pixel into 16-bit lanes;                                        *
+ *   2. the horizontal taps run once per (source row, group of 4 output pixels); results are     *
+ *      reordered to destination bytes by one PRMT per pixel and stored PACKED (12 or 16 bytes   *
+ *      per group) as the tile's horizontally filtered rows;                                     *
+ *   3. a thread owns one 16-byte column of the tile and walks output rows: per run of rows that *
+ *      share a source row pair, two 128-bit shared-memory reads expanded to 16-bit lanes; per   *
+ *      output row 16 multiply-adds (two bytes each), 4 PRMTs, ONE 128-bit store -- 1 multiply   *
+ *      per output byte and a fully coalesced row segment per warp whatever the pixel size       *
+ *      (the per-pixel kernel above spends 16 multiplies and 3 stores per 12 bytes at 24bpp).    *
+ * ------------------------------------------------------------------------------------------ */
+
+struct MagbParams
+{
+    TapsParams t;
+    uint32_t nb_row;                /* bytes per output row: w_out * bpp_out */
+    uint32_t tile_b, tile_h;        /* output tile: tile_b bytes (16 << chunks_log2), tile_h rows (<= 64) */
+    uint32_t chunks_log2;           /* log2 (tile_b / 16), at most 8 */
+    uint32_t gcols_log2;            /* thread columns of stage 2: power of two >= pixel groups per tile, at most 8 */
+    uint32_t u_pitch;               /* pixels per row of the unpacked source window */
+    uint32_t u_cw, u_cw_log2;       /* thread columns of stage 1 (power of two, at most 256) */
+    uint32_t h_pitch;               /* bytes per horizontally filtered row: tile_b + 32 */
+    uint32_t max_src_rows;
+    uint32_t acc_prmt_sel;          /* (acc_a, acc_b) high bytes -> destination byte order */
+};
+
+/* BI / BO bytes per pixel in / out; IU unassociated input (premultiplied on unpack); AF alpha is
+ * byte 0 of the source pixel; SRC32 source rows are 4-byte aligned. */
+template <int BI, int BO, bool IU, bool AF, bool SRC32>
+__global__ void __launch_bounds__ (256)
+smol_magb_kernel (const MagbParams M)
+{
+    extern __shared__ __align__ (16) uint8_t sm_dyn[];
+    __shared__ uint32_t sm_ty[64];
+    const TapsParams &P = M.t;
+    const uint32_t tid = threadIdx.x;
+    constexpr bool GROUPS = BI == 3 && SRC32;       /* stage 1 works on groups of four 24bpp pixels */
+
+    pdl_launch_dependents ();
+
+    const uint32_t b0 = blockIdx.x * M.tile_b;
+    const uint32_t b1 = min (b0 + M.tile_b, M.nb_row);             /* exclusive */
+    const uint32_t yl0 = blockIdx.y * M.tile_h;
+    const uint32_t yl1 = min (yl0 + M.tile_h, P.n_rows);
+    const uint32_t th = yl1 - yl0;
+    /* groups of four output pixels that overlap the tile's bytes */
+    const uint32_t g_lo = b0 / (4 * BO), g_hi = (b1 - 1) / (4 * BO);
+    const uint32_t n_groups = g_hi - g_lo + 1;
+    const uint32_t x_hi = min (4 * g_hi + 3, P.w_out - 1);
+
+    /* source window (tables are library-owned: readable before the dependency wait) */
+    uint32_t c_lo = SMOL_TAB_OFS (__ldg (&P.tab_x[4 * g_lo]));
+    if constexpr (GROUPS)
+        c_lo &= ~3u;
+    const uint32_t c_hi = min (SMOL_TAB_OFS (__ldg (&P.tab_x[x_hi])) + 1, P.w_in - 1);
+    const uint32_t r_lo = SMOL_TAB_OFS (__ldg (&P.tab_y[P.first_row + yl0]));
+    const uint32_t r_hi = min (SMOL_TAB_OFS (__ldg (&P.tab_y[P.first_row + yl1 - 1])) + 1, P.h_in - 1);
+    const uint32_t n_cols = c_hi - c_lo + 1, n_rows = r_hi - r_lo + 1;
+    if (tid < th)
+        sm_ty[tid] = __ldg (&P.tab_y[P.first_row + yl0 + tid]);
+
+    uint2 *sm_u = reinterpret_cast<uint2 *> (sm_dyn);                               /* [rows][u_pitch] unpacked source */
+    uint8_t *sm_h = sm_dyn + (size_t) M.max_src_rows * M.u_pitch * 8;               /* [rows][h_pitch] filtered rows, destination bytes */
+
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
+    uint8_t *dst_img = P.dst + (size_t) blockIdx.z * P.dst_image_stride;
+
+    pdl_wait ();
+
+    /* stage 1: load + unpack the source window */
+    {
+        auto unpack_store = [&] (uint32_t raw, uint2 *to)
+        {
+            uint32_t a = raw & 0x00ff00ffu, b2 = (raw >> 8) & 0x00ff00ffu;
+            if constexpr (IU)
+            {
+                /* premultiply: ((c + 1) * (alpha + 1) - 1) >> 8, alpha lane untouched (generic:238-244) */
+                if constexpr (AF)
+                {
+                    const uint32_t alpha = raw & 0xff, m = alpha + 1;
+                    a = (((((a & 0x00ff0000u) + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff0000u) | alpha;
+                    b2 = (((b2 + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff00ffu;
+                }
+                else
+                {
+                    const uint32_t alpha = raw >> 24, m = alpha + 1;
+                    a = (((a + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff00ffu;
+                    b2 = (((((b2 & 0x000000ffu) + 0x00010001u) * m - 0x00010001u) >> 8) & 0x000000ffu) | (alpha << 16);
+                }
+            }
+            *to = make_uint2 (a, b2);
+        };
+        auto load_bytes = [&] (const uint8_t *p) -> uint32_t
+        {
+            uint32_t raw = (uint32_t) __ldg (p) | ((uint32_t) __ldg (p + 1) << 8) | ((uint32_t) __ldg (p + 2) << 16);
+            raw |= BI == 4 ? ((uint32_t) __ldg (p + 3) << 24) : 0xff000000u;
+            return raw;
+        };
+        const uint32_t n_items = GROUPS ? (n_cols + 3) >> 2 : n_cols;
+        const uint32_t ct = tid & (M.u_cw - 1), rt = tid >> M.u_cw_log2, r_step = 256u >> M.u_cw_log2;
+        for (uint32_t r = rt; r < n_rows; r += r_step)
+        {
+            const uint8_t *row = src + (size_t) (r_lo + r) * P.src_pitch + (size_t) c_lo * BI;
+            uint2 *urow = sm_u + r * M.u_pitch;
+            for (uint32_t c = ct; c < n_items; c += M.u_cw)
+            {
+                if constexpr (GROUPS)
+                {
+                    if (c_lo + 4 * c + 3 < P.w_in)
+                    {
+                        /* four pixels = three aligned words (c_lo is a multiple of 4) */
+                        const uint32_t *w = reinterpret_cast<const uint32_t *> (row + 12 * c);
+                        const uint32_t w0 = __ldg (w), w1 = __ldg (w + 1), w2 = __ldg (w + 2);
+                        unpack_store (w0 | 0xff000000u, urow + 4 * c);
+                        unpack_store (__funnelshift_r (w0, w1, 24) | 0xff000000u, urow + 4 * c + 1);
+                        unpack_store (__funnelshift_r (w1, w2, 16) | 0xff000000u, urow + 4 * c + 2);
+                        unpack_store ((w2 >> 8) | 0xff000000u, urow + 4 * c + 3);
+                    }
+                    else
+                    {
+                        for (uint32_t k = 0; k < 4 && c_lo + 4 * c + k < P.w_in; k++)
+                            unpack_store (load_bytes (row + 12 * c + 3 * k), urow + 4 * c + k);
+                    }
+                }
+                else if constexpr (BI == 4 && SRC32)
+                    unpack_store (__ldg (reinterpret_cast<const uint32_t *> (row + 4 * c)), urow + c);
+                else
+                    unpack_store (load_bytes (row + c * BI), urow + c);
+            }
+        }
+    }
+    __syncthreads ();
+
+    /* stage 2: horizontal taps once per (source row, group of four output pixels); the thread's
+     * column of groups is fixed, so offsets and weights stay in registers across rows */
+    {
+        const uint32_t gi = tid & ((1u << M.gcols_log2) - 1), rl = tid >> M.gcols_log2, r_step = 256u >> M.gcols_log2;
+        if (gi < n_groups)
+        {
+            uint32_t op[4], oq[4], F[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                const uint32_t e = __ldg (&P.tab_x[min (4 * (g_lo + gi) + i, P.w_out - 1)]);
+                op[i] = SMOL_TAB_OFS (e) - c_lo;
+                oq[i] = min (SMOL_TAB_OFS (e) + 1, P.w_in - 1) - c_lo;
+                F[i] = SMOL_TAB_F (e);
+            }
+            /* output byte b of the row lives at sm_h[row][16 + b - b0]: the tile's first byte is
+             * 16-byte aligned, groups that start before it (24bpp) fit in the 16 bytes of slack */
+            const uint32_t hofs = 16 + (g_lo + gi) * 4 * BO - b0;
+            for (uint32_t r = rl; r < n_rows; r += r_step)
+            {
+                const uint2 *u = sm_u + r * M.u_pitch;
+                uint32_t D[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                {
+                    const uint2 p = u[op[i]], q = u[oq[i]];
+                    const uint32_t G = 256u - F[i];
+                    D[i] = __byte_perm (p.x * F[i] + q.x * G, p.y * F[i] + q.y * G, M.acc_prmt_sel);
+                }
+                uint8_t *h = sm_h + r * M.h_pitch + hofs;
+                if constexpr (BO == 4)
+                    *reinterpret_cast<uint4 *> (h) = make_uint4 (D[0], D[1], D[2], D[3]);
+                else
+                {
+                    uint32_t *h32 = reinterpret_cast<uint32_t *> (h);
+                    h32[0] = __byte_perm (D[0], D[1], 0x4210);
+                    h32[1] = __byte_perm (D[1], D[2], 0x5421);
+                    h32[2] = __byte_perm (D[2], D[3], 0x6542);
+                }
+            }
+        }
+    }
+    __syncthreads ();
+
+    /* stage 3: vertical taps on bytes.  Thread -> one 16-byte column, a contiguous share of the rows. */
+    const uint32_t c = tid & ((1u << M.chunks_log2) - 1), grp = tid >> M.chunks_log2;
+    const uint32_t bb = b0 + 16 * c;
+    if (bb >= b1)
+        return;
+    const uint32_t n_valid = min (16u, b1 - bb);
+    const uint32_t rows_per = (th + (256u >> M.chunks_log2) - 1) >> (8 - M.chunks_log2);
+    const uint32_t ry_begin = grp * rows_per, ry_end = min (ry_begin + rows_per, th);
+    uint8_t *dst = dst_img + (size_t) (yl0 + ry_begin) * P.dst_pitch + bb;
+    const uint8_t *hcol = sm_h + 16 + 16 * c;
+    uint32_t ry = ry_begin;
+    uint32_t e = ry < ry_end ? sm_ty[ry] : 0;
+    while (ry < ry_end)
+    {
+        /* one run = consecutive output rows that read the same source row pair */
+        const uint32_t ofs = SMOL_TAB_OFS (e);
+        const uint32_t r0 = ofs - r_lo, r1 = min (ofs + 1, P.h_in - 1) - r_lo;
+        const uint4 tv = *reinterpret_cast<const uint4 *> (hcol + r0 * M.h_pitch);
+        const uint4 bv = *reinterpret_cast<const uint4 *> (hcol + r1 * M.h_pitch);
+        const uint32_t tw[4] = { tv.x, tv.y, tv.z, tv.w }, bw[4] = { bv.x, bv.y, bv.z, bv.w };
+        uint32_t T[8], B[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            T[2 * k] = __byte_perm (tw[k], 0, 0x4140);  T[2 * k + 1] = __byte_perm (tw[k], 0, 0x4342);
+            B[2 * k] = __byte_perm (bw[k], 0, 0x4140);  B[2 * k + 1] = __byte_perm (bw[k], 0, 0x4342);
+        }
+
+        do
+        {
+            const uint32_t F = SMOL_TAB_F (e), G = 256u - F;
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                o[j] = __byte_perm (T[2 * j] * F + B[2 * j] * G, T[2 * j + 1] * F + B[2 * j + 1] * G, 0x7531);
+            if (n_valid == 16)
+                *reinterpret_cast<uint4 *> (dst) = make_uint4 (o[0], o[1], o[2], o[3]);
+            else
+            {
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    if ((uint32_t) k < n_valid)
+                        dst[k] = (uint8_t) (o[k >> 2] >> ((k & 3) * 8));
+            }
+            ry++;
+            dst += P.dst_pitch;
+            e = sm_ty[min (ry, th - 1)];
+        }
+        while (ry < ry_end && SMOL_TAB_OFS (e) == ofs);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ *
  * "box" kernel: box filter on both axes (large downscales; BASELINE config 3), 32bpp source.     *
  *                                                                                              *
  * Almost all the work of a big downscale is per SOURCE pixel (unpack, and for linear light the  *
@@ -2641,7 +2877,7 @@ smol_tile128_kernel (const Tile128Params M)
 
 static const char *const kernel_names[SMOL_KERNEL_MAX] =
 {
-    "auto", "general", "taps_direct", "half2x", "box", "mag", "taps128", "tile128"
+    "auto", "general", "taps_direct", "half2x", "box", "mag", "taps128", "tile128", "magb"
 };
 
 extern "C" const char *
@@ -2711,6 +2947,14 @@ mag_eligible (const SmolLaunch &L)
 }
 
 static bool
+magb_eligible (const SmolLaunch &L)
+{
+    /* byte-granular vertical stage: no per-pixel work after the horizontal pass, 16-byte stores */
+    return mag_eligible (L) && !L.d.out_unassoc
+           && aligned16 (L.dst) && (L.dst_pitch & 15) == 0 && (L.dst_image_stride & 15) == 0;
+}
+
+static bool
 box_eligible (const SmolLaunch &L)
 {
     const SmolJobDesc &d = L.d;
@@ -2739,6 +2983,8 @@ smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
 
     if (forced == SMOL_KERNEL_MAG)
         return mag_ok ? SMOL_KERNEL_MAG : SMOL_KERNEL_GENERAL;
+    if (forced == SMOL_KERNEL_MAGB)
+        return magb_eligible (*launch) ? SMOL_KERNEL_MAGB : SMOL_KERNEL_GENERAL;
     if (forced == SMOL_KERNEL_TAPS128)
         return taps128_eligible (*launch) ? SMOL_KERNEL_TAPS128 : SMOL_KERNEL_GENERAL;
     if (forced == SMOL_KERNEL_TILE128)
@@ -2760,6 +3006,8 @@ smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
         return SMOL_KERNEL_TAPS128;
     if (tile128_eligible (*launch) && (forced == SMOL_KERNEL_AUTO || forced == SMOL_KERNEL_TILE128))
         return SMOL_KERNEL_TILE128;
+    if (mag_ok && magb_eligible (*launch))
+        return SMOL_KERNEL_MAGB;
     if (mag_ok)
         return SMOL_KERNEL_MAG;
     if (taps_ok)
@@ -3233,6 +3481,105 @@ launch_mag (const SmolLaunch &L, cudaStream_t stream)
     return launch_mag_fmt<4, 4, false, false, false> (M, grid, smem, stream);
 }
 
+template <int BI, int BO, bool IU, bool AF>
+static cudaError_t
+launch_magb_fmt (const MagbParams &M, bool src32, dim3 grid, size_t smem, cudaStream_t stream)
+{
+    if (src32)
+    {
+        if (smem > 40 * 1024)
+            cudaFuncSetAttribute (smol_magb_kernel<BI, BO, IU, AF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        return launch_pdl (smol_magb_kernel<BI, BO, IU, AF, true>, M, grid, dim3 (256), smem, stream);
+    }
+    if (smem > 40 * 1024)
+        cudaFuncSetAttribute (smol_magb_kernel<BI, BO, IU, AF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return launch_pdl (smol_magb_kernel<BI, BO, IU, AF, false>, M, grid, dim3 (256), smem, stream);
+}
+
+static cudaError_t
+launch_magb (const SmolLaunch &L, cudaStream_t stream)
+{
+    const SmolJobDesc &d = L.d;
+    MagbParams M;
+
+    taps_params_init (M.t, L);
+    static int tune_tb = -1, tune_th = -1;
+    if (tune_tb < 0)
+    {
+        const char *a = getenv ("SMOL_MAGB_TB"), *b = getenv ("SMOL_MAGB_TH");
+        tune_tb = a ? atoi (a) : 0;
+        tune_th = b ? atoi (b) : 0;
+    }
+    M.nb_row = d.w_out * d.bpp_out;
+    /* tile width: 16 << k bytes, the smallest that covers the row, at most 1024 (64 threads wide) */
+    const uint32_t tb_cap = tune_tb >= 16 ? (uint32_t) tune_tb : 1024;
+    M.chunks_log2 = 0;
+    while ((16u << M.chunks_log2) < tb_cap && (16u << M.chunks_log2) < M.nb_row && M.chunks_log2 < 8)
+        M.chunks_log2++;
+    M.tile_b = 16u << M.chunks_log2;
+    M.h_pitch = M.tile_b + 32;
+    M.tile_h = tune_th > 0 ? (uint32_t) (tune_th > 64 ? 64 : tune_th) : 32;
+
+    /* pixel groups per tile: tile_b / (4 bpp) rounded up, + 1 for a group straddling the tile's start */
+    const uint32_t max_groups = (M.tile_b + 4 * d.bpp_out - 1) / (4 * d.bpp_out) + 1;
+    M.gcols_log2 = 0;
+    while ((1u << M.gcols_log2) < max_groups && M.gcols_log2 < 8)
+        M.gcols_log2++;
+    if ((1u << M.gcols_log2) < max_groups)
+        return cudaErrorInvalidValue;   /* cannot happen: tile_b <= 4096 bytes */
+
+    const bool src32 = (reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
+                       && (L.src_image_stride & 3) == 0;
+
+    /* Source window bounds from the sampling step (see launch_mag); + 3 pixels either side for
+     * the 4-pixel load groups of 24bpp sources. */
+    size_t smem;
+    for (;;)
+    {
+        const uint64_t px = (uint64_t) max_groups * 4;
+        const uint64_t cols = (px * d.w_in + d.w_out - 1) / d.w_out + 3 + 8;
+        const uint64_t rows = ((uint64_t) M.tile_h * d.h_in + d.h_out - 1) / d.h_out + 3;
+        M.u_pitch = (uint32_t) (cols < (uint64_t) d.w_in + 8 ? cols : (uint64_t) d.w_in + 8);
+        M.u_pitch = (M.u_pitch + 1) & ~1u;                         /* keeps the filtered rows 16-byte aligned */
+        M.max_src_rows = (uint32_t) (rows < d.h_in ? rows : d.h_in);
+        smem = (size_t) M.max_src_rows * ((size_t) M.u_pitch * 8 + M.h_pitch);
+        if (smem <= 56 * 1024 || M.tile_h <= 4)
+            break;
+        M.tile_h /= 2;
+    }
+    const uint32_t items = d.bpp_in == 3 && src32 ? (M.u_pitch + 3) / 4 : M.u_pitch;
+    M.u_cw = 1;
+    M.u_cw_log2 = 0;
+    while (M.u_cw < 256 && M.u_cw < items)
+    {
+        M.u_cw *= 2;
+        M.u_cw_log2++;
+    }
+
+    static const uint32_t acc_byte[4] = { 1, 5, 3, 7 };
+    uint32_t sel = 0;
+    for (int j = 0; j < 4; j++)
+        sel |= acc_byte[(M.t.prmt_sel >> (4 * j)) & 3] << (4 * j);
+    M.acc_prmt_sel = sel;
+
+    dim3 grid ((M.nb_row + M.tile_b - 1) / M.tile_b, (L.n_rows + M.tile_h - 1) / M.tile_h, L.n_images);
+    const bool af = d.in_alpha_idx == 0;
+
+    if (d.bpp_in == 3)
+        return d.bpp_out == 3 ? launch_magb_fmt<3, 3, false, false> (M, src32, grid, smem, stream)
+                              : launch_magb_fmt<3, 4, false, false> (M, src32, grid, smem, stream);
+    if (d.in_unassoc)
+    {
+        if (d.bpp_out == 3)
+            return af ? launch_magb_fmt<4, 3, true, true> (M, src32, grid, smem, stream)
+                      : launch_magb_fmt<4, 3, true, false> (M, src32, grid, smem, stream);
+        return af ? launch_magb_fmt<4, 4, true, true> (M, src32, grid, smem, stream)
+                  : launch_magb_fmt<4, 4, true, false> (M, src32, grid, smem, stream);
+    }
+    return d.bpp_out == 3 ? launch_magb_fmt<4, 3, false, false> (M, src32, grid, smem, stream)
+                          : launch_magb_fmt<4, 4, false, false> (M, src32, grid, smem, stream);
+}
+
 static void
 box_params_init (BoxParams &P, const SmolLaunch &L)
 {
@@ -3605,6 +3952,8 @@ smol_cuda_launch (const SmolLaunch *launch, int kernel_id, void *stream_p, const
         return (int) launch_taps128 (L, stream);
     if (kernel_id == SMOL_KERNEL_TILE128 && tile128_eligible (L))
         return (int) launch_tile128 (L, stream);
+    if (kernel_id == SMOL_KERNEL_MAGB && magb_eligible (L))
+        return (int) launch_magb (L, stream);
     if (kernel_id == SMOL_KERNEL_MAG && mag_eligible (L))
         return (int) launch_mag (L, stream);
     if (kernel_id == SMOL_KERNEL_TAPS_DIRECT && taps_eligible (L))

@@ -31,6 +31,7 @@ enum
     SMOL_KERNEL_MAG = 5,         /* vertical magnification: two-phase shared-memory tile */
     SMOL_KERNEL_TAPS128 = 6,     /* bilinear with halvings, 128bpp intermediate (linear light, P16) */
     SMOL_KERNEL_TILE128 = 7,     /* bilinear without halvings / copy / one, 128bpp intermediate */
+    SMOL_KERNEL_MAGB = 8,        /* vertical magnification, byte-granular vertical stage (no alpha work on output) */
     SMOL_KERNEL_MAX
 };
 

@@ -466,6 +466,7 @@ static int g_device_count = -1;
 static int g_forced_kernel = 0;
 
 static uint64_t g_stat_launches, g_stat_h2d, g_stat_d2h, g_stat_uploads;
+static uint64_t g_stat_by_kernel[SMOL_CUDA_MAX_KERNEL_FAMILIES];
 
 static __thread void *tl_stream = NULL;
 static __thread int tl_device = -1;
@@ -885,11 +886,21 @@ static void
 launch_checked (const SmolLaunch *L, cudaStream_t stream)
 {
     int kid = smol_cuda_pick_kernel (L, g_forced_kernel);
-    int e = smol_cuda_launch (L, kid, stream, NULL);
+    const char *name = NULL;
+    int e = smol_cuda_launch (L, kid, stream, &name);
 
     if (e != 0)
         smol_fatal ("kernel launch failed", cudaGetErrorString ((cudaError_t) e));
     __atomic_add_fetch (&g_stat_launches, 1, __ATOMIC_RELAXED);
+    /* the family that actually ran (the launcher falls back to the general kernel) */
+    for (int k = 0; k < SMOL_KERNEL_MAX && k < SMOL_CUDA_MAX_KERNEL_FAMILIES; k++)
+    {
+        if (name == smol_cuda_kernel_name (k))
+        {
+            __atomic_add_fetch (&g_stat_by_kernel[k], 1, __ATOMIC_RELAXED);
+            break;
+        }
+    }
 }
 
 /* 2D copy that also tolerates pitches smaller than the row width (rows then overlap in the
@@ -1341,6 +1352,24 @@ smol_cuda_reset_stats (void)
     __atomic_store_n (&g_stat_h2d, 0, __ATOMIC_RELAXED);
     __atomic_store_n (&g_stat_d2h, 0, __ATOMIC_RELAXED);
     __atomic_store_n (&g_stat_uploads, 0, __ATOMIC_RELAXED);
+    for (int k = 0; k < SMOL_CUDA_MAX_KERNEL_FAMILIES; k++)
+        __atomic_store_n (&g_stat_by_kernel[k], 0, __ATOMIC_RELAXED);
+}
+
+SMOL_EXPORT int
+smol_cuda_get_kernel_launches (uint64_t *counts, const char **names, int max_families)
+{
+    int n = SMOL_KERNEL_MAX < SMOL_CUDA_MAX_KERNEL_FAMILIES ? SMOL_KERNEL_MAX : SMOL_CUDA_MAX_KERNEL_FAMILIES;
+
+    if (n > max_families)
+        n = max_families;
+    for (int k = 0; k < n; k++)
+    {
+        counts[k] = __atomic_load_n (&g_stat_by_kernel[k], __ATOMIC_RELAXED);
+        if (names)
+            names[k] = smol_cuda_kernel_name (k);
+    }
+    return n;
 }
 
 SMOL_EXPORT void

@@ -43,11 +43,11 @@ def test_golden_digests(sb):
     assert not bad, "CUDA output differs from the reference digests: %s" % bad[:10]
 
 
-@pytest.mark.parametrize("forced", [0, 1, 2, 4, 5, 6, 7],
-                         ids=["auto", "general", "taps", "box", "mag", "taps128", "tile128"])
+@pytest.mark.parametrize("forced", [0, 1, 2, 4, 5, 6, 7, 8],
+                         ids=["auto", "general", "taps", "box", "mag", "taps128", "tile128", "magb"])
 def test_random_matrix_vs_oracle(sb, restatement, forced):
     """forced = 0: the dispatcher's choice; 1: everything through the general kernel;
-    2 / 5: the direct taps / magnification kernel wherever eligible (general elsewhere)."""
+    2 / 5 / 8: the direct taps / magnification kernels wherever eligible (general elsewhere)."""
     sb.force_kernel(forced)
     try:
         for idx, job in enumerate(cases.job_matrix(4242, 600)):
@@ -106,6 +106,39 @@ def test_half_kernel_family(sb, restatement):
         torch.cuda.synchronize()
         assert np.array_equal(d_out.cpu().numpy()[4:4 + want.size], want), job
     assert n_fast > 100
+
+
+MAGB_GEOMETRIES = [(1, 1, 7, 9), (2, 3, 5, 8), (5, 4, 40, 30), (37, 21, 41, 37), (64, 48, 256, 192), (100, 7, 60, 29),
+                   (33, 30, 130, 31), (300, 40, 1500, 97), (1024, 40, 4096, 161), (90, 3, 349, 65)]
+
+
+def test_magb_kernel_family(sb, restatement):
+    """Vertical magnifications with 16-byte-aligned destination rows (the byte-granular kernel's
+    domain): every source type x every destination type without unassociated alpha, ragged row
+    ends, tiles that start mid-pixel (24bpp), row bands.  Automatic dispatch == oracle."""
+    rng = np.random.default_rng(11)
+    outs = [cases.RGBA8_P, cases.BGRA8_P, cases.ARGB8_P, cases.ABGR8_P, cases.RGB8, cases.BGR8]
+    sb.reset_stats()
+    for gi, (wi, hi, wo, ho) in enumerate(MAGB_GEOMETRIES):
+        for ti in cases.ALL_TYPES:
+            to = outs[int(rng.integers(len(outs)))]
+            si = wi * cases.bpp(ti) + int(rng.choice([0, 1, 4]))
+            so = (wo * cases.bpp(to) + 15) // 16 * 16 + int(rng.choice([0, 16]))
+            mode = cases.IMAGE_MODES[int(rng.integers(len(cases.IMAGE_MODES)))]
+            src = cases.make_image(ti, wi, hi, si, mode, seed=gi)
+            want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, 0)
+            got = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, 0)
+            assert np.array_equal(got, want), ((ti, wi, hi, si, to, wo, ho, so, mode), describe(got, want))
+            # a row band through the batch API
+            y0 = int(rng.integers(0, ho))
+            n = int(rng.integers(1, ho - y0 + 1))
+            dest = np.full(so * (n - 1) + wo * cases.bpp(to), 0xCD, np.uint8)
+            ctx = sb.ScaleCtx(src, ti, wi, hi, si, None, to, wo, ho, so, 0)
+            ctx.batch_full(dest, y0, n)
+            ctx.destroy()
+            assert np.array_equal(dest, want[y0 * so: y0 * so + dest.size]), (ti, to, wi, hi, wo, ho, y0, n)
+    by_kernel = sb.kernel_launches()
+    assert by_kernel["magb"] >= 2 * len(MAGB_GEOMETRIES) * len(cases.ALL_TYPES) * 3 // 4, by_kernel
 
 
 def test_unaligned_host_pointers(sb, restatement):
