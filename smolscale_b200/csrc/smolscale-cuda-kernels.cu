@@ -21,6 +21,7 @@
  * No tensor cores: every output is a 2-tap (bilinear) or variable-span (box) integer stencil
  * with a floor after each tap, i.e. bandwidth-bound byte work, not a dense contraction. */
 
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -596,6 +597,34 @@ __device__ __forceinline__ void pdl_launch_dependents ()
 __device__ __forceinline__ void pdl_wait ()
 {
     asm volatile ("griddepcontrol.wait;" ::: "memory");
+}
+
+/* shared-memory reads by 32-bit window address (LDS [R]: no generic-pointer arithmetic) */
+__device__ __forceinline__ uint32_t lds_u32 (uint32_t addr)
+{
+    uint32_t v;
+    asm ("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64 (uint32_t addr)
+{
+    uint2 v;
+    asm ("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+/* staging-buffer read: ordered against the cp.async / __syncwarp around it */
+__device__ __forceinline__ uint32_t lds_u32_ordered (uint32_t addr)
+{
+    uint32_t v;
+    asm volatile ("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ uint2 lds_u64_ordered (uint32_t addr)
+{
+    uint2 v;
+    asm volatile ("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
 }
 
 __device__ __forceinline__ uint32_t byte_avg_floor (uint32_t a, uint32_t b)
@@ -1646,6 +1675,7 @@ smol_magb_kernel (const MagbParams M)
 {
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
     __shared__ uint32_t sm_ty[64];
+    __shared__ uint4 sm_row[64];            /* per output row of the tile: { F, 256 - F, source row offset, end of its run } */
     const TapsParams &P = M.t;
     const uint32_t tid = threadIdx.x;
     constexpr bool GROUPS = BI == 3 && SRC32;       /* stage 1 works on groups of four 24bpp pixels */
@@ -1678,6 +1708,18 @@ smol_magb_kernel (const MagbParams M)
 
     const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
     uint8_t *dst_img = P.dst + (size_t) blockIdx.z * P.dst_image_stride;
+
+    /* stage 2's taps (this thread's column of pixel groups): fetched now, so the table latency
+     * hides behind stage 1.  Kept as byte offsets into a row of sm_u. */
+    const uint32_t gi = tid & ((1u << M.gcols_log2) - 1);
+    uint32_t po[4], qo[4], F2[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const uint32_t e = __ldg (&P.tab_x[min (4 * (g_lo + gi) + i, P.w_out - 1)]);
+        po[i] = SMOL_TAB_OFS (e);
+        F2[i] = SMOL_TAB_F (e);
+    }
 
     pdl_wait ();
 
@@ -1745,36 +1787,47 @@ smol_magb_kernel (const MagbParams M)
     }
     __syncthreads ();
 
-    /* stage 2: horizontal taps once per (source row, group of four output pixels); the thread's
-     * column of groups is fixed, so offsets and weights stay in registers across rows */
+    /* Rows of the tile grouped into runs that share a source row pair: per row its two weights
+     * (one 64-bit broadcast read per row in stage 3), its source row and where its run ends. */
+    if (tid < th)
     {
-        const uint32_t gi = tid & ((1u << M.gcols_log2) - 1), rl = tid >> M.gcols_log2, r_step = 256u >> M.gcols_log2;
+        const uint32_t e = sm_ty[tid], ofs = SMOL_TAB_OFS (e);
+        uint32_t j = tid + 1;
+        while (j < th && SMOL_TAB_OFS (sm_ty[j]) == ofs)
+            j++;
+        sm_row[tid] = make_uint4 (SMOL_TAB_F (e), 256u - SMOL_TAB_F (e), ofs, j);
+    }
+
+    /* stage 2: horizontal taps once per (source row, group of four output pixels); the thread's
+     * column of groups is fixed, so offsets and weights stay in registers across rows and the
+     * eight tap addresses just advance by a row */
+    {
+        const uint32_t rl = tid >> M.gcols_log2, r_step = 256u >> M.gcols_log2;
         if (gi < n_groups)
         {
-            uint32_t op[4], oq[4], F[4];
+            const uint32_t u_row = M.u_pitch * 8, u_base = (uint32_t) __cvta_generic_to_shared (sm_u) + rl * u_row;
 #pragma unroll
             for (int i = 0; i < 4; i++)
             {
-                const uint32_t e = __ldg (&P.tab_x[min (4 * (g_lo + gi) + i, P.w_out - 1)]);
-                op[i] = SMOL_TAB_OFS (e) - c_lo;
-                oq[i] = min (SMOL_TAB_OFS (e) + 1, P.w_in - 1) - c_lo;
-                F[i] = SMOL_TAB_F (e);
+                qo[i] = u_base + (min (po[i] + 1, P.w_in - 1) - c_lo) * 8;
+                po[i] = u_base + (po[i] - c_lo) * 8;
             }
             /* output byte b of the row lives at sm_h[row][16 + b - b0]: the tile's first byte is
              * 16-byte aligned, groups that start before it (24bpp) fit in the 16 bytes of slack */
-            const uint32_t hofs = 16 + (g_lo + gi) * 4 * BO - b0;
-            for (uint32_t r = rl; r < n_rows; r += r_step)
+            uint8_t *h = sm_h + rl * M.h_pitch + (16 + (g_lo + gi) * 4 * BO - b0);
+            const uint32_t u_inc = r_step * u_row, h_inc = r_step * M.h_pitch;
+            for (uint32_t r = rl; r < n_rows; r += r_step, h += h_inc)
             {
-                const uint2 *u = sm_u + r * M.u_pitch;
                 uint32_t D[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++)
                 {
-                    const uint2 p = u[op[i]], q = u[oq[i]];
-                    const uint32_t G = 256u - F[i];
-                    D[i] = __byte_perm (p.x * F[i] + q.x * G, p.y * F[i] + q.y * G, M.acc_prmt_sel);
+                    const uint2 p = lds_u64_ordered (po[i]), q = lds_u64_ordered (qo[i]);
+                    const uint32_t G = 256u - F2[i];
+                    D[i] = __byte_perm (p.x * F2[i] + q.x * G, p.y * F2[i] + q.y * G, M.acc_prmt_sel);
+                    po[i] += u_inc;
+                    qo[i] += u_inc;
                 }
-                uint8_t *h = sm_h + r * M.h_pitch + hofs;
                 if constexpr (BO == 4)
                     *reinterpret_cast<uint4 *> (h) = make_uint4 (D[0], D[1], D[2], D[3]);
                 else
@@ -1799,46 +1852,73 @@ smol_magb_kernel (const MagbParams M)
     const uint32_t ry_begin = grp * rows_per, ry_end = min (ry_begin + rows_per, th);
     uint8_t *dst = dst_img + (size_t) (yl0 + ry_begin) * P.dst_pitch + bb;
     const uint8_t *hcol = sm_h + 16 + 16 * c;
-    uint32_t ry = ry_begin;
-    uint32_t e = ry < ry_end ? sm_ty[ry] : 0;
-    while (ry < ry_end)
+    /* The two source rows of a run, expanded to 16-bit lanes.  On a magnification the next run's
+     * upper row is this run's lower row, so the two register sets swap roles from run to run
+     * (X on top, then Y on top) and only one row is fetched and expanded per run.
+     * FULL: the column's 16 bytes all lie inside the row (everything but a ragged last column). */
+    auto stage3 = [&] (auto full_tag)
     {
-        /* one run = consecutive output rows that read the same source row pair */
-        const uint32_t ofs = SMOL_TAB_OFS (e);
-        const uint32_t r0 = ofs - r_lo, r1 = min (ofs + 1, P.h_in - 1) - r_lo;
-        const uint4 tv = *reinterpret_cast<const uint4 *> (hcol + r0 * M.h_pitch);
-        const uint4 bv = *reinterpret_cast<const uint4 *> (hcol + r1 * M.h_pitch);
-        const uint32_t tw[4] = { tv.x, tv.y, tv.z, tv.w }, bw[4] = { bv.x, bv.y, bv.z, bv.w };
-        uint32_t T[8], B[8];
-#pragma unroll
-        for (int k = 0; k < 4; k++)
+        constexpr bool FULL = decltype (full_tag)::value;
+        uint32_t X[8], Y[8], hx = 0xffffffffu, hy = 0xffffffffu;
+        auto fetch_row = [&] (uint32_t (&R)[8], uint32_t r)
         {
-            T[2 * k] = __byte_perm (tw[k], 0, 0x4140);  T[2 * k + 1] = __byte_perm (tw[k], 0, 0x4342);
-            B[2 * k] = __byte_perm (bw[k], 0, 0x4140);  B[2 * k + 1] = __byte_perm (bw[k], 0, 0x4342);
-        }
-
-        do
-        {
-            const uint32_t F = SMOL_TAB_F (e), G = 256u - F;
-            uint32_t o[4];
+            const uint4 v = *reinterpret_cast<const uint4 *> (hcol + r * M.h_pitch);
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                o[j] = __byte_perm (T[2 * j] * F + B[2 * j] * G, T[2 * j + 1] * F + B[2 * j + 1] * G, 0x7531);
-            if (n_valid == 16)
-                *reinterpret_cast<uint4 *> (dst) = make_uint4 (o[0], o[1], o[2], o[3]);
-            else
+            for (int k = 0; k < 4; k++)
             {
-#pragma unroll
-                for (int k = 0; k < 16; k++)
-                    if ((uint32_t) k < n_valid)
-                        dst[k] = (uint8_t) (o[k >> 2] >> ((k & 3) * 8));
+                R[2 * k] = __byte_perm (w[k], 0, 0x4140);
+                R[2 * k + 1] = __byte_perm (w[k], 0, 0x4342);
             }
-            ry++;
-            dst += P.dst_pitch;
-            e = sm_ty[min (ry, th - 1)];
+        };
+        uint32_t ry = ry_begin;
+        uint8_t *out = dst;
+        auto run_rows = [&] (const uint32_t (&T)[8], const uint32_t (&B)[8], uint32_t run_end)
+        {
+            do
+            {
+                const uint2 fg = *reinterpret_cast<const uint2 *> (&sm_row[ry]);
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    o[j] = __byte_perm (T[2 * j] * fg.x + B[2 * j] * fg.y, T[2 * j + 1] * fg.x + B[2 * j + 1] * fg.y, 0x7531);
+                if constexpr (FULL)
+                    *reinterpret_cast<uint4 *> (out) = make_uint4 (o[0], o[1], o[2], o[3]);
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                        if ((uint32_t) k < n_valid)
+                            out[k] = (uint8_t) (o[k >> 2] >> ((k & 3) * 8));
+                }
+                out += P.dst_pitch;
+            }
+            while (++ry < run_end);
+        };
+        while (ry < ry_end)
+        {
+            {
+                const uint2 oe = *reinterpret_cast<const uint2 *> (&sm_row[ry].z);
+                const uint32_t r0 = oe.x - r_lo, r1 = min (oe.x + 1, P.h_in - 1) - r_lo;
+                if (hx != r0) { fetch_row (X, r0); hx = r0; }
+                if (hy != r1) { fetch_row (Y, r1); hy = r1; }
+                run_rows (X, Y, min (oe.y, ry_end));
+            }
+            if (ry >= ry_end)
+                break;
+            {
+                const uint2 oe = *reinterpret_cast<const uint2 *> (&sm_row[ry].z);
+                const uint32_t r0 = oe.x - r_lo, r1 = min (oe.x + 1, P.h_in - 1) - r_lo;
+                if (hy != r0) { fetch_row (Y, r0); hy = r0; }
+                if (hx != r1) { fetch_row (X, r1); hx = r1; }
+                run_rows (Y, X, min (oe.y, ry_end));
+            }
         }
-        while (ry < ry_end && SMOL_TAB_OFS (e) == ofs);
-    }
+    };
+    if (n_valid == 16)
+        stage3 (std::true_type {});
+    else
+        stage3 (std::false_type {});
 }
 
 /* ------------------------------------------------------------------------------------------ *
@@ -2065,26 +2145,6 @@ template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_scale (const BoxP
 #define SMOL_BOX3_FROM_WIN 0x10000u
 
 #define SMOL_BOX3_INV_WIN  0x20000u
-
-__device__ __forceinline__ uint32_t lds_u32 (uint32_t addr)
-{
-    uint32_t v;
-    asm ("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint2 lds_u64 (uint32_t addr)
-{
-    uint2 v;
-    asm ("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-    return v;
-}
-/* staging-buffer read: ordered against the cp.async / __syncwarp around it */
-__device__ __forceinline__ uint32_t lds_u32_ordered (uint32_t addr)
-{
-    uint32_t v;
-    asm volatile ("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
 
 /* PRMT with a selector known to have bit 3 of every nibble clear (__byte_perm masks its selector
  * with 0x7777 first, an extra instruction whenever the selector is a kernel parameter) */
