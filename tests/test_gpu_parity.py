@@ -108,6 +108,26 @@ def test_half_kernel_family(sb, restatement):
     assert n_fast > 100
 
 
+def test_box_window_shapes(sb, restatement):
+    """Box x box jobs whose per-warp source windows are long (ratios 12..16 keep one lane per column:
+    more than 96 sixteen-byte chunks per window), short, or ragged at the row end, on every
+    intermediate encoding (linear light or not, premultiplied / unassociated / 24bpp sources)."""
+    rng = np.random.default_rng(21)
+    geoms = [(200, 90, 15, 9), (255, 100, 16, 7), (1500, 120, 100, 11), (3000, 64, 230, 5), (1300, 99, 87, 9),
+             (1021, 50, 64, 5), (777, 95, 33, 7), (4000, 40, 15, 3), (130, 130, 9, 9)]
+    for gi, (wi, hi, wo, ho) in enumerate(geoms):
+        for ti in (cases.RGBA8_P, cases.ARGB8_P, cases.BGRA8_U, cases.ABGR8_U, cases.RGB8):
+            for srgb in (0, 1):
+                to = int(rng.integers(10))
+                si = (wi * cases.bpp(ti) + 15) // 16 * 16 if gi % 2 == 0 else wi * cases.bpp(ti) + int(rng.choice([0, 1, 4]))
+                so = wo * cases.bpp(to) + int(rng.choice([0, 3]))
+                mode = cases.IMAGE_MODES[int(rng.integers(len(cases.IMAGE_MODES)))]
+                src = cases.make_image(ti, wi, hi, si, mode, seed=gi)
+                want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
+                got = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, srgb)
+                assert np.array_equal(got, want), ((ti, wi, hi, si, to, wo, ho, so, srgb, mode), describe(got, want))
+
+
 MAGB_GEOMETRIES = [(1, 1, 7, 9), (2, 3, 5, 8), (5, 4, 40, 30), (37, 21, 41, 37), (64, 48, 256, 192), (100, 7, 60, 29),
                    (33, 30, 130, 31), (300, 40, 1500, 97), (1024, 40, 4096, 161), (90, 3, 349, 65)]
 

@@ -10,7 +10,8 @@ chk = oracle.restatement()
 seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 120
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rng = np.random.default_rng(seed0)
-pairs = cases.AXIS_PAIRS + cases.HALF_AXIS_PAIRS + [(640, 200), (641, 97), (333, 777), (1000, 3), (4000, 15), (12, 700), (255, 1), (256, 1), (257, 1), (2040, 8), (2041, 8), (96, 12), (100, 50), (77, 154)]
+pairs = cases.AXIS_PAIRS + cases.HALF_AXIS_PAIRS + [(640, 200), (641, 97), (333, 777), (1000, 3), (4000, 15), (12, 700), (255, 1), (256, 1), (257, 1), (2040, 8), (2041, 8), (96, 12), (100, 50), (77, 154),
+                                                       (200, 15), (255, 16), (1500, 100), (3000, 230), (1300, 87), (160, 640), (33, 1000)]
 t0 = time.time(); n = 0; bad = 0
 while time.time() - t0 < seconds:
     wi, wo = pairs[int(rng.integers(len(pairs)))]
