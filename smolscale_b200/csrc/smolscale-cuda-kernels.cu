@@ -599,6 +599,24 @@ __device__ __forceinline__ void pdl_wait ()
     asm volatile ("griddepcontrol.wait;" ::: "memory");
 }
 
+/* L2 prefetch of a line this thread is going to read.  Issued BEFORE the dependency wait: a
+ * prefetch has no functional effect (L2 is the coherence point, so data the previous grid still
+ * has to write lands in the same L2 line), but it lets a grid that became resident early pull
+ * its first source rows out of HBM while the previous grid drains -- the launch-to-launch bubble
+ * of per-frame calls is otherwise idle HBM time.  SMOL_PDL_PREFETCH=0 turns it off (a launcher
+ * parameter, for measurements). */
+__device__ __forceinline__ void prefetch_l2 (const void *p)
+{
+    asm volatile ("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
+/* Only CTAs of the grid's first wave can be resident before the previous grid has finished; for
+ * the rest a prefetch is pure overhead.  `first_wave` = how many CTAs (in launch order) that is. */
+__device__ __forceinline__ bool in_first_wave (uint32_t first_wave)
+{
+    return blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) < first_wave;
+}
+
 /* shared-memory reads by 32-bit window address (LDS [R]: no generic-pointer arithmetic) */
 __device__ __forceinline__ uint32_t lds_u32 (uint32_t addr)
 {
@@ -642,6 +660,7 @@ struct HalfParams
     uint32_t items_per_row;         /* ceil (w_out / 4) */
     uint32_t prmt_sel;              /* source byte order -> destination byte order */
     const uint32_t *inv_div_p8;     /* device LUT */
+    uint32_t prefetch;              /* CTAs (in launch order) that L2-prefetch their source on entry, ahead of the dependency wait */
 };
 
 /* Unpremultiply one packed pixel, kept in source byte order (reference generic:246-259 via
@@ -709,6 +728,26 @@ smol_half_kernel (const HalfParams P)
     __shared__ uint32_t sm_inv[256];
 
     pdl_launch_dependents ();
+    constexpr int SRC_PER_OUT = 2 << HH;            /* source pixels per output pixel per row */
+    constexpr int VEC_PER_OUT = SRC_PER_OUT / 4 > 0 ? SRC_PER_OUT / 4 : 1;
+
+    const uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t yl = blockIdx.y * blockDim.y + threadIdx.y;
+    if (P.prefetch && xi < P.items_per_row
+        && (SRC_PER_OUT * 16 >= 128 || (threadIdx.x & (128 / (SRC_PER_OUT * 16) - 1)) == 0))
+    {
+        /* L2 prefetch (see prefetch_l2), one lane per 128-byte line */
+        if (yl < P.n_rows && in_first_wave (P.prefetch))
+        {
+            const uint8_t *p = P.src + (size_t) blockIdx.z * P.src_image_stride
+                               + (size_t) (2 * ((P.first_row + yl) << VH)) * P.src_pitch + (size_t) xi * (SRC_PER_OUT * 16);
+#pragma unroll
+            for (int r = 0; r < (2 << VH); r++)
+#pragma unroll
+                for (int b = 0; b < SRC_PER_OUT * 16; b += 128)
+                    prefetch_l2 (p + (size_t) r * P.src_pitch + b);
+        }
+    }
     if constexpr (PACK != 0)
     {
         /* the LUT is library-owned constant data: safe to read before the dependency wait */
@@ -718,20 +757,13 @@ smol_half_kernel (const HalfParams P)
     }
     pdl_wait ();
 
-    constexpr int SRC_PER_OUT = 2 << HH;            /* source pixels per output pixel per row */
-    constexpr int VEC_PER_OUT = SRC_PER_OUT / 4 > 0 ? SRC_PER_OUT / 4 : 1;
-
-    const uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t yl = blockIdx.y * blockDim.y + threadIdx.y;
-    if (xi >= P.items_per_row || yl >= P.n_rows)
-        return;
-
+    const bool live = xi < P.items_per_row && yl < P.n_rows;
     const uint32_t x = xi * 4;
     const uint32_t y = P.first_row + yl;
     const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
     uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl * P.dst_pitch + (size_t) x * 4;
-    const uint32_t n_px = min (4u, P.w_out - x);
-    uint32_t out[4];
+    const uint32_t n_px = live ? min (4u, P.w_out - x) : 0u;
+    uint32_t out[4] = { 0, 0, 0, 0 };      /* filtered pixels, source byte order */
 
     if (n_px == 4)
     {
@@ -794,24 +826,15 @@ smol_half_kernel (const HalfParams P)
             for (int o = 0; o < 4; o++)
                 out[o] = ((acc_lo[o] >> VH) & 0x00ff00ffu) | (((acc_hi[o] >> VH) & 0x00ff00ffu) << 8);
         }
-
-#pragma unroll
-        for (int o = 0; o < 4; o++)
-        {
-            uint32_t v = out[o];
-            if constexpr (PACK == 1)
-                v = half_unpremul<false> (v, sm_inv);
-            else if constexpr (PACK == 2)
-                v = half_unpremul<true> (v, sm_inv);
-            out[o] = __byte_perm (v, 0, P.prmt_sel);
-        }
-        *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
     }
     else
     {
         /* ragged end of a row: one pixel at a time, same arithmetic */
-        for (uint32_t o = 0; o < n_px; o++)
+#pragma unroll
+        for (int o = 0; o < 3; o++)
         {
+            if ((uint32_t) o >= n_px)
+                continue;
             uint32_t acc_lo = 0, acc_hi = 0, res = 0;
 
             for (int kv = 0; kv < (1 << VH); kv++)
@@ -839,12 +862,31 @@ smol_half_kernel (const HalfParams P)
             }
             if (VH > 0)
                 res = ((acc_lo >> VH) & 0x00ff00ffu) | (((acc_hi >> VH) & 0x00ff00ffu) << 8);
-            if constexpr (PACK == 1)
-                res = half_unpremul<false> (res, sm_inv);
-            else if constexpr (PACK == 2)
-                res = half_unpremul<true> (res, sm_inv);
-            reinterpret_cast<uint32_t *> (dst)[o] = __byte_perm (res, 0, P.prmt_sel);
+            out[o] = res;
         }
+    }
+
+    if (n_px == 0)
+        return;
+
+#pragma unroll
+    for (int o = 0; o < 4; o++)
+    {
+        uint32_t v = out[o];
+        if constexpr (PACK == 1)
+            v = half_unpremul<false> (v, sm_inv);
+        else if constexpr (PACK == 2)
+            v = half_unpremul<true> (v, sm_inv);
+        out[o] = __byte_perm (v, 0, P.prmt_sel);
+    }
+    if (n_px == 4)
+        *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
+    else
+    {
+#pragma unroll
+        for (int o = 0; o < 3; o++)
+            if ((uint32_t) o < n_px)
+                reinterpret_cast<uint32_t *> (dst)[o] = out[o];
     }
 }
 
@@ -862,14 +904,6 @@ smol_half_wide_kernel (const HalfParams P)
     __shared__ uint32_t sm_inv[256];
 
     pdl_launch_dependents ();
-    if constexpr (PACK != 0)
-    {
-        for (uint32_t i = threadIdx.y * blockDim.x + threadIdx.x; i < 256; i += blockDim.x * blockDim.y)
-            sm_inv[i] = __ldg (&P.inv_div_p8[i]) << 3;
-        __syncthreads ();
-    }
-    pdl_wait ();
-
     constexpr int N_ROWS = 2 << VH;
     const uint32_t cx = blockIdx.x * blockDim.x + threadIdx.x;      /* 16-byte chunk within the row */
     const uint32_t yl = blockIdx.y * blockDim.y + threadIdx.y;
@@ -878,6 +912,23 @@ smol_half_wide_kernel (const HalfParams P)
     const uint32_t y = P.first_row + yl;
     const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride
                          + (size_t) (y << (VH + 1)) * P.src_pitch + (size_t) cx * 16;
+    if (P.prefetch && cx < n_chunks && (threadIdx.x & 7) == 0)
+    {
+        /* eight lanes share a 128-byte line: one prefetch per line and row (see prefetch_l2) */
+        if (yl < P.n_rows && in_first_wave (P.prefetch))
+        {
+#pragma unroll
+            for (int r = 0; r < N_ROWS; r++)
+                prefetch_l2 (src + (size_t) r * P.src_pitch);
+        }
+    }
+    if constexpr (PACK != 0)
+    {
+        for (uint32_t i = threadIdx.y * blockDim.x + threadIdx.x; i < 256; i += blockDim.x * blockDim.y)
+            sm_inv[i] = __ldg (&P.inv_div_p8[i]) << 3;
+        __syncthreads ();
+    }
+    pdl_wait ();
 
     uint4 rows[N_ROWS];
 #pragma unroll
@@ -1160,6 +1211,7 @@ struct Taps0Params
     TapsParams t;
     uint32_t acc_prmt_sel;          /* (acc_a, acc_b) high bytes -> destination byte order */
     uint32_t src_u32_ok;            /* 32bpp source rows are 4-byte aligned */
+    uint32_t prefetch;              /* CTAs (in launch order) that L2-prefetch their first source rows on entry (see prefetch_l2) */
 };
 
 template <int BI, bool IU, bool AF, bool U32OK>
@@ -1241,6 +1293,14 @@ smol_taps0_kernel (const Taps0Params T)
     uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl0 * P.dst_pitch + (size_t) x * BO;
     const bool fast_store = FASTIO && n_px == PX;
 
+    if (in_first_wave (T.prefetch))
+    {
+        /* the strip's first two source rows */
+        const uint32_t r = SMOL_TAB_OFS (__ldg (&P.tab_y[P.first_row + yl0]));
+        const uint8_t *p = src + (size_t) r * P.src_pitch + (size_t) op[0] * BI;
+        prefetch_l2 (p);
+        prefetch_l2 (p + (size_t) (r + 1 < P.h_in ? P.src_pitch : 0));
+    }
     pdl_wait ();
 
     auto hrow = [&] (uint32_t r, Px16 *out)
@@ -1370,6 +1430,14 @@ smol_tapsn_kernel (const Taps0Params T, uint32_t hh, uint32_t vh)
     const uint32_t *ty = P.tab_y + ((P.first_row + yl) << vh);
     const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
 
+    if (in_first_wave (T.prefetch) && (threadIdx.x & 3) == 0)
+    {
+        /* every source row of this output pixel, from its first column on (four lanes share the prefetch) */
+        const uint32_t c0 = SMOL_TAB_OFS (__ldg (&tx[0])) * BI;
+        const uint32_t ra = SMOL_TAB_OFS (__ldg (&ty[0])), rb = min (SMOL_TAB_OFS (__ldg (&ty[n_v - 1])) + 1, P.h_in - 1);
+        for (uint32_t r = ra; r <= rb; r++)
+            prefetch_l2 (src + (size_t) r * P.src_pitch + c0);
+    }
     pdl_wait ();
 
     auto hval = [&] (uint32_t r) -> Px16
@@ -1665,6 +1733,7 @@ struct MagbParams
     uint32_t h_pitch;               /* bytes per horizontally filtered row: tile_b + 32 */
     uint32_t max_src_rows;
     uint32_t acc_prmt_sel;          /* (acc_a, acc_b) high bytes -> destination byte order */
+    uint32_t prefetch;              /* CTAs (in launch order) that L2-prefetch their source window ahead of the dependency wait */
 };
 
 /* BI / BO bytes per pixel in / out; IU unassociated input (premultiplied on unpack); AF alpha is
@@ -1708,6 +1777,18 @@ smol_magb_kernel (const MagbParams M)
 
     const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
     uint8_t *dst_img = P.dst + (size_t) blockIdx.z * P.dst_image_stride;
+
+    if (in_first_wave (M.prefetch))
+    {
+        /* the tile's source window, one 128-byte line per thread (see prefetch_l2) */
+        const uint32_t w_bytes = n_cols * BI, lines = (w_bytes + 127) / 128 + 1;
+        if (tid < lines * n_rows)
+        {
+            const uint32_t r = tid / lines, l = tid - r * lines;
+            const uint8_t *p = src + (size_t) (r_lo + r) * P.src_pitch + (size_t) c_lo * BI;
+            prefetch_l2 (l + 1 < lines ? p + 128 * l : p + w_bytes - 1);
+        }
+    }
 
     /* stage 2's taps (this thread's column of pixel groups): fetched now, so the table latency
      * hides behind stage 1.  Kept as byte offsets into a row of sm_u. */
@@ -1966,6 +2047,7 @@ struct BoxParams
     uint32_t mul8_x, mul8_y;        /* span_mul << 8 (span_mul < 2^24 on every box axis) */
     uint32_t warps_lo;              /* warps whose staging buffers lie below the tables (window < 0x10000) */
     uint32_t unroll2;               /* walk the span two pixels per trip */
+    uint32_t prefetch;              /* L2-prefetch the first window rows ahead of the dependency wait */
 };
 
 __device__ __forceinline__ void cp_async_16 (uint32_t smem_addr, const void *gptr, uint32_t src_bytes)
@@ -2275,7 +2357,7 @@ smol_box_kernel (const BoxParams P)
             sm_from_plain[threadIdx.x] = P.luts->from_srgb[threadIdx.x];
     }
     __syncthreads ();
-    pdl_wait ();
+    bool waited = false;            /* the dependency wait happens at the warp's first item, after an L2 prefetch */
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t G = 1u << P.lanes_per_col_log2, g = lane & (G - 1);
@@ -2365,6 +2447,19 @@ smol_box_kernel (const BoxParams P)
         BoxPx<MODE> vacc;
 #pragma unroll
         for (int i = 0; i < (S128 ? 4 : 2); i++) vacc.v[i] = 0;
+
+        if (!waited)
+        {
+            if (P.prefetch)
+            {
+                /* the first rows of the warp's first window, one 128-byte line per lane (see prefetch_l2) */
+                const uint32_t lines = (n_chunks + 7) / 8 + 1, r = lane / lines, l = lane - r * lines;
+                if (T + r <= r_end)
+                    prefetch_l2 (src + (size_t) (T + r) * P.src_pitch + min (128u * l, 16u * n_chunks - 1u));
+            }
+            pdl_wait ();
+            waited = true;
+        }
 
         if constexpr (LUTM == 3)
         {
@@ -3090,6 +3185,37 @@ num_sms ()
     return g_num_sms;
 }
 
+/* See prefetch_l2 / in_first_wave: the number of CTAs of a launch that can be resident at once
+ * (0 when SMOL_PDL_PREFETCH=0). */
+static int num_sms ();
+
+static uint32_t
+pdl_first_wave (uint32_t threads_per_cta, size_t smem_per_cta)
+{
+    static int on = -1;
+    if (on < 0)
+    {
+        const char *e = getenv ("SMOL_PDL_PREFETCH");
+        on = e ? atoi (e) : 1;
+    }
+    if (on == 0)
+        return 0;
+    if (on == 2)
+        return 0xffffffffu;             /* measurement: every CTA prefetches */
+    uint32_t per_sm = 2048 / (threads_per_cta ? threads_per_cta : 1);
+    if (per_sm > 32)
+        per_sm = 32;
+    if (smem_per_cta > 0)
+    {
+        const uint32_t by_smem = (uint32_t) ((227 * 1024) / (smem_per_cta + 1024));
+        if (by_smem < per_sm)
+            per_sm = by_smem;
+    }
+    if (per_sm < 1)
+        per_sm = 1;
+    return (uint32_t) num_sms () * per_sm;
+}
+
 /* Launch with programmatic stream serialization allowed (see pdl_wait). */
 template <typename Kernel, typename Params>
 static cudaError_t
@@ -3201,6 +3327,13 @@ launch_half (const SmolLaunch &L, cudaStream_t stream)
     dim3 block (bx, by);
     dim3 grid ((n_x + bx - 1) / bx, (L.n_rows + by - 1) / by, L.n_images);
     const int pack = d.out_unassoc ? (d.in_alpha_idx == 0 ? 2 : 1) : 0;
+    /* With an inverse table to stage (its load and barrier sit between kernel entry and the first
+     * source load) every CTA prefetches: the source then streams in during that phase.  Without
+     * one the loads follow at once and only the first wave has anything to gain (measured: 4K ->
+     * 1080p unassociated 8.2 -> 7.1 us per frame; 64 thumbnails per launch 156 -> 152 us). */
+    P.prefetch = pdl_first_wave (bx * by, pack ? 1024 : 0);
+    if (pack && P.prefetch)
+        P.prefetch = 0xffffffffu;
 
     switch (d.h_halvings * 3 + d.v_halvings)
     {
@@ -3314,6 +3447,9 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
         T.acc_prmt_sel = sel;
         T.src_u32_ok = d.bpp_in == 3 || ((reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
                                          && (L.src_image_stride & 3) == 0);
+        T.prefetch = pdl_first_wave (256, d.out_unassoc ? 1024 : 0);
+        if (d.out_unassoc && T.prefetch)
+            T.prefetch = 0xffffffffu;   /* an inverse table is staged first: see launch_half */
         const bool af = d.in_alpha_idx == 0;
         const bool fastio = T.src_u32_ok && (reinterpret_cast<uintptr_t> (L.dst) & 3) == 0
                             && (L.dst_pitch & 3) == 0 && (L.dst_image_stride & 3) == 0;
@@ -3371,6 +3507,9 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
         T.acc_prmt_sel = 0;
         T.src_u32_ok = d.bpp_in == 3 || ((reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
                                          && (L.src_image_stride & 3) == 0);
+        T.prefetch = pdl_first_wave (256, d.out_unassoc ? 1024 : 0);
+        if (d.out_unassoc && T.prefetch)
+            T.prefetch = 0xffffffffu;   /* an inverse table is staged first: see launch_half */
         const bool dst_ok = d.bpp_out == 3 || ((reinterpret_cast<uintptr_t> (L.dst) & 3) == 0 && (L.dst_pitch & 3) == 0
                                                && (L.dst_image_stride & 3) == 0);
         if (T.src_u32_ok && dst_ok)
@@ -3624,6 +3763,7 @@ launch_magb (const SmolLaunch &L, cudaStream_t stream)
 
     dim3 grid ((M.nb_row + M.tile_b - 1) / M.tile_b, (L.n_rows + M.tile_h - 1) / M.tile_h, L.n_images);
     const bool af = d.in_alpha_idx == 0;
+    M.prefetch = pdl_first_wave (256, smem + 1280);
 
     if (d.bpp_in == 3)
         return d.bpp_out == 3 ? launch_magb_fmt<3, 3, false, false> (M, src32, grid, smem, stream)
@@ -3668,6 +3808,7 @@ box_params_init (BoxParams &P, const SmolLaunch &L)
     P.sel_f2 = 0x7604u | ((d.in_col0 + 2u) << 4);
     P.warps_lo = 0;
     P.unroll2 = 1;
+    P.prefetch = 0;
     P.mul8_x = d.span_mul_x << 8;
     P.mul8_y = d.span_mul_y << 8;
     {
@@ -3732,6 +3873,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     }
 
     P.unroll2 = tune_unroll != 0;
+    P.prefetch = pdl_first_wave (1024, 0) != 0;
     const bool bi3 = d.bpp_in == 3;     /* 24bpp sources are never unassociated: modes P8_P / P8L_P only */
 #define BOX_KERNEL_FOR(M) (lutm == 3 ? (const void *) smol_box_kernel<M, 3, 4> : lutm == 1 ? (const void *) smol_box_kernel<M, 1, 4> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 4> : (const void *) smol_box_kernel<M, 0, 4>)
 #define BOX_KERNEL_FOR3(M) (lutm == 3 ? (const void *) smol_box_kernel<M, 3, 3> : lutm == 1 ? (const void *) smol_box_kernel<M, 1, 3> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 3> : (const void *) smol_box_kernel<M, 0, 3>)
