@@ -1736,13 +1736,16 @@ struct MagbParams
     uint32_t prefetch;              /* CTAs (in launch order) that L2-prefetch their source window ahead of the dependency wait */
 };
 
-/* BI / BO bytes per pixel in / out; IU unassociated input (premultiplied on unpack); AF alpha is
- * byte 0 of the source pixel; SRC32 source rows are 4-byte aligned. */
-template <int BI, int BO, bool IU, bool AF, bool SRC32>
+/* BI / BO bytes per pixel in / out; IU unassociated input (premultiplied on unpack); OU unassociated
+ * output (32bpp only: a 16-byte column is then four whole pixels, unpremultiplied just before the
+ * store); AF alpha is byte 0 of the source pixel; SRC32 source rows are 4-byte aligned. */
+template <int BI, int BO, bool IU, bool OU, bool AF, bool SRC32>
 __global__ void __launch_bounds__ (256)
 smol_magb_kernel (const MagbParams M)
 {
+    static_assert (!OU || BO == 4, "unassociated output is 32bpp");
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
+    __shared__ uint32_t sm_inv[OU ? 256 : 1];
     __shared__ uint32_t sm_ty[64];
     __shared__ uint4 sm_row[64];            /* per output row of the tile: { F, 256 - F, source row offset, end of its run } */
     const TapsParams &P = M.t;
@@ -1750,6 +1753,8 @@ smol_magb_kernel (const MagbParams M)
     constexpr bool GROUPS = BI == 3 && SRC32;       /* stage 1 works on groups of four 24bpp pixels */
 
     pdl_launch_dependents ();
+    if constexpr (OU)
+        sm_inv[tid] = __ldg (&P.inv_div_p8[tid]) << 3;      /* visible after the stage barriers */
 
     const uint32_t b0 = blockIdx.x * M.tile_b;
     const uint32_t b1 = min (b0 + M.tile_b, M.nb_row);             /* exclusive */
@@ -1905,7 +1910,8 @@ smol_magb_kernel (const MagbParams M)
                 {
                     const uint2 p = lds_u64_ordered (po[i]), q = lds_u64_ordered (qo[i]);
                     const uint32_t G = 256u - F2[i];
-                    D[i] = __byte_perm (p.x * F2[i] + q.x * G, p.y * F2[i] + q.y * G, M.acc_prmt_sel);
+                    /* destination byte order, or source order when the pixels still have to be unpremultiplied */
+                    D[i] = __byte_perm (p.x * F2[i] + q.x * G, p.y * F2[i] + q.y * G, OU ? 0x7351u : M.acc_prmt_sel);
                     po[i] += u_inc;
                     qo[i] += u_inc;
                 }
@@ -1963,6 +1969,12 @@ smol_magb_kernel (const MagbParams M)
 #pragma unroll
                 for (int j = 0; j < 4; j++)
                     o[j] = __byte_perm (T[2 * j] * fg.x + B[2 * j] * fg.y, T[2 * j + 1] * fg.x + B[2 * j + 1] * fg.y, 0x7531);
+                if constexpr (OU)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        o[j] = __byte_perm (half_unpremul<AF> (o[j], sm_inv), 0, P.prmt_sel);
+                }
                 if constexpr (FULL)
                     *reinterpret_cast<uint4 *> (out) = make_uint4 (o[0], o[1], o[2], o[3]);
                 else
@@ -3104,9 +3116,16 @@ mag_eligible (const SmolLaunch &L)
 static bool
 magb_eligible (const SmolLaunch &L)
 {
-    /* byte-granular vertical stage: no per-pixel work after the horizontal pass, 16-byte stores */
-    return mag_eligible (L) && !L.d.out_unassoc
-           && aligned16 (L.dst) && (L.dst_pitch & 15) == 0 && (L.dst_image_stride & 15) == 0;
+    /* byte-granular vertical stage with 16-byte stores; SMOL_MAGB_ALL=1 (measurements) sends every
+     * bilinear job without halvings here, not just vertical magnifications */
+    static int all = -1;
+    if (all < 0)
+    {
+        const char *e = getenv ("SMOL_MAGB_ALL");
+        all = e ? atoi (e) : 0;
+    }
+    const bool shape_ok = all ? (taps_eligible (L) && L.d.h_halvings == 0 && L.d.v_halvings == 0) : mag_eligible (L);
+    return shape_ok && aligned16 (L.dst) && (L.dst_pitch & 15) == 0 && (L.dst_image_stride & 15) == 0;
 }
 
 static bool
@@ -3161,10 +3180,14 @@ smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
         return SMOL_KERNEL_TAPS128;
     if (tile128_eligible (*launch) && (forced == SMOL_KERNEL_AUTO || forced == SMOL_KERNEL_TILE128))
         return SMOL_KERNEL_TILE128;
-    if (mag_ok && magb_eligible (*launch))
+    /* Measured on B200 (4K outputs, graph replay, us per frame, taps_direct vs magb): 24bpp -> 24bpp
+     * 2x 17.2 / 15.2, 4x 15.4 / 12.0, 8x 10.3 / 7.2; 32bpp -> 32bpp 2x 14.1 / 23.3, 4x 10.9 / 12.3,
+     * 8x 9.8 / 9.6; 32 -> 24bpp 2x 13.6 / 18.6; 24 -> 24bpp 1.5x 19.4 / 25.4.  The byte-granular tile
+     * pays off where the register kernel has to assemble 24bpp stores; the older per-pixel tile
+     * ("mag") loses to one or the other everywhere and is kept for forced runs only. */
+    if (magb_eligible (*launch) && launch->d.bpp_in == 3 && launch->d.bpp_out == 3
+        && launch->d.h_out >= 2 * launch->d.h_in)
         return SMOL_KERNEL_MAGB;
-    if (mag_ok)
-        return SMOL_KERNEL_MAG;
     if (taps_ok)
         return SMOL_KERNEL_TAPS_DIRECT;
     return SMOL_KERNEL_GENERAL;
@@ -3680,19 +3703,19 @@ launch_mag (const SmolLaunch &L, cudaStream_t stream)
     return launch_mag_fmt<4, 4, false, false, false> (M, grid, smem, stream);
 }
 
-template <int BI, int BO, bool IU, bool AF>
+template <int BI, int BO, bool IU, bool OU, bool AF>
 static cudaError_t
 launch_magb_fmt (const MagbParams &M, bool src32, dim3 grid, size_t smem, cudaStream_t stream)
 {
     if (src32)
     {
         if (smem > 40 * 1024)
-            cudaFuncSetAttribute (smol_magb_kernel<BI, BO, IU, AF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        return launch_pdl (smol_magb_kernel<BI, BO, IU, AF, true>, M, grid, dim3 (256), smem, stream);
+            cudaFuncSetAttribute (smol_magb_kernel<BI, BO, IU, OU, AF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        return launch_pdl (smol_magb_kernel<BI, BO, IU, OU, AF, true>, M, grid, dim3 (256), smem, stream);
     }
     if (smem > 40 * 1024)
-        cudaFuncSetAttribute (smol_magb_kernel<BI, BO, IU, AF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    return launch_pdl (smol_magb_kernel<BI, BO, IU, AF, false>, M, grid, dim3 (256), smem, stream);
+        cudaFuncSetAttribute (smol_magb_kernel<BI, BO, IU, OU, AF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return launch_pdl (smol_magb_kernel<BI, BO, IU, OU, AF, false>, M, grid, dim3 (256), smem, stream);
 }
 
 static cudaError_t
@@ -3710,42 +3733,84 @@ launch_magb (const SmolLaunch &L, cudaStream_t stream)
         tune_th = b ? atoi (b) : 0;
     }
     M.nb_row = d.w_out * d.bpp_out;
-    /* tile width: 16 << k bytes, the smallest that covers the row, at most 1024 (64 threads wide) */
-    const uint32_t tb_cap = tune_tb >= 16 ? (uint32_t) tune_tb : 1024;
-    M.chunks_log2 = 0;
-    while ((16u << M.chunks_log2) < tb_cap && (16u << M.chunks_log2) < M.nb_row && M.chunks_log2 < 8)
-        M.chunks_log2++;
-    M.tile_b = 16u << M.chunks_log2;
-    M.h_pitch = M.tile_b + 32;
-    M.tile_h = tune_th > 0 ? (uint32_t) (tune_th > 64 ? 64 : tune_th) : 32;
-
-    /* pixel groups per tile: tile_b / (4 bpp) rounded up, + 1 for a group straddling the tile's start */
-    const uint32_t max_groups = (M.tile_b + 4 * d.bpp_out - 1) / (4 * d.bpp_out) + 1;
-    M.gcols_log2 = 0;
-    while ((1u << M.gcols_log2) < max_groups && M.gcols_log2 < 8)
-        M.gcols_log2++;
-    if ((1u << M.gcols_log2) < max_groups)
-        return cudaErrorInvalidValue;   /* cannot happen: tile_b <= 4096 bytes */
-
     const bool src32 = (reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
                        && (L.src_image_stride & 3) == 0;
 
-    /* Source window bounds from the sampling step (see launch_mag); + 3 pixels either side for
-     * the 4-pixel load groups of 24bpp sources. */
-    size_t smem;
-    for (;;)
+    /* Shape of a tile (tile_b = 16 << k bytes wide, tile_h rows): everything that depends on it. */
+    auto shape = [&] (uint32_t chunks_log2, uint32_t tile_h, size_t &smem_out) -> bool
     {
+        M.chunks_log2 = chunks_log2;
+        M.tile_b = 16u << chunks_log2;
+        M.h_pitch = M.tile_b + 32;
+        M.tile_h = tile_h;
+        /* pixel groups per tile: tile_b / (4 bpp) rounded up, + 1 for a group straddling the tile's start */
+        const uint32_t max_groups = (M.tile_b + 4 * d.bpp_out - 1) / (4 * d.bpp_out) + 1;
+        M.gcols_log2 = 0;
+        while ((1u << M.gcols_log2) < max_groups && M.gcols_log2 < 8)
+            M.gcols_log2++;
+        if ((1u << M.gcols_log2) < max_groups)
+            return false;
+        /* Source window bounds from the sampling step (see launch_mag); + 3 pixels either side for
+         * the 4-pixel load groups of 24bpp sources. */
         const uint64_t px = (uint64_t) max_groups * 4;
         const uint64_t cols = (px * d.w_in + d.w_out - 1) / d.w_out + 3 + 8;
-        const uint64_t rows = ((uint64_t) M.tile_h * d.h_in + d.h_out - 1) / d.h_out + 3;
+        const uint64_t rows = ((uint64_t) tile_h * d.h_in + d.h_out - 1) / d.h_out + 3;
         M.u_pitch = (uint32_t) (cols < (uint64_t) d.w_in + 8 ? cols : (uint64_t) d.w_in + 8);
         M.u_pitch = (M.u_pitch + 1) & ~1u;                         /* keeps the filtered rows 16-byte aligned */
         M.max_src_rows = (uint32_t) (rows < d.h_in ? rows : d.h_in);
-        smem = (size_t) M.max_src_rows * ((size_t) M.u_pitch * 8 + M.h_pitch);
-        if (smem <= 56 * 1024 || M.tile_h <= 4)
-            break;
-        M.tile_h /= 2;
+        smem_out = (size_t) M.max_src_rows * ((size_t) M.u_pitch * 8 + M.h_pitch);
+        return true;
+    };
+
+    /* Pick the shape with the lowest estimated time per output row:
+     *   work  = 1 (vertical stage) + 1.6 x source rows per output row (horizontal stage runs once
+     *           per source row of the tile, halo included) + a fixed per-tile share,
+     *   waves = CTAs / (SMs x CTAs resident per SM): the last, partly filled wave costs a full one
+     *           (a 1.4-wave grid runs as long as a 2-wave one), and low residency hides less latency. */
+    size_t smem = 0;
+    uint32_t best_c = 0, best_h = 0;
+    {
+        double best = 1e30;
+        uint32_t c_max = 0;
+        while ((16u << c_max) < M.nb_row && c_max < 7)
+            c_max++;
+        for (uint32_t c = c_max >= 5 ? 5 : c_max; c <= c_max; c++)
+        {
+            for (uint32_t h = 8; h <= 64; h *= 2)
+            {
+                size_t sm;
+                if ((tune_tb >= 16 && (16u << c) != (uint32_t) tune_tb && c != c_max) || (tune_th > 0 && h != (uint32_t) tune_th))
+                    continue;
+                if (!shape (c, h, sm) || sm > 100 * 1024)
+                    continue;
+                uint32_t per_sm = (uint32_t) ((220 * 1024) / (sm + 3 * 1024));
+                per_sm = per_sm > 8 ? 8 : per_sm;
+                if (per_sm < 2)
+                    continue;
+                const double ctas = (double) ((M.nb_row + M.tile_b - 1) / M.tile_b) * ((L.n_rows + h - 1) / h) * L.n_images;
+                const double waves = ctas / ((double) num_sms () * per_sm);
+                const double eff = waves / (double) (uint64_t) (waves + 0.999999);
+                const double work = 1.0 + 1.6 * M.max_src_rows / h + 8.0 / h * (1024.0 / M.tile_b);
+                const double t = work / eff * (per_sm < 4 ? 1.3 : per_sm < 6 ? 1.1 : 1.0);
+                if (t < best)
+                {
+                    best = t;
+                    best_c = c;
+                    best_h = h;
+                }
+            }
+        }
+        if (best_h == 0)
+        {
+            /* nothing fits comfortably (very wide source windows): shrink the tile until it does */
+            best_c = c_max < 6 ? c_max : 6;
+            best_h = 32;
+            while (best_h > 4 && shape (best_c, best_h, smem) && smem > 56 * 1024)
+                best_h /= 2;
+        }
     }
+    if (!shape (best_c, best_h, smem))
+        return cudaErrorInvalidValue;   /* cannot happen: tile_b <= 2048 bytes */
     const uint32_t items = d.bpp_in == 3 && src32 ? (M.u_pitch + 3) / 4 : M.u_pitch;
     M.u_cw = 1;
     M.u_cw_log2 = 0;
@@ -3763,21 +3828,28 @@ launch_magb (const SmolLaunch &L, cudaStream_t stream)
 
     dim3 grid ((M.nb_row + M.tile_b - 1) / M.tile_b, (L.n_rows + M.tile_h - 1) / M.tile_h, L.n_images);
     const bool af = d.in_alpha_idx == 0;
-    M.prefetch = pdl_first_wave (256, smem + 1280);
+    M.prefetch = pdl_first_wave (256, smem + 2304);
 
     if (d.bpp_in == 3)
-        return d.bpp_out == 3 ? launch_magb_fmt<3, 3, false, false> (M, src32, grid, smem, stream)
-                              : launch_magb_fmt<3, 4, false, false> (M, src32, grid, smem, stream);
+    {
+        if (d.bpp_out == 3)     return launch_magb_fmt<3, 3, false, false, false> (M, src32, grid, smem, stream);
+        if (d.out_unassoc)      return launch_magb_fmt<3, 4, false, true, false> (M, src32, grid, smem, stream);
+        return launch_magb_fmt<3, 4, false, false, false> (M, src32, grid, smem, stream);
+    }
     if (d.in_unassoc)
     {
         if (d.bpp_out == 3)
-            return af ? launch_magb_fmt<4, 3, true, true> (M, src32, grid, smem, stream)
-                      : launch_magb_fmt<4, 3, true, false> (M, src32, grid, smem, stream);
-        return af ? launch_magb_fmt<4, 4, true, true> (M, src32, grid, smem, stream)
-                  : launch_magb_fmt<4, 4, true, false> (M, src32, grid, smem, stream);
+            return af ? launch_magb_fmt<4, 3, true, false, true> (M, src32, grid, smem, stream)
+                      : launch_magb_fmt<4, 3, true, false, false> (M, src32, grid, smem, stream);
+        return af ? launch_magb_fmt<4, 4, true, false, true> (M, src32, grid, smem, stream)
+                  : launch_magb_fmt<4, 4, true, false, false> (M, src32, grid, smem, stream);
     }
-    return d.bpp_out == 3 ? launch_magb_fmt<4, 3, false, false> (M, src32, grid, smem, stream)
-                          : launch_magb_fmt<4, 4, false, false> (M, src32, grid, smem, stream);
+    if (d.bpp_out == 3)
+        return launch_magb_fmt<4, 3, false, false, false> (M, src32, grid, smem, stream);
+    if (d.out_unassoc)
+        return af ? launch_magb_fmt<4, 4, false, true, true> (M, src32, grid, smem, stream)
+                  : launch_magb_fmt<4, 4, false, true, false> (M, src32, grid, smem, stream);
+    return launch_magb_fmt<4, 4, false, false, false> (M, src32, grid, smem, stream);
 }
 
 static void

@@ -134,31 +134,45 @@ MAGB_GEOMETRIES = [(1, 1, 7, 9), (2, 3, 5, 8), (5, 4, 40, 30), (37, 21, 41, 37),
 
 def test_magb_kernel_family(sb, restatement):
     """Vertical magnifications with 16-byte-aligned destination rows (the byte-granular kernel's
-    domain): every source type x every destination type without unassociated alpha, ragged row
-    ends, tiles that start mid-pixel (24bpp), row bands.  Automatic dispatch == oracle."""
-    rng = np.random.default_rng(11)
-    outs = [cases.RGBA8_P, cases.BGRA8_P, cases.ARGB8_P, cases.ABGR8_P, cases.RGB8, cases.BGR8]
+    domain): every source type x random destination types, ragged row ends, tiles that start
+    mid-pixel (24bpp), row bands.  Run twice: with the kernel forced wherever it can run (the
+    dispatcher itself only picks it for 24bpp -> 24bpp at 2x and more) and with automatic dispatch.
+    (Unassociated -> unassociated pairs use the 128bpp intermediate and so another kernel.)"""
+    for forced in (8, 0):
+        rng = np.random.default_rng(11)
+        outs = cases.ALL_TYPES
+        sb.reset_stats()
+        sb.force_kernel(forced)
+        try:
+            for gi, (wi, hi, wo, ho) in enumerate(MAGB_GEOMETRIES):
+                for ti in cases.ALL_TYPES:
+                    to = outs[int(rng.integers(len(outs)))]
+                    si = wi * cases.bpp(ti) + int(rng.choice([0, 1, 4]))
+                    so = (wo * cases.bpp(to) + 15) // 16 * 16 + int(rng.choice([0, 16]))
+                    mode = cases.IMAGE_MODES[int(rng.integers(len(cases.IMAGE_MODES)))]
+                    src = cases.make_image(ti, wi, hi, si, mode, seed=gi)
+                    want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, 0)
+                    got = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, 0)
+                    assert np.array_equal(got, want), ((ti, wi, hi, si, to, wo, ho, so, mode), forced, describe(got, want))
+                    # a row band through the batch API
+                    y0 = int(rng.integers(0, ho))
+                    n = int(rng.integers(1, ho - y0 + 1))
+                    dest = np.full(so * (n - 1) + wo * cases.bpp(to), 0xCD, np.uint8)
+                    ctx = sb.ScaleCtx(src, ti, wi, hi, si, None, to, wo, ho, so, 0)
+                    ctx.batch_full(dest, y0, n)
+                    ctx.destroy()
+                    assert np.array_equal(dest, want[y0 * so: y0 * so + dest.size]), (ti, to, wi, hi, wo, ho, y0, n, forced)
+        finally:
+            sb.force_kernel(0)
+        by_kernel = sb.kernel_launches()
+        if forced:
+            assert by_kernel["magb"] >= 2 * len(MAGB_GEOMETRIES) * len(cases.ALL_TYPES) * 6 // 10, by_kernel
+    # the dispatcher's own choice: 24bpp -> 24bpp at 2x and more
+    src = cases.make_image(cases.RGB8, 64, 48, 192, "random", seed=1)
     sb.reset_stats()
-    for gi, (wi, hi, wo, ho) in enumerate(MAGB_GEOMETRIES):
-        for ti in cases.ALL_TYPES:
-            to = outs[int(rng.integers(len(outs)))]
-            si = wi * cases.bpp(ti) + int(rng.choice([0, 1, 4]))
-            so = (wo * cases.bpp(to) + 15) // 16 * 16 + int(rng.choice([0, 16]))
-            mode = cases.IMAGE_MODES[int(rng.integers(len(cases.IMAGE_MODES)))]
-            src = cases.make_image(ti, wi, hi, si, mode, seed=gi)
-            want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, 0)
-            got = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, 0)
-            assert np.array_equal(got, want), ((ti, wi, hi, si, to, wo, ho, so, mode), describe(got, want))
-            # a row band through the batch API
-            y0 = int(rng.integers(0, ho))
-            n = int(rng.integers(1, ho - y0 + 1))
-            dest = np.full(so * (n - 1) + wo * cases.bpp(to), 0xCD, np.uint8)
-            ctx = sb.ScaleCtx(src, ti, wi, hi, si, None, to, wo, ho, so, 0)
-            ctx.batch_full(dest, y0, n)
-            ctx.destroy()
-            assert np.array_equal(dest, want[y0 * so: y0 * so + dest.size]), (ti, to, wi, hi, wo, ho, y0, n)
-    by_kernel = sb.kernel_launches()
-    assert by_kernel["magb"] >= 2 * len(MAGB_GEOMETRIES) * len(cases.ALL_TYPES) * 3 // 4, by_kernel
+    got = cuda_scale(sb, src, cases.RGB8, 64, 48, 192, cases.BGR8, 256, 192, 768, 0)
+    assert np.array_equal(got, restatement.scale_simple(src, cases.RGB8, 64, 48, 192, cases.BGR8, 256, 192, 768, 0))
+    assert sb.kernel_launches()["magb"] == 1
 
 
 def test_unaligned_host_pointers(sb, restatement):
