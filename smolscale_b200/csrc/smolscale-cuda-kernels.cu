@@ -610,6 +610,11 @@ __device__ __forceinline__ void prefetch_l2 (const void *p)
     asm volatile ("prefetch.global.L2 [%0];" :: "l"(p));
 }
 
+__device__ __forceinline__ void prefetch_l1 (const void *p)
+{
+    asm volatile ("prefetch.global.L1 [%0];" :: "l"(p));
+}
+
 /* Only CTAs of the grid's first wave can be resident before the previous grid has finished; for
  * the rest a prefetch is pure overhead.  `first_wave` = how many CTAs (in launch order) that is. */
 __device__ __forceinline__ bool in_first_wave (uint32_t first_wave)
@@ -1212,6 +1217,7 @@ struct Taps0Params
     uint32_t acc_prmt_sel;          /* (acc_a, acc_b) high bytes -> destination byte order */
     uint32_t src_u32_ok;            /* 32bpp source rows are 4-byte aligned */
     uint32_t prefetch;              /* CTAs (in launch order) that L2-prefetch their first source rows on entry (see prefetch_l2) */
+    uint32_t row_ahead;             /* taps0: L1-prefetch the source row this many rows below the one being fetched (0: off) */
 };
 
 template <int BI, bool IU, bool AF, bool U32OK>
@@ -1306,6 +1312,8 @@ smol_taps0_kernel (const Taps0Params T)
     auto hrow = [&] (uint32_t r, Px16 *out)
     {
         const uint8_t *row = src + (size_t) min (r, P.h_in - 1) * P.src_pitch;
+        if (T.row_ahead && r + T.row_ahead < P.h_in)
+            prefetch_l1 (row + (size_t) T.row_ahead * P.src_pitch + (size_t) op[0] * BI);   /* the strip walks down: hide the next rows' latency */
 #pragma unroll
         for (int o = 0; o < PX; o++)
         {
@@ -1405,12 +1413,13 @@ smol_taps0_kernel (const Taps0Params T)
  * next to no reuse between neighbouring outputs to exploit.  The thread sums 2^vh vertical
  * samples, each a tap between two horizontally filtered source rows (two-entry register cache:
  * consecutive samples usually share a row), each of those the sum of 2^hh horizontal taps. */
-template <int BI, int BO, bool IU, bool OU, bool AF>
+template <int BI, int BO, bool IU, bool OU, bool AF, int HH>
 __global__ void __launch_bounds__ (256)
-smol_tapsn_kernel (const Taps0Params T, uint32_t hh, uint32_t vh)
+smol_tapsn_kernel (const Taps0Params T, uint32_t vh)
 {
     __shared__ uint32_t sm_inv[256];
     const TapsParams &P = T.t;
+    constexpr uint32_t N_H = 1u << HH;
 
     pdl_launch_dependents ();
     if constexpr (OU)
@@ -1425,18 +1434,28 @@ smol_tapsn_kernel (const Taps0Params T, uint32_t hh, uint32_t vh)
     if (x >= P.w_out || yl >= P.n_rows)
         return;
 
-    const uint32_t n_h = 1u << hh, n_v = 1u << vh;
-    const uint32_t *tx = P.tab_x + (x << hh);
+    const uint32_t n_v = 1u << vh;
     const uint32_t *ty = P.tab_y + ((P.first_row + yl) << vh);
     const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
 
+    /* this pixel's horizontal taps are the same on every source row: decoded once, kept in registers */
+    uint32_t op[N_H], oq[N_H], Fx[N_H];
+#pragma unroll
+    for (uint32_t k = 0; k < N_H; k++)
+    {
+        const uint32_t e = __ldg (&P.tab_x[(x << HH) + k]);
+        op[k] = SMOL_TAB_OFS (e) * BI;
+        oq[k] = min (SMOL_TAB_OFS (e) + 1, P.w_in - 1) * BI;
+        Fx[k] = SMOL_TAB_F (e);
+    }
+
     if (in_first_wave (T.prefetch) && (threadIdx.x & 3) == 0)
     {
-        /* every source row of this output pixel, from its first column on (four lanes share the prefetch) */
-        const uint32_t c0 = SMOL_TAB_OFS (__ldg (&tx[0])) * BI;
+        /* every source row of this output pixel, from its first column on (four lanes share the
+         * prefetch).  (Pulling the rows into L1 in every CTA was measured too: slower.) */
         const uint32_t ra = SMOL_TAB_OFS (__ldg (&ty[0])), rb = min (SMOL_TAB_OFS (__ldg (&ty[n_v - 1])) + 1, P.h_in - 1);
         for (uint32_t r = ra; r <= rb; r++)
-            prefetch_l2 (src + (size_t) r * P.src_pitch + c0);
+            prefetch_l2 (src + (size_t) r * P.src_pitch + op[0]);
     }
     pdl_wait ();
 
@@ -1444,19 +1463,18 @@ smol_tapsn_kernel (const Taps0Params T, uint32_t hh, uint32_t vh)
     {
         const uint8_t *row = src + (size_t) r * P.src_pitch;
         uint32_t acc_a = 0, acc_b = 0;
-#pragma unroll 1
-        for (uint32_t k = 0; k < n_h; k++)
+#pragma unroll
+        for (uint32_t k = 0; k < N_H; k++)
         {
-            const uint32_t e = __ldg (&tx[k]);
-            const uint32_t ofs = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e), G = 256u - F;
-            const Px16 p = taps0_fetch<BI, IU, AF, true> (row, ofs);
-            const Px16 q = taps0_fetch<BI, IU, AF, true> (row, min (ofs + 1, P.w_in - 1));
+            const uint32_t F = Fx[k], G = 256u - F;
+            const Px16 p = taps0_fetch<BI, IU, AF, true> (row + op[k], 0);
+            const Px16 q = taps0_fetch<BI, IU, AF, true> (row + oq[k], 0);
             acc_a += __byte_perm (p.a * F + q.a * G, 0, 0x4341);       /* ((..) >> 8) & 0x00ff00ff */
             acc_b += __byte_perm (p.b * F + q.b * G, 0, 0x4341);
         }
         Px16 h;
-        h.a = (acc_a >> hh) & 0x00ff00ffu;
-        h.b = (acc_b >> hh) & 0x00ff00ffu;
+        h.a = (acc_a >> HH) & 0x00ff00ffu;
+        h.b = (acc_b >> HH) & 0x00ff00ffu;
         return h;
     };
 
@@ -3473,6 +3491,15 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
         T.prefetch = pdl_first_wave (256, d.out_unassoc ? 1024 : 0);
         if (d.out_unassoc && T.prefetch)
             T.prefetch = 0xffffffffu;   /* an inverse table is staged first: see launch_half */
+        {
+            static int tune_ahead = -1;
+            if (tune_ahead < 0)
+            {
+                const char *e = getenv ("SMOL_TAPS_ROW_AHEAD");
+                tune_ahead = e ? atoi (e) : 2;      /* measured: 4K 1:1 21.8 -> 19.8 us, 4K -> 1440p 12.4 -> 10.8 us */
+            }
+            T.row_ahead = (uint32_t) tune_ahead;
+        }
         const bool af = d.in_alpha_idx == 0;
         const bool fastio = T.src_u32_ok && (reinterpret_cast<uintptr_t> (L.dst) & 3) == 0
                             && (L.dst_pitch & 3) == 0 && (L.dst_image_stride & 3) == 0;
@@ -3533,6 +3560,15 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
         T.prefetch = pdl_first_wave (256, d.out_unassoc ? 1024 : 0);
         if (d.out_unassoc && T.prefetch)
             T.prefetch = 0xffffffffu;   /* an inverse table is staged first: see launch_half */
+        {
+            static int tune_ahead = -1;
+            if (tune_ahead < 0)
+            {
+                const char *e = getenv ("SMOL_TAPS_ROW_AHEAD");
+                tune_ahead = e ? atoi (e) : 2;      /* measured: 4K 1:1 21.8 -> 19.8 us, 4K -> 1440p 12.4 -> 10.8 us */
+            }
+            T.row_ahead = (uint32_t) tune_ahead;
+        }
         const bool dst_ok = d.bpp_out == 3 || ((reinterpret_cast<uintptr_t> (L.dst) & 3) == 0 && (L.dst_pitch & 3) == 0
                                                && (L.dst_image_stride & 3) == 0);
         if (T.src_u32_ok && dst_ok)
@@ -3547,7 +3583,9 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
             dim3 ngrid ((d.w_out + nbx - 1) / nbx, (L.n_rows + nby - 1) / nby, L.n_images);
             const bool af = d.in_alpha_idx == 0;
             const uint32_t hh = d.h_halvings, vh = d.v_halvings;
-#define TAPSN(BI, BO, IU, OU, AF) launch_pdl_args (smol_tapsn_kernel<BI, BO, IU, OU, AF>, ngrid, nblock, 0, stream, T, hh, vh)
+#define TAPSN(BI, BO, IU, OU, AF) (hh == 0 ? launch_pdl_args (smol_tapsn_kernel<BI, BO, IU, OU, AF, 0>, ngrid, nblock, 0, stream, T, vh) \
+                                   : hh == 1 ? launch_pdl_args (smol_tapsn_kernel<BI, BO, IU, OU, AF, 1>, ngrid, nblock, 0, stream, T, vh) \
+                                             : launch_pdl_args (smol_tapsn_kernel<BI, BO, IU, OU, AF, 2>, ngrid, nblock, 0, stream, T, vh))
             if (d.bpp_in == 3)
             {
                 if (d.bpp_out == 3)     return TAPSN (3, 3, false, false, false);
