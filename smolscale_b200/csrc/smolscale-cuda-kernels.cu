@@ -2333,7 +2333,6 @@ smol_box_kernel (const BoxParams P)
     constexpr uint32_t TAB_BYTES = TAB ? 65536 * 2 : REP_BYTES;
     /* LUTM = 3: first window address above the tables */
     constexpr uint32_t WIN_HI = NEED_INV ? SMOL_BOX3_INV_WIN + 65536u : SMOL_BOX3_FROM_WIN + 65536u;
-    static_assert (LUTM != 3 || NEED_FROM, "byte-addressed tables: linear-light modes only");
     const SmolJobDesc &d = P.d;
     const uint16_t *sm_tab = reinterpret_cast<const uint16_t *> (sm_dyn);
     const uint32_t *sm_inv8 = sm_inv8_plain, *sm_from = sm_from_plain;
@@ -2362,6 +2361,10 @@ smol_box_kernel (const BoxParams P)
         }
         sm_from = rep_from + (threadIdx.x & 31);
         sm_inv8 = rep_inv + (threadIdx.x & 31);
+    }
+    else if constexpr (LUTM == 3 && !NEED_FROM)
+    {
+        /* the lean row loop without data tables (8-bit and 16-bit premultiplied intermediates) */
     }
     else if constexpr (LUTM == 3)
     {
@@ -2393,7 +2396,7 @@ smol_box_kernel (const BoxParams P)
     const uint32_t G = 1u << P.lanes_per_col_log2, g = lane & (G - 1);
     const uint32_t cols_per_item = 32u >> P.lanes_per_col_log2;
     uint8_t *bufs = sm_dyn + TAB_BYTES + (size_t) warp * 2 * P.seg_bytes;
-    if constexpr (LUTM == 3)
+    if constexpr (LUTM == 3 && NEED_FROM)
     {
         /* staging buffers: the first warps_lo warps below the tables, the others above them */
         const uint32_t dyn_win = (uint32_t) __cvta_generic_to_shared (sm_dyn) & 0x00ffffffu;
@@ -2559,7 +2562,24 @@ smol_box_kernel (const BoxParams P)
                     const uint32_t b = j * 3 - win0, a = row + (b & ~3u);
                     return __funnelshift_r (lds_u32_ordered (a), lds_u32_ordered (a + 4), (b & 3) * 8) | 0xff000000u;
                 };
-                uint32_t acc[4] = { 0, 0, 0, 0 };
+                BoxPx<MODE> acc;
+#pragma unroll
+                for (int i = 0; i < (S128 ? 4 : 2); i++) acc.v[i] = 0;
+                /* unpack one pixel into the accumulators, table modes through box3_accum */
+                auto accum = [&] (uint32_t raw)
+                {
+                    if constexpr (NEED_FROM)
+                        box3_accum<MODE, false> (raw, 0, acc.v, P, from_y, inv_y);
+                    else
+                        box_add<MODE> (acc, box_unpack<MODE, 0> (raw, P, nullptr, nullptr, nullptr));
+                };
+                auto accum_w = [&] (uint32_t raw, uint32_t w)
+                {
+                    if constexpr (NEED_FROM)
+                        box3_accum<MODE, true> (raw, w, acc.v, P, from_y, inv_y);
+                    else
+                        box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE, 0> (raw, P, nullptr, nullptr, nullptr), w));
+                };
 
                 if constexpr (BI == 4)
                 {
@@ -2571,61 +2591,57 @@ smol_box_kernel (const BoxParams P)
                         for (; a + 4 * G < a_end; a += 8 * G)
                         {
                             const uint32_t raw0 = lds_u32_ordered (a), raw1 = lds_u32_ordered (a + 4 * G);
-                            box3_accum<MODE, false> (raw0, 0, acc, P, from_y, inv_y);
-                            box3_accum<MODE, false> (raw1, 0, acc, P, from_y, inv_y);
+                            accum (raw0);
+                            accum (raw1);
                         }
                         if (a < a_end)
-                            box3_accum<MODE, false> (lds_u32_ordered (a), 0, acc, P, from_y, inv_y);
+                            accum (lds_u32_ordered (a));
                     }
                     else
                     {
                         for (; a < a_end; a += 4 * G)
-                            box3_accum<MODE, false> (lds_u32_ordered (a), 0, acc, P, from_y, inv_y);
+                            accum (lds_u32_ordered (a));
                     }
                     if (g == 0)
-                        box3_accum<MODE, true> (lds_u32_ordered (row + o_left), wl, acc, P, from_y, inv_y);
+                        accum_w (lds_u32_ordered (row + o_left), wl);
                     if (g == G - 1 && wr > 0)
-                        box3_accum<MODE, true> (lds_u32_ordered (row + o_end), wr, acc, P, from_y, inv_y);
+                        accum_w (lds_u32_ordered (row + o_end), wr);
                 }
                 else
                 {
                     for (uint32_t j = hL + 1 + g; j < hR; j += G)
-                        box3_accum<MODE, false> (fetch3 (j), 0, acc, P, from_y, inv_y);
+                        accum (fetch3 (j));
                     if (g == 0)
-                        box3_accum<MODE, true> (fetch3 (hL), wl, acc, P, from_y, inv_y);
+                        accum_w (fetch3 (hL), wl);
                     if (g == G - 1 && wr > 0)
-                        box3_accum<MODE, true> (fetch3 (hR), wr, acc, P, from_y, inv_y);
+                        accum_w (fetch3 (hR), wr);
                 }
                 for (uint32_t m = G >> 1; m; m >>= 1)
                 {
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        acc[i] += __shfl_xor_sync (0xffffffffu, acc[i], m);
+                    for (int i = 0; i < (S128 ? 4 : 2); i++)
+                        acc.v[i] += __shfl_xor_sync (0xffffffffu, acc.v[i], m);
                 }
 
-                /* scale_128bpp_half (generic:1247-1261): the 16-bit mask cannot bite in the
-                 * P8-LINEAR modes (lanes are averages of values below 2^11) */
-                uint32_t h[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++)
+                /* scale_128bpp_half / scale_64bpp (generic:1231-1261): in the P8-LINEAR modes the
+                 * 16-bit mask cannot bite (lanes are averages of values below 2^11) */
+                BoxPx<MODE> h;
+                if constexpr (S128)
                 {
-                    h[i] = (uint32_t) (((uint64_t) acc[i] * P.mul8_x + 0x80000000ull) >> 32);
-                    if constexpr (MODE == BM_P16L_U)
-                        h[i] &= 0xffffu;
-                }
-                if (r == T || r == B)
-                {
-                    const uint32_t wrow = r == T ? w1 : w2;
 #pragma unroll
                     for (int i = 0; i < 4; i++)
-                        vacc.v[i] += (h[i] * wrow) >> 8;
+                    {
+                        h.v[i] = (uint32_t) (((uint64_t) acc.v[i] * P.mul8_x + 0x80000000ull) >> 32);
+                        if constexpr (MODE == BM_P16L_U || MODE == BM_P16_U)
+                            h.v[i] &= 0xffffu;
+                    }
                 }
                 else
-                {
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        vacc.v[i] += h[i];
-                }
+                    h = box_scale<MODE> (acc, d.span_mul_x, true);
+                if (r == T || r == B)
+                    box_add<MODE> (vacc, box_weight<MODE> (h, r == T ? w1 : w2));
+                else
+                    box_add<MODE> (vacc, h);
                 cur = P.seg_bytes - cur;
                 __syncwarp ();      /* everyone is done with this slot before it is refilled */
             }
@@ -3960,12 +3976,14 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     }
     /* table placement (see box_unpack / box3_accum): modes without gathers need none */
     const bool has_lut = mode == BM_P8L_P || mode == BM_P8L_U || mode == BM_P16L_U;
-    int lutm = has_lut ? tune_lut : 0;
+    /* 3 = the lean row loop (with byte-addressed tables where the mode has any); other values
+     * select the older table placements for the linear-light modes and the plain loop elsewhere */
+    int lutm = has_lut ? tune_lut : (tune_lut == 3 ? 3 : 0);
     if (lutm == 1 && d.mid != SMOL_MID_P8L)
         lutm = 2;
     if (lutm == 3 && (d.span_mul_x >= (1u << 24) || d.span_mul_y >= (1u << 24)))
-        lutm = 2;                       /* the multiply-high normalisation wants span_mul << 8 in 32 bits */
-    if (lutm == 3)
+        lutm = has_lut ? 2 : 0;         /* the multiply-high normalisation wants span_mul << 8 in 32 bits */
+    if (lutm == 3 && has_lut)
     {
         /* the 64 KB-per-table layout must leave room for at least 8 warps' staging buffers
          * (longest segments: the starting G of the loop below) */
@@ -3990,11 +4008,12 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     const void *fn;
     switch (mode)
     {
-        case BM_P8_P:   fn = bi3 ? (const void *) smol_box_kernel<BM_P8_P, 0, 3> : (const void *) smol_box_kernel<BM_P8_P, 0, 4>; break;
-        case BM_P8_U:   fn = (const void *) smol_box_kernel<BM_P8_U, 0, 4>; break;
+        case BM_P8_P:   fn = lutm == 3 ? (bi3 ? (const void *) smol_box_kernel<BM_P8_P, 3, 3> : (const void *) smol_box_kernel<BM_P8_P, 3, 4>)
+                                       : (bi3 ? (const void *) smol_box_kernel<BM_P8_P, 0, 3> : (const void *) smol_box_kernel<BM_P8_P, 0, 4>); break;
+        case BM_P8_U:   fn = lutm == 3 ? (const void *) smol_box_kernel<BM_P8_U, 3, 4> : (const void *) smol_box_kernel<BM_P8_U, 0, 4>; break;
         case BM_P8L_P:  fn = bi3 ? BOX_KERNEL_FOR3 (BM_P8L_P) : BOX_KERNEL_FOR (BM_P8L_P); break;
         case BM_P8L_U:  fn = BOX_KERNEL_FOR (BM_P8L_U); break;
-        case BM_P16_U:  fn = (const void *) smol_box_kernel<BM_P16_U, 0, 4>; break;
+        case BM_P16_U:  fn = lutm == 3 ? (const void *) smol_box_kernel<BM_P16_U, 3, 4> : (const void *) smol_box_kernel<BM_P16_U, 0, 4>; break;
         default:        fn = lutm == 3 ? (const void *) smol_box_kernel<BM_P16L_U, 3, 4>
                              : lutm == 2 ? (const void *) smol_box_kernel<BM_P16L_U, 2, 4> : (const void *) smol_box_kernel<BM_P16L_U, 0, 4>; break;
     }
@@ -4010,7 +4029,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         glog++;
 
     const size_t lut_bytes = lutm == 1 ? 131072
-                             : lutm == 3 ? (mode == BM_P8L_P ? 131072 : 65536)
+                             : lutm == 3 ? (mode == BM_P8L_P ? 131072 : has_lut ? 65536 : 0)
                              : lutm == 2 ? (mode == BM_P8L_P ? 65536 : 32768) : 0;
     size_t smem = 0;
     uint32_t per_sm = 1, warps_per_cta = lutm == 2 ? 16 : 8;
@@ -4040,7 +4059,8 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
             const size_t per_warp = 2 * (size_t) P.seg_bytes;
             const size_t win_hi = lut_bytes == 131072 ? 0x30000 : 0x20000;
             const size_t dyn_max = 225 * 1024 - 64;
-            const size_t lo_room = 0x10000 - 0x480, hi_room = dyn_max - (win_hi - 0x400);
+            /* without tables the buffers are simply contiguous ("lo" = all of them) */
+            const size_t lo_room = has_lut ? 0x10000 - 0x480 : dyn_max, hi_room = has_lut ? dyn_max - (win_hi - 0x400) : 0;
             uint32_t lo = (uint32_t) (lo_room / per_warp), hi = (uint32_t) (hi_room / per_warp);
             lo = lo > 32 ? 32 : lo;
             hi = hi > 32 - lo ? 32 - lo : hi;
@@ -4071,7 +4091,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
             }
             P.warps_lo = lo;
             warps_per_cta = lo + hi;
-            smem = (win_hi - 0x400) + hi * per_warp;
+            smem = has_lut ? (win_hi - 0x400) + hi * per_warp : (size_t) warps_per_cta * per_warp;
         }
         if (smem > 32 * 1024)        /* static shared memory counts against the 48 KB default too */
             cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
@@ -4094,11 +4114,12 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
 #define BOX_LAUNCH_LUT(M, B) (lutm == 3 ? BOX_LAUNCH (M, 3, B) : lutm == 1 ? BOX_LAUNCH (M, 1, B) : lutm == 2 ? BOX_LAUNCH (M, 2, B) : BOX_LAUNCH (M, 0, B))
     switch (mode)
     {
-        case BM_P8_P:   return bi3 ? BOX_LAUNCH (BM_P8_P, 0, 3) : BOX_LAUNCH (BM_P8_P, 0, 4);
-        case BM_P8_U:   return BOX_LAUNCH (BM_P8_U, 0, 4);
+        case BM_P8_P:   return lutm == 3 ? (bi3 ? BOX_LAUNCH (BM_P8_P, 3, 3) : BOX_LAUNCH (BM_P8_P, 3, 4))
+                                         : (bi3 ? BOX_LAUNCH (BM_P8_P, 0, 3) : BOX_LAUNCH (BM_P8_P, 0, 4));
+        case BM_P8_U:   return lutm == 3 ? BOX_LAUNCH (BM_P8_U, 3, 4) : BOX_LAUNCH (BM_P8_U, 0, 4);
         case BM_P8L_P:  return bi3 ? BOX_LAUNCH_LUT (BM_P8L_P, 3) : BOX_LAUNCH_LUT (BM_P8L_P, 4);
         case BM_P8L_U:  return BOX_LAUNCH_LUT (BM_P8L_U, 4);
-        case BM_P16_U:  return BOX_LAUNCH (BM_P16_U, 0, 4);
+        case BM_P16_U:  return lutm == 3 ? BOX_LAUNCH (BM_P16_U, 3, 4) : BOX_LAUNCH (BM_P16_U, 0, 4);
         default:        return lutm == 3 ? BOX_LAUNCH (BM_P16L_U, 3, 4) : lutm == 2 ? BOX_LAUNCH (BM_P16L_U, 2, 4) : BOX_LAUNCH (BM_P16L_U, 0, 4);
     }
 #undef BOX_LAUNCH_LUT

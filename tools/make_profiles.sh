@@ -3,7 +3,7 @@
 # bench lines for the five BASELINE configurations, the reference arm, the ncu launch list of the
 # default bench command, one `ncu --set full` capture per configuration's kernel, the type-pair
 # matrices and the bandwidth probe.  Everything lands in gpurun_out/; summaries are made from the
-# .ncu-rep files afterwards with tools/ncu_summary.py and copied to profiles/.
+# reports on the box with tools/ncu_summary.py / ncu_sass_hot.py; copy what should be judged to profiles/.
 R=${1:-r01}
 O=gpurun_out
 mkdir -p $O
@@ -15,8 +15,11 @@ python bench.py --impl reference 2>/dev/null | tail -1 > $O/${R}_bench_reference
 python tools/bw_probe.py > $O/${R}_bw_probe.json 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_launches_cfg2.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
-prof () { # name, kernel regex, one_conv args
+prof () { # name, kernel regex, one_conv args: summary + hottest SASS lines; the report itself is dropped (gpurun_out is capped at 64 MiB)
   ncu --set full --clock-control none --import-source on -k regex:$2 -s 2 -c 1 -f -o $O/${R}_full_$1 python tools/one_conv.py $3 > /dev/null 2>&1
+  python tools/ncu_summary.py $O/${R}_full_$1.ncu-rep > $O/${R}_ncu_full_$1.txt 2>&1
+  python tools/ncu_sass_hot.py $O/${R}_full_$1.ncu-rep 1 > $O/${R}_ncu_sass_hot_$1.txt 2>&1
+  rm -f $O/${R}_full_$1.ncu-rep
 }
 prof cfg1 smol_half "1920 1080 960 540 0 0 0"
 prof cfg2 smol_half "3840 2160 1920 1080 1 5 0"
