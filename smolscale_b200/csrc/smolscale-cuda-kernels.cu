@@ -1429,16 +1429,19 @@ smol_tapsn_kernel (const Taps0Params T, uint32_t vh)
         __syncthreads ();
     }
 
+    /* one thread = one output column x a strip of rows_per_thread output rows: the column's
+     * horizontal taps are decoded once, and the two-row cache carries over from one output row
+     * to the next (its last source row is often the next one's first) */
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t yl = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= P.w_out || yl >= P.n_rows)
+    const uint32_t yl0 = (blockIdx.y * blockDim.y + threadIdx.y) * P.rows_per_thread;
+    if (x >= P.w_out || yl0 >= P.n_rows)
         return;
+    const uint32_t yl1 = min (yl0 + P.rows_per_thread, P.n_rows);
 
     const uint32_t n_v = 1u << vh;
-    const uint32_t *ty = P.tab_y + ((P.first_row + yl) << vh);
+    const uint32_t *ty = P.tab_y + ((P.first_row + yl0) << vh);
     const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
 
-    /* this pixel's horizontal taps are the same on every source row: decoded once, kept in registers */
     uint32_t op[N_H], oq[N_H], Fx[N_H];
 #pragma unroll
     for (uint32_t k = 0; k < N_H; k++)
@@ -1451,8 +1454,8 @@ smol_tapsn_kernel (const Taps0Params T, uint32_t vh)
 
     if (in_first_wave (T.prefetch) && (threadIdx.x & 3) == 0)
     {
-        /* every source row of this output pixel, from its first column on (four lanes share the
-         * prefetch).  (Pulling the rows into L1 in every CTA was measured too: slower.) */
+        /* every source row of the strip's first output pixel, from its first column on (four lanes
+         * share the prefetch).  (Pulling the rows into L1 in every CTA was measured too: slower.) */
         const uint32_t ra = SMOL_TAB_OFS (__ldg (&ty[0])), rb = min (SMOL_TAB_OFS (__ldg (&ty[n_v - 1])) + 1, P.h_in - 1);
         for (uint32_t r = ra; r <= rb; r++)
             prefetch_l2 (src + (size_t) r * P.src_pitch + op[0]);
@@ -1481,47 +1484,52 @@ smol_tapsn_kernel (const Taps0Params T, uint32_t vh)
     uint32_t idx0 = 0xffffffffu, idx1 = 0xffffffffu;
     Px16 c0, c1;
     c0.a = c0.b = c1.a = c1.b = 0;
-    uint32_t acc_a = 0, acc_b = 0;
+    uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl0 * P.dst_pitch + (size_t) x * BO;
 
 #pragma unroll 1
-    for (uint32_t kv = 0; kv < n_v; kv++)
+    for (uint32_t yl = yl0; yl < yl1; yl++, ty += n_v, dst += P.dst_pitch)
     {
-        const uint32_t e = __ldg (&ty[kv]);
-        const uint32_t r0 = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e), G = 256u - F;
-        const uint32_t r1 = min (r0 + 1, P.h_in - 1);
+        uint32_t acc_a = 0, acc_b = 0;
 
-        if (r0 != idx0)
+#pragma unroll 1
+        for (uint32_t kv = 0; kv < n_v; kv++)
         {
-            if (r0 == idx1)
+            const uint32_t e = __ldg (&ty[kv]);
+            const uint32_t r0 = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e), G = 256u - F;
+            const uint32_t r1 = min (r0 + 1, P.h_in - 1);
+
+            if (r0 != idx0)
             {
-                const Px16 t = c0; c0 = c1; c1 = t;
-                idx1 = idx0;
+                if (r0 == idx1)
+                {
+                    const Px16 t = c0; c0 = c1; c1 = t;
+                    idx1 = idx0;
+                }
+                else
+                    c0 = hval (r0);
+                idx0 = r0;
             }
-            else
-                c0 = hval (r0);
-            idx0 = r0;
+            if (r1 != idx1)
+            {
+                c1 = hval (r1);
+                idx1 = r1;
+            }
+            acc_a += __byte_perm (c0.a * F + c1.a * G, 0, 0x4341);
+            acc_b += __byte_perm (c0.b * F + c1.b * G, 0, 0x4341);
         }
-        if (r1 != idx1)
+
+        const uint32_t fa = (acc_a >> vh) & 0x00ff00ffu, fb = (acc_b >> vh) & 0x00ff00ffu;
+        uint32_t v = fa | (fb << 8);                                         /* source byte order */
+        if constexpr (OU)
+            v = half_unpremul<AF> (v, sm_inv);
+        v = __byte_perm (v, 0, P.prmt_sel);
+
+        if constexpr (BO == 4)
+            *reinterpret_cast<uint32_t *> (dst) = v;
+        else
         {
-            c1 = hval (r1);
-            idx1 = r1;
+            dst[0] = (uint8_t) v; dst[1] = (uint8_t) (v >> 8); dst[2] = (uint8_t) (v >> 16);
         }
-        acc_a += __byte_perm (c0.a * F + c1.a * G, 0, 0x4341);
-        acc_b += __byte_perm (c0.b * F + c1.b * G, 0, 0x4341);
-    }
-
-    const uint32_t fa = (acc_a >> vh) & 0x00ff00ffu, fb = (acc_b >> vh) & 0x00ff00ffu;
-    uint32_t v = fa | (fb << 8);                                         /* source byte order */
-    if constexpr (OU)
-        v = half_unpremul<AF> (v, sm_inv);
-    v = __byte_perm (v, 0, P.prmt_sel);
-
-    uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl * P.dst_pitch + (size_t) x * BO;
-    if constexpr (BO == 4)
-        *reinterpret_cast<uint32_t *> (dst) = v;
-    else
-    {
-        dst[0] = (uint8_t) v; dst[1] = (uint8_t) (v >> 8); dst[2] = (uint8_t) (v >> 16);
     }
 }
 
@@ -1739,6 +1747,13 @@ smol_mag_kernel (const MagParams M)
  *      (the per-pixel kernel above spends 16 multiplies and 3 stores per 12 bytes at 24bpp).    *
  * ------------------------------------------------------------------------------------------ */
 
+/* Resident CTAs per SM asked of the compiler.  8 (32 registers per thread) would let BASELINE
+ * config 4's 1152 tiles run as one wave instead of 1.3, but the spills it costs are worse
+ * (measured: 11.7 -> 12.3 us; 2x 24bpp 15.2 -> 19.1 us), so the kernel keeps its 40 registers. */
+#ifndef SMOL_MAGB_MINBLOCKS
+#define SMOL_MAGB_MINBLOCKS 1
+#endif
+
 struct MagbParams
 {
     TapsParams t;
@@ -1758,7 +1773,7 @@ struct MagbParams
  * output (32bpp only: a 16-byte column is then four whole pixels, unpremultiplied just before the
  * store); AF alpha is byte 0 of the source pixel; SRC32 source rows are 4-byte aligned. */
 template <int BI, int BO, bool IU, bool OU, bool AF, bool SRC32>
-__global__ void __launch_bounds__ (256)
+__global__ void __launch_bounds__ (256, SMOL_MAGB_MINBLOCKS)
 smol_magb_kernel (const MagbParams M)
 {
     static_assert (!OU || BO == 4, "unassociated output is 32bpp");
@@ -3592,11 +3607,26 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
             uint32_t nbx = 32;
             while (nbx < 128 && nbx < d.w_out)
                 nbx *= 2;
+            /* output rows per thread (SMOL_TAPSN_RPT) */
+            static int tune_nrpt = -1;
+            if (tune_nrpt < 0)
+            {
+                const char *e = getenv ("SMOL_TAPSN_RPT");
+                tune_nrpt = e ? atoi (e) : 0;
+            }
+            /* Measured (4K source, us per frame at 1 / 2 / 4 rows per thread): -> 1280x720 14.1 /
+             * 14.4 / 17.1, -> 1600x900 20.8 / 18.4 / 17.9, -> 800x450 15.0 / 16.3 / 22.2: the row
+             * cache rarely carries over and the lost parallelism costs more, so one row it is. */
+            uint32_t nrpt = 1;
+            if (tune_nrpt > 0)
+                nrpt = (uint32_t) tune_nrpt;
+            T.t.rows_per_thread = nrpt;
+            const uint32_t nstrips = (L.n_rows + nrpt - 1) / nrpt;
             uint32_t nby = 256 / nbx;
-            if (nby > L.n_rows)
-                nby = L.n_rows;
+            if (nby > nstrips)
+                nby = nstrips;
             dim3 nblock (nbx, nby);
-            dim3 ngrid ((d.w_out + nbx - 1) / nbx, (L.n_rows + nby - 1) / nby, L.n_images);
+            dim3 ngrid ((d.w_out + nbx - 1) / nbx, (nstrips + nby - 1) / nby, L.n_images);
             const bool af = d.in_alpha_idx == 0;
             const uint32_t hh = d.h_halvings, vh = d.v_halvings;
 #define TAPSN(BI, BO, IU, OU, AF) (hh == 0 ? launch_pdl_args (smol_tapsn_kernel<BI, BO, IU, OU, AF, 0>, ngrid, nblock, 0, stream, T, vh) \

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""HBM bandwidth probe: write-only (fill), read-only (sum) and copy, large buffers, CUDA events.
+"""HBM bandwidth probe: write-only (fill) and copy, large buffers, CUDA events.
 Context for the roofline of write-dominated configurations (cfg4 writes 16x what it reads)."""
 import torch, json
 n = 1 << 30
@@ -16,9 +16,4 @@ def timeit(f, reps=10):
 res = {}
 res["fill_GBs"] = n / timeit(lambda: a.zero_()) / 1e6
 res["copy_rw_GBs"] = 2 * n / timeit(lambda: b.copy_(a)) / 1e6
-a32 = a.view(torch.int32)
-res["read_sum_GBs"] = n / timeit(lambda: a32.sum()) / 1e6
-# write-heavy mix like cfg4: read 1/16, write 1
-src = a[: n // 16]
-res["expand16_rw_GBs"] = (n + n // 16) / timeit(lambda: b.view(16, n // 16).copy_(src.expand(16, n // 16))) / 1e6
 print(json.dumps(res))

@@ -10,12 +10,22 @@ chk = oracle.restatement()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 bad = 0
 jobs = cases.job_matrix(31337, n) + cases.half_jobs()[:40]
+# aligned-pitch magnifications (byte-granular tile kernel) and box jobs with long / ragged windows
+for (wi, hi, wo, ho) in [(64, 48, 256, 192), (100, 7, 349, 65), (33, 30, 130, 61), (5, 4, 40, 30), (300, 40, 1500, 97)]:
+    for ti, to in [(cases.RGB8, cases.BGR8), (cases.BGR8, cases.RGB8), (cases.RGBA8_P, cases.RGB8)]:
+        jobs.append((ti, wi, hi, wi * cases.bpp(ti), to, wo, ho, (wo * cases.bpp(to) + 15) // 16 * 16, 0, "random"))
+for (wi, hi, wo, ho) in [(200, 90, 15, 9), (255, 100, 16, 7), (1500, 120, 100, 11), (1021, 50, 64, 5), (4000, 40, 15, 3)]:
+    for ti, srgb in [(cases.RGBA8_P, 1), (cases.ARGB8_U, 1), (cases.RGB8, 0), (cases.BGRA8_U, 0), (cases.RGB8, 1)]:
+        jobs.append((ti, wi, hi, (wi * cases.bpp(ti) + 15) // 16 * 16, cases.RGBA8_P, wo, ho, wo * 4, srgb, "random"))
 for idx, job in enumerate(jobs):
     ti, wi, hi, si, to, wo, ho, so, srgb, mode = job
     src = cases.make_image(ti, wi, hi, si, mode, seed=idx)
     want = chk.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
     # device pointers placed at the very end of their allocations: any over-read/-write is out of bounds
-    d_in = torch.empty(src.size, dtype=torch.uint8, device="cuda"); d_in.copy_(torch.from_numpy(src))
+    # (run with PYTORCH_NO_CUDA_MEMORY_CACHING=1 so that every tensor is its own cudaMalloc); the last
+    # source row carries no pitch padding
+    n_in = si * (hi - 1) + wi * cases.bpp(ti)
+    d_in = torch.empty(n_in, dtype=torch.uint8, device="cuda"); d_in.copy_(torch.from_numpy(src[:n_in]))
     d_out = torch.full((want.size,), 0xCD, dtype=torch.uint8, device="cuda")
     sb.scale_simple(d_in, ti, wi, hi, si, d_out, to, wo, ho, so, srgb)
     torch.cuda.synchronize()
