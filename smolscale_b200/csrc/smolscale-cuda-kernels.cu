@@ -2057,7 +2057,7 @@ smol_magb_kernel (const MagbParams M)
  *     (G lanes share a column when spans are long); warps stride over the work items, so load   *
  *     balance is at warp granularity and no block-wide barrier is ever needed;                  *
  *   - for each source row of the item the warp copies the row segment it needs into its own     *
- *     shared-memory buffer with cp.async (16-byte, fully coalesced, zero-filled past the row's  *
+ *     shared-memory buffer with cp.async (16-byte, fully coalesced; byte-exact at a ragged row  *
  *     end), double-buffered so the copy of row r + 1 overlaps the arithmetic on row r;          *
  *   - each lane then walks its own span in shared memory (stride ~ratio words between lanes:    *
  *     practically conflict-free), unpacks and accumulates in registers, applies the two edge    *
@@ -2095,9 +2095,26 @@ struct BoxParams
     uint32_t prefetch;              /* L2-prefetch the first window rows ahead of the dependency wait */
 };
 
+/* One 16-byte chunk of a staged row, of which the first src_bytes (1..16) lie inside the source
+ * row.  A whole chunk is an asynchronous copy; a partial one (only the chunk that straddles the end
+ * of a row whose length is not a multiple of 16) is copied byte by byte: cp.async with a short
+ * src-size still touches all 16 source bytes, which on the image's last row may lie outside the
+ * caller's buffer (compute-sanitizer memcheck, buffers allocated with no slack).  The bytes past
+ * the row's end are never read, so they need no zero-fill.  The plain stores become visible to the
+ * warp at the __syncwarp that follows the cp.async wait. */
 __device__ __forceinline__ void cp_async_16 (uint32_t smem_addr, const void *gptr, uint32_t src_bytes)
 {
-    asm volatile ("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
+    if (src_bytes >= 16)
+        asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gptr) : "memory");
+    else
+    {
+        const uint8_t *g = static_cast<const uint8_t *> (gptr);
+        for (uint32_t i = 0; i < src_bytes; i++)
+        {
+            const uint32_t v = __ldg (g + i);
+            asm volatile ("st.shared.u8 [%0], %1;" :: "r"(smem_addr + i), "r"(v) : "memory");
+        }
+    }
 }
 __device__ __forceinline__ void cp_async_16_full (uint32_t smem_addr, const void *gptr)
 {
