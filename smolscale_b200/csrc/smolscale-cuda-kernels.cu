@@ -2832,43 +2832,60 @@ pack128_fast (const uint32_t lane[4], const SmolJobDesc &d, const SmolDeviceLuts
  * ------------------------------------------------------------------------------------------ */
 
 template <int MODE, int BI>
-__global__ void __launch_bounds__ (512, 2)
+__global__ void __launch_bounds__ (1024, 1)
 smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u32_ok)
 {
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
     constexpr bool NEED_INV = MODE == BM_P8L_P;
     constexpr bool NEED_FROM = MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U;
     const SmolJobDesc &d = P.d;
-    const uint32_t tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
 
     pdl_launch_dependents ();
-    uint32_t *rep_from = reinterpret_cast<uint32_t *> (sm_dyn);
-    uint32_t *rep_inv = rep_from + (NEED_FROM ? 8192 : 0);
-    for (uint32_t i = tid; i < 8192; i += nthr)
+    /* byte-addressed lane-replicated tables at fixed window addresses: layout and use as in the
+     * box kernel (see box3_accum) */
+    uint32_t from_y = 0, inv_y = 0;
+    if constexpr (NEED_FROM)
     {
-        if constexpr (NEED_FROM)
-            rep_from[i] = P.luts->from_srgb[i >> 5];
-        if constexpr (NEED_INV)
-            rep_inv[i] = P.luts->inv_div_p8[i >> 5] << 3;
+        const uint32_t dyn_addr = (uint32_t) __cvta_generic_to_shared (sm_dyn), dyn_win = dyn_addr & 0x00ffffffu;
+        uint32_t *t_from = reinterpret_cast<uint32_t *> (sm_dyn + (SMOL_BOX3_FROM_WIN - dyn_win));
+        uint2 *t_inv = reinterpret_cast<uint2 *> (sm_dyn + (SMOL_BOX3_INV_WIN - dyn_win));
+        for (uint32_t i = tid; i < 8192; i += nthr)
+        {
+            const uint32_t e = i >> 5, l = i & 31;
+            t_from[e * 64 + l] = (uint32_t) P.luts->from_srgb[e] + (MODE == BM_P16L_U ? 0u : 1u);
+            if constexpr (NEED_INV)
+                t_inv[e * 32 + l] = make_uint2 (P.luts->inv_div_p8[e] << 3, e * 8 + 1);
+        }
+        from_y = (dyn_addr & 0xff000000u) | SMOL_BOX3_FROM_WIN | ((tid & 31) * 4);
+        inv_y = (dyn_addr & 0xff000000u) | SMOL_BOX3_INV_WIN | ((tid & 31) * 8);
     }
-    const uint32_t *sm_from = rep_from + (tid & 31), *sm_inv8 = rep_inv + (tid & 31);
     __shared__ uint8_t sm_to_srgb[2048];
     if constexpr (MODE != BM_P16_U)
         for (uint32_t i = tid; i < 512; i += nthr)
             reinterpret_cast<uint32_t *> (sm_to_srgb)[i] = reinterpret_cast<const uint32_t *> (P.luts->to_srgb)[i];
     __syncthreads ();
 
-    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t yl = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= d.w_out || yl >= P.n_rows)
-        return;
+    pdl_wait ();
+
+    /* Persistent CTAs: the 64 KB of lane-replicated tables are filled once per CTA and then serve
+     * every work item its warps walk over (item = 32 adjacent output pixels of one row; the host
+     * picks the warp count that wastes least of the last round, as for the box kernel). */
+    const uint32_t items_x = (d.w_out + 31) / 32, items_per_image = items_x * P.n_rows;
+    const uint32_t n_items = items_per_image * P.n_images;
+    const uint32_t warps = nthr >> 5;
+    for (uint32_t item = blockIdx.x * warps + (tid >> 5); item < n_items; item += gridDim.x * warps)
+    {
+    const uint32_t tz = item / items_per_image, trem = item - tz * items_per_image;
+    const uint32_t yl = trem / items_x;
+    const uint32_t x = (trem - yl * items_x) * 32 + (tid & 31);
+    if (x >= d.w_out)
+        continue;
 
     const uint32_t n_h = 1u << hh, n_v = 1u << vh;
     const uint32_t *tx = P.tab_x + (x << hh);
     const uint32_t *ty = P.tab_y + ((P.first_row + yl) << vh);
-    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
-
-    pdl_wait ();
+    const uint8_t *src = P.src + (size_t) tz * P.src_image_stride;
 
     auto fetch = [&] (const uint8_t *row, uint32_t j) -> BoxPx<MODE>
     {
@@ -2881,7 +2898,16 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
             raw = (uint32_t) __ldg (p) | ((uint32_t) __ldg (p + 1) << 8) | ((uint32_t) __ldg (p + 2) << 16);
             raw |= BI == 4 ? ((uint32_t) __ldg (p + 3) << 24) : 0xff000000u;
         }
-        return box_unpack<MODE, 2> (raw, P, sm_inv8, sm_from, nullptr);
+        if constexpr (NEED_FROM)
+        {
+            BoxPx<MODE> r;
+#pragma unroll
+            for (int i = 0; i < 4; i++) r.v[i] = 0;
+            box3_accum<MODE, false> (raw, 0, r.v, P, from_y, inv_y);
+            return r;
+        }
+        else
+            return box_unpack<MODE, 0> (raw, P, nullptr, nullptr, nullptr);
     };
 
     auto hval = [&] (uint32_t r) -> BoxPx<MODE>
@@ -2943,8 +2969,9 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
 #pragma unroll
     for (int i = 0; i < 4; i++) fin[i] = (acc.v[i] >> vh) & 0x00ffffffu;
     const uint32_t packed = pack128_fast<MODE> (fin, d, P.luts, sm_to_srgb);
-    uint8_t *o8 = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl * P.dst_pitch + (size_t) x * d.bpp_out;
+    uint8_t *o8 = P.dst + (size_t) tz * P.dst_image_stride + (size_t) yl * P.dst_pitch + (size_t) x * d.bpp_out;
     store_raw_px (o8, packed, d.bpp_out);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ *
@@ -4185,25 +4212,62 @@ launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
     const uint32_t src_u32_ok = d.bpp_in == 3 || ((reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
                                                   && (L.src_image_stride & 3) == 0);
     const uint32_t hh = d.h_halvings, vh = d.v_halvings;
-    uint32_t bx = 32;
-    while (bx < 128 && bx < d.w_out)
-        bx *= 2;
-    uint32_t by = 512 / bx;
-    if (by > L.n_rows)
-        by = L.n_rows;
-    dim3 block (bx, by), grid ((d.w_out + bx - 1) / bx, (L.n_rows + by - 1) / by, L.n_images);
+    /* Persistent CTAs: warps walk work items of 32 output pixels.  The warp count per CTA
+     * (20..32) is the one that wastes least of the last round of items, given how many CTAs of
+     * that size are resident per SM (registers and the up to 64 KB of tables decide). */
+    const uint64_t n_items = (uint64_t) ((d.w_out + 31) / 32) * L.n_rows * L.n_images;
+    if (n_items > 0x7fffffffull)
+        return cudaErrorInvalidValue;
 
-#define T128(M, B, BYTES) (cudaFuncSetAttribute (smol_taps128_kernel<M, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), \
-                           launch_pdl_args (smol_taps128_kernel<M, B>, grid, block, (size_t) (BYTES), stream, P, hh, vh, src_u32_ok))
-    if (d.mid == SMOL_MID_P8L)
+    int variant;
+    const void *fn;
+    size_t bytes;
+    /* dynamic shared memory: up to the end of the tables' fixed window addresses (see box3_accum) */
+    const size_t one_tab = 0x20000 - 0x400, two_tabs = 0x30000 - 0x400;
+    if (d.mid == SMOL_MID_P8L && d.in_unassoc)      { variant = 0; fn = (const void *) smol_taps128_kernel<BM_P8L_U, 4>; bytes = one_tab; }
+    else if (d.mid == SMOL_MID_P8L && d.bpp_in == 3) { variant = 1; fn = (const void *) smol_taps128_kernel<BM_P8L_P, 3>; bytes = two_tabs; }
+    else if (d.mid == SMOL_MID_P8L)                 { variant = 2; fn = (const void *) smol_taps128_kernel<BM_P8L_P, 4>; bytes = two_tabs; }
+    else if (d.mid == SMOL_MID_P16)                 { variant = 3; fn = (const void *) smol_taps128_kernel<BM_P16_U, 4>; bytes = 0; }
+    else                                            { variant = 4; fn = (const void *) smol_taps128_kernel<BM_P16L_U, 4>; bytes = one_tab; }
+
+    static int occ_cache[5][33];        /* resident CTAs per SM by variant and warps per CTA (0: not asked yet) */
+    uint32_t best_w = 32, best_occ = 1;
     {
-        if (d.in_unassoc)
-            return T128 (BM_P8L_U, 4, 32768);
-        return d.bpp_in == 3 ? T128 (BM_P8L_P, 3, 65536) : T128 (BM_P8L_P, 4, 65536);
+        double best_eff = 0.0;
+        for (uint32_t w = 32; w >= 20; w--)
+        {
+            int occ = occ_cache[variant][w];
+            if (occ == 0)
+            {
+                cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, (int) w * 32, bytes) != cudaSuccess || occ < 1)
+                    occ = 1;
+                occ_cache[variant][w] = occ;
+            }
+            const uint64_t slots = (uint64_t) num_sms () * occ * w;
+            const uint64_t rounds = (n_items + slots - 1) / slots;
+            /* efficiency of the last round, scaled by how many warps the SM holds (latency hiding) */
+            const double eff = (double) n_items / (double) (rounds * slots) * (0.5 + 0.5 * (double) (occ * w) / 36.0);
+            if (eff > best_eff + 0.01)
+            {
+                best_eff = eff;
+                best_w = w;
+                best_occ = (uint32_t) occ;
+            }
+        }
     }
-    if (d.mid == SMOL_MID_P16)
-        return T128 (BM_P16_U, 4, 0);
-    return T128 (BM_P16L_U, 4, 32768);
+    const uint64_t ctas = (n_items + best_w - 1) / best_w, resident = (uint64_t) num_sms () * best_occ;
+    dim3 block (best_w * 32), grid ((unsigned) (ctas < resident ? ctas : resident));
+
+#define T128(M, B) launch_pdl_args (smol_taps128_kernel<M, B>, grid, block, bytes, stream, P, hh, vh, src_u32_ok)
+    switch (variant)
+    {
+        case 0:  return T128 (BM_P8L_U, 4);
+        case 1:  return T128 (BM_P8L_P, 3);
+        case 2:  return T128 (BM_P8L_P, 4);
+        case 3:  return T128 (BM_P16_U, 4);
+        default: return T128 (BM_P16L_U, 4);
+    }
 #undef T128
 }
 
