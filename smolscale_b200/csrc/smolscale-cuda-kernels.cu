@@ -2833,7 +2833,7 @@ pack128_fast (const uint32_t lane[4], const SmolJobDesc &d, const SmolDeviceLuts
 
 template <int MODE, int BI>
 __global__ void __launch_bounds__ (1024, 1)
-smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u32_ok)
+smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u32_ok, uint32_t rows_per_item)
 {
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
     constexpr bool NEED_INV = MODE == BM_P8L_P;
@@ -2871,20 +2871,23 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
     /* Persistent CTAs: the 64 KB of lane-replicated tables are filled once per CTA and then serve
      * every work item its warps walk over (item = 32 adjacent output pixels of one row; the host
      * picks the warp count that wastes least of the last round, as for the box kernel). */
-    const uint32_t items_x = (d.w_out + 31) / 32, items_per_image = items_x * P.n_rows;
+    /* an item is rows_per_item consecutive output rows of 32 columns: without halvings the
+     * two-row cache then carries half of every output row's work over from the row above */
+    const uint32_t items_x = (d.w_out + 31) / 32, strips = (P.n_rows + rows_per_item - 1) / rows_per_item;
+    const uint32_t items_per_image = items_x * strips;
     const uint32_t n_items = items_per_image * P.n_images;
     const uint32_t warps = nthr >> 5;
     for (uint32_t item = blockIdx.x * warps + (tid >> 5); item < n_items; item += gridDim.x * warps)
     {
     const uint32_t tz = item / items_per_image, trem = item - tz * items_per_image;
-    const uint32_t yl = trem / items_x;
-    const uint32_t x = (trem - yl * items_x) * 32 + (tid & 31);
+    const uint32_t strip = trem / items_x;
+    const uint32_t yl0 = strip * rows_per_item, yl1 = min (yl0 + rows_per_item, P.n_rows);
+    const uint32_t x = (trem - strip * items_x) * 32 + (tid & 31);
     if (x >= d.w_out)
         continue;
 
     const uint32_t n_h = 1u << hh, n_v = 1u << vh;
     const uint32_t *tx = P.tab_x + (x << hh);
-    const uint32_t *ty = P.tab_y + ((P.first_row + yl) << vh);
     const uint8_t *src = P.src + (size_t) tz * P.src_image_stride;
 
     auto fetch = [&] (const uint8_t *row, uint32_t j) -> BoxPx<MODE>
@@ -2933,9 +2936,17 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
     };
 
     uint32_t idx0 = 0xffffffffu, idx1 = 0xffffffffu;
-    BoxPx<MODE> c0, c1, acc;
+    BoxPx<MODE> c0, c1;
 #pragma unroll
-    for (int i = 0; i < 4; i++) c0.v[i] = c1.v[i] = acc.v[i] = 0;
+    for (int i = 0; i < 4; i++) c0.v[i] = c1.v[i] = 0;
+
+#pragma unroll 1
+    for (uint32_t yl = yl0; yl < yl1; yl++)
+    {
+    const uint32_t *ty = P.tab_y + ((P.first_row + yl) << vh);
+    BoxPx<MODE> acc;
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc.v[i] = 0;
 
 #pragma unroll 1
     for (uint32_t kv = 0; kv < n_v; kv++)
@@ -2971,6 +2982,7 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
     const uint32_t packed = pack128_fast<MODE> (fin, d, P.luts, sm_to_srgb);
     uint8_t *o8 = P.dst + (size_t) tz * P.dst_image_stride + (size_t) yl * P.dst_pitch + (size_t) x * d.bpp_out;
     store_raw_px (o8, packed, d.bpp_out);
+    }
     }
 }
 
@@ -3183,10 +3195,22 @@ taps128_eligible (const SmolLaunch &L)
     const SmolJobDesc &d = L.d;
 
     /* one thread per output pixel pays off when outputs are few and taps many (a halving on
-     * either axis, i.e. more than 2:1); near 1:1 and on upscales the general kernel's per-column
-     * row cache avoids recomputing the costly unpack chain */
-    return d.h_kind == SMOL_AXIS_TAPS && d.v_kind == SMOL_AXIS_TAPS && d.storage128
-           && d.mid != SMOL_MID_P8 && (d.h_halvings > 0 || d.v_halvings > 0);
+     * either axis, i.e. more than 2:1); SMOL_TAPS128_ALL=1 (measurements) takes every 128bpp
+     * bilinear job */
+    static int all = -1;
+    if (all < 0)
+    {
+        const char *e = getenv ("SMOL_TAPS128_ALL");
+        all = e ? atoi (e) : 0;
+    }
+    if (d.h_kind != SMOL_AXIS_TAPS || d.v_kind != SMOL_AXIS_TAPS || !d.storage128 || d.mid == SMOL_MID_P8)
+        return false;
+    if (all || d.h_halvings > 0 || d.v_halvings > 0)
+        return true;
+    /* Without halvings: a strip of rows per thread column with the two-row cache beats the tile
+     * kernel up to mild magnifications (4K, us per frame, taps128 / tile128: 1:1 82 / 113, 1.5:1
+     * down 48 / 79, 2x up 66 / 42), so the tile kernel keeps the upscales beyond 1.5x in area. */
+    return (uint64_t) d.w_out * d.h_out * 2 <= (uint64_t) d.w_in * d.h_in * 3;
 }
 
 static bool
@@ -4215,7 +4239,16 @@ launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
     /* Persistent CTAs: warps walk work items of 32 output pixels.  The warp count per CTA
      * (20..32) is the one that wastes least of the last round of items, given how many CTAs of
      * that size are resident per SM (registers and the up to 64 KB of tables decide). */
-    const uint64_t n_items = (uint64_t) ((d.w_out + 31) / 32) * L.n_rows * L.n_images;
+    static int tune_rpi = -1;
+    if (tune_rpi < 0)
+    {
+        const char *e = getenv ("SMOL_TAPS128_RPI");
+        tune_rpi = e ? atoi (e) : 0;
+    }
+    /* rows per item: with halvings the row cache rarely carries over (one row); without, strips */
+    const uint32_t rpi = tune_rpi > 0 ? (uint32_t) tune_rpi
+                         : (hh == 0 && vh == 0 ? ((uint64_t) d.h_in * 4 < (uint64_t) d.h_out * 5 ? 8u : 4u) : 1u);
+    const uint64_t n_items = (uint64_t) ((d.w_out + 31) / 32) * ((L.n_rows + rpi - 1) / rpi) * L.n_images;
     if (n_items > 0x7fffffffull)
         return cudaErrorInvalidValue;
 
@@ -4259,7 +4292,7 @@ launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
     const uint64_t ctas = (n_items + best_w - 1) / best_w, resident = (uint64_t) num_sms () * best_occ;
     dim3 block (best_w * 32), grid ((unsigned) (ctas < resident ? ctas : resident));
 
-#define T128(M, B) launch_pdl_args (smol_taps128_kernel<M, B>, grid, block, bytes, stream, P, hh, vh, src_u32_ok)
+#define T128(M, B) launch_pdl_args (smol_taps128_kernel<M, B>, grid, block, bytes, stream, P, hh, vh, src_u32_ok, rpi)
     switch (variant)
     {
         case 0:  return T128 (BM_P8L_U, 4);
