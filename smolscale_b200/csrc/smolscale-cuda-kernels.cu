@@ -3878,11 +3878,14 @@ launch_magb (const SmolLaunch &L, cudaStream_t stream)
 
     taps_params_init (M.t, L);
     static int tune_tb = -1, tune_th = -1;
+    static uint32_t magb_reg_ctas = 8;
     if (tune_tb < 0)
     {
-        const char *a = getenv ("SMOL_MAGB_TB"), *b = getenv ("SMOL_MAGB_TH");
+        const char *a = getenv ("SMOL_MAGB_TB"), *b = getenv ("SMOL_MAGB_TH"), *c = getenv ("SMOL_MAGB_CTAS");
         tune_tb = a ? atoi (a) : 0;
         tune_th = b ? atoi (b) : 0;
+        if (c && atoi (c) > 0)
+            magb_reg_ctas = (uint32_t) atoi (c);
     }
     M.nb_row = d.w_out * d.bpp_out;
     const bool src32 = (reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
@@ -3935,8 +3938,10 @@ launch_magb (const SmolLaunch &L, cudaStream_t stream)
                     continue;
                 if (!shape (c, h, sm) || sm > 100 * 1024)
                     continue;
+                /* (finer tile heights and the register-limited residency of 6 were tried in this
+                 * estimate: no better on cfg 4, worse at 2x and 8x) */
                 uint32_t per_sm = (uint32_t) ((220 * 1024) / (sm + 3 * 1024));
-                per_sm = per_sm > 8 ? 8 : per_sm;
+                per_sm = per_sm > magb_reg_ctas ? magb_reg_ctas : per_sm;
                 if (per_sm < 2)
                     continue;
                 const double ctas = (double) ((M.nb_row + M.tile_b - 1) / M.tile_b) * ((L.n_rows + h - 1) / h) * L.n_images;
