@@ -635,11 +635,13 @@ __device__ __forceinline__ uint2 lds_u64 (uint32_t addr)
     asm ("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
-/* staging-buffer read: ordered against the cp.async / __syncwarp around it */
+/* staging-buffer read: volatile, so it keeps its place among the cp.async waits and warp barriers
+ * around it (all volatile asm); no "memory" clobber, which would make the compiler re-read kernel
+ * parameters (the PRMT selectors) after every pixel */
 __device__ __forceinline__ uint32_t lds_u32_ordered (uint32_t addr)
 {
     uint32_t v;
-    asm volatile ("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    asm volatile ("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 
