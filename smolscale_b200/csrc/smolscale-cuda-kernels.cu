@@ -2301,11 +2301,16 @@ __device__ __forceinline__ uint32_t prmt_raw (uint32_t a, uint32_t b, uint32_t s
     return d;
 }
 
-template <int MODE, bool WEIGHTED>
+/* OPAQUE (24bpp sources: alpha is 255 everywhere): unpremultiplying by 255 is the identity
+ * ((c * (inv_div_p8[255] << 3)) >> 16 == c for every byte c), so the whole chain is a function of
+ * the colour byte alone and the "from" table holds ((from_srgb[c] + 1) * 2041 - 1) >> 11 directly:
+ * PRMT, LDS, add per channel. */
+template <int MODE, bool WEIGHTED, bool OPAQUE = false>
 __device__ __forceinline__ void
 box3_accum (uint32_t raw, uint32_t w, uint32_t acc[4], const BoxParams &P, uint32_t from_y, uint32_t inv_y)
 {
     static_assert (MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U, "linear-light modes only");
+    static_assert (!OPAQUE || MODE == BM_P8L_P, "opaque shortcut: premultiplied linear-light unpack");
     auto add = [&] (uint32_t &a, uint32_t v, int shift)
     {
         if constexpr (WEIGHTED)
@@ -2314,7 +2319,14 @@ box3_accum (uint32_t raw, uint32_t w, uint32_t acc[4], const BoxParams &P, uint3
             a += v >> shift;
     };
 
-    if constexpr (MODE == BM_P8L_P)
+    if constexpr (OPAQUE)
+    {
+        add (acc[0], 255u, 0);
+        add (acc[1], lds_u32 (prmt_raw (raw, from_y, P.sel_f0)), 0);
+        add (acc[2], lds_u32 (prmt_raw (raw, from_y, P.sel_f1)), 0);
+        add (acc[3], lds_u32 (prmt_raw (raw, from_y, P.sel_f2)), 0);
+    }
+    else if constexpr (MODE == BM_P8L_P)
     {
         const uint2 im = lds_u64 (prmt_raw (raw, inv_y, P.sel_aaddr));
         const uint32_t c[3] = { prmt_raw (raw, 0, P.sel_c0), prmt_raw (raw, 0, P.sel_c1), prmt_raw (raw, 0, P.sel_c2) };
@@ -2361,7 +2373,8 @@ smol_box_kernel (const BoxParams P)
     __shared__ uint32_t sm_from_plain[LUTM == 0 ? 256 : 1];
     constexpr bool S128 = MODE >= BM_P8L_P;
     constexpr bool TAB = LUTM == 1;
-    constexpr bool NEED_INV = MODE == BM_P8L_P;
+    constexpr bool OPAQUE = LUTM == 3 && BI == 3 && MODE == BM_P8L_P;   /* see box3_accum */
+    constexpr bool NEED_INV = MODE == BM_P8L_P && !OPAQUE;
     constexpr bool NEED_FROM = MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U;
     constexpr uint32_t REP_BYTES = LUTM == 2 ? ((NEED_INV ? 32768u : 0u) + (NEED_FROM ? 32768u : 0u)) : 0u;
     constexpr uint32_t TAB_BYTES = TAB ? 65536 * 2 : REP_BYTES;
@@ -2411,7 +2424,8 @@ smol_box_kernel (const BoxParams P)
         for (uint32_t i = threadIdx.x; i < 8192; i += blockDim.x)
         {
             const uint32_t e = i >> 5, l = i & 31;
-            t_from[e * 64 + l] = (uint32_t) P.luts->from_srgb[e] + (MODE == BM_P16L_U ? 0u : 1u);
+            const uint32_t lin = P.luts->from_srgb[e];
+            t_from[e * 64 + l] = OPAQUE ? ((lin + 1) * 2041u - 1) >> 11 : lin + (MODE == BM_P16L_U ? 0u : 1u);
             if constexpr (NEED_INV)
                 t_inv[e * 32 + l] = make_uint2 (P.luts->inv_div_p8[e] << 3, e * 8 + 1);
         }
@@ -2603,14 +2617,14 @@ smol_box_kernel (const BoxParams P)
                 auto accum = [&] (uint32_t raw)
                 {
                     if constexpr (NEED_FROM)
-                        box3_accum<MODE, false> (raw, 0, acc.v, P, from_y, inv_y);
+                        box3_accum<MODE, false, OPAQUE> (raw, 0, acc.v, P, from_y, inv_y);
                     else
                         box_add<MODE> (acc, box_unpack<MODE, 0> (raw, P, nullptr, nullptr, nullptr));
                 };
                 auto accum_w = [&] (uint32_t raw, uint32_t w)
                 {
                     if constexpr (NEED_FROM)
-                        box3_accum<MODE, true> (raw, w, acc.v, P, from_y, inv_y);
+                        box3_accum<MODE, true, OPAQUE> (raw, w, acc.v, P, from_y, inv_y);
                     else
                         box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE, 0> (raw, P, nullptr, nullptr, nullptr), w));
                 };
@@ -2838,7 +2852,8 @@ __global__ void __launch_bounds__ (1024, 1)
 smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u32_ok, uint32_t rows_per_item)
 {
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
-    constexpr bool NEED_INV = MODE == BM_P8L_P;
+    constexpr bool OPAQUE = BI == 3 && MODE == BM_P8L_P;       /* see box3_accum */
+    constexpr bool NEED_INV = MODE == BM_P8L_P && !OPAQUE;
     constexpr bool NEED_FROM = MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U;
     const SmolJobDesc &d = P.d;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
@@ -2855,7 +2870,8 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
         for (uint32_t i = tid; i < 8192; i += nthr)
         {
             const uint32_t e = i >> 5, l = i & 31;
-            t_from[e * 64 + l] = (uint32_t) P.luts->from_srgb[e] + (MODE == BM_P16L_U ? 0u : 1u);
+            const uint32_t lin = P.luts->from_srgb[e];
+            t_from[e * 64 + l] = OPAQUE ? ((lin + 1) * 2041u - 1) >> 11 : lin + (MODE == BM_P16L_U ? 0u : 1u);
             if constexpr (NEED_INV)
                 t_inv[e * 32 + l] = make_uint2 (P.luts->inv_div_p8[e] << 3, e * 8 + 1);
         }
@@ -2908,7 +2924,7 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
             BoxPx<MODE> r;
 #pragma unroll
             for (int i = 0; i < 4; i++) r.v[i] = 0;
-            box3_accum<MODE, false> (raw, 0, r.v, P, from_y, inv_y);
+            box3_accum<MODE, false, OPAQUE> (raw, 0, r.v, P, from_y, inv_y);
             return r;
         }
         else
@@ -4100,7 +4116,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
             glog0 = (uint32_t) tune_g;
         const uint64_t seg_px0 = ((uint64_t) (32u >> glog0) * d.w_in + d.w_out - 1) / d.w_out + 3;
         const size_t per_warp0 = 2 * (size_t) ((seg_px0 * d.bpp_in + 32 + 15) & ~(uint64_t) 15);
-        const size_t win_hi0 = mode == BM_P8L_P ? 0x30000 : 0x20000;
+        const size_t win_hi0 = mode == BM_P8L_P && d.bpp_in != 3 ? 0x30000 : 0x20000;    /* 24bpp: no inverse table (box3_accum) */
         if ((0x10000 - 0x480) / per_warp0 + (225 * 1024 - 64 - (win_hi0 - 0x400)) / per_warp0 < 8)
             lutm = 2;
     }
@@ -4134,7 +4150,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         glog++;
 
     const size_t lut_bytes = lutm == 1 ? 131072
-                             : lutm == 3 ? (mode == BM_P8L_P ? 131072 : has_lut ? 65536 : 0)
+                             : lutm == 3 ? (mode == BM_P8L_P && d.bpp_in != 3 ? 131072 : has_lut ? 65536 : 0)
                              : lutm == 2 ? (mode == BM_P8L_P ? 65536 : 32768) : 0;
     size_t smem = 0;
     uint32_t per_sm = 1, warps_per_cta = lutm == 2 ? 16 : 8;
@@ -4265,7 +4281,7 @@ launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
     /* dynamic shared memory: up to the end of the tables' fixed window addresses (see box3_accum) */
     const size_t one_tab = 0x20000 - 0x400, two_tabs = 0x30000 - 0x400;
     if (d.mid == SMOL_MID_P8L && d.in_unassoc)      { variant = 0; fn = (const void *) smol_taps128_kernel<BM_P8L_U, 4>; bytes = one_tab; }
-    else if (d.mid == SMOL_MID_P8L && d.bpp_in == 3) { variant = 1; fn = (const void *) smol_taps128_kernel<BM_P8L_P, 3>; bytes = two_tabs; }
+    else if (d.mid == SMOL_MID_P8L && d.bpp_in == 3) { variant = 1; fn = (const void *) smol_taps128_kernel<BM_P8L_P, 3>; bytes = one_tab; }
     else if (d.mid == SMOL_MID_P8L)                 { variant = 2; fn = (const void *) smol_taps128_kernel<BM_P8L_P, 4>; bytes = two_tabs; }
     else if (d.mid == SMOL_MID_P16)                 { variant = 3; fn = (const void *) smol_taps128_kernel<BM_P16_U, 4>; bytes = 0; }
     else                                            { variant = 4; fn = (const void *) smol_taps128_kernel<BM_P16L_U, 4>; bytes = one_tab; }
