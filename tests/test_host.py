@@ -144,3 +144,31 @@ def test_band_source_rows(sb):
         if p["filter_v"] in (2, 3) and hi > ho:
             assert covered_lo == 0
         ctx.destroy()
+
+
+def test_dispatch_table():
+    """The dispatcher's choice of kernel family for representative jobs (pure host logic, best-case
+    alignment): the five BASELINE configurations and the measured crossovers documented in
+    smol_cuda_pick_kernel / DESIGN.md section 5."""
+    import smolscale_b200 as sb
+    c = cases
+    expect = [
+        ("half2x", c.RGBA8_P, 1920, 1080, c.RGBA8_P, 960, 540, 0),          # cfg 1: exact 2:1
+        ("half2x", c.BGRA8_P, 3840, 2160, c.BGRA8_U, 1920, 1080, 0),        # cfg 2: exact 2:1 + unpremultiply
+        ("box", c.RGBA8_P, 7680, 4320, c.RGBA8_P, 800, 450, 1),             # cfg 3: box x box, linear light
+        ("magb", c.RGB8, 1024, 768, c.RGB8, 4096, 3072, 0),                 # cfg 4: 24bpp -> 24bpp, 4x up
+        ("half2x", c.ARGB8_P, 2048, 2048, c.ARGB8_P, 256, 256, 0),          # cfg 5: exact 8:1
+        ("taps_direct", c.RGBA8_P, 1920, 1080, c.RGBA8_P, 3840, 2160, 0),   # 32bpp upscale: register kernel
+        ("taps_direct", c.RGB8, 2560, 1440, c.RGB8, 3840, 2160, 0),         # 24bpp below 2x: register kernel
+        ("taps_direct", c.RGBA8_P, 3840, 2160, c.BGRA8_U, 3839, 2159, 0),   # the reference's conv shape
+        ("taps_direct", c.RGBA8_P, 3840, 2160, c.RGBA8_P, 1280, 720, 0),    # 3:1, one halving
+        ("taps128", c.RGBA8_P, 3840, 2160, c.RGBA8_P, 1280, 720, 1),        # ... in linear light
+        ("taps128", c.RGBA8_U, 3840, 2160, c.RGBA8_U, 3839, 2159, 0),       # unassociated -> unassociated, ~1:1
+        ("tile128", c.RGBA8_U, 1920, 1080, c.RGBA8_U, 3840, 2160, 0),       # ... upscale
+        ("box", c.RGB8, 7680, 4320, c.RGB8, 800, 450, 0),                   # box without linear light
+        ("general", c.RGBA8_P, 3000, 7, c.RGBA8_P, 11, 7, 0),               # box on one axis only
+        ("general", c.RGBA8_P, 9000, 1, c.RGBA8_P, 1, 1, 0),                # > 255:1 without linear light
+    ]
+    for want, ti, wi, hi, to, wo, ho, srgb in expect:
+        got = sb.plan_query(ti, wi, hi, to, wo, ho, srgb)["kernel_name"]
+        assert got == want, ((ti, wi, hi, to, wo, ho, srgb), got, want)
