@@ -2650,10 +2650,22 @@ smol_box_kernel (const BoxParams P)
                         for (; a < a_end; a += 4 * G)
                             accum (lds_u32_ordered (a));
                     }
-                    if (g == 0)
-                        accum_w (lds_u32_ordered (row + o_left), wl);
-                    if (g == G - 1 && wr > 0)
-                        accum_w (lds_u32_ordered (row + o_end), wr);
+                    if (G == 1)
+                    {
+                        /* both edge pixels at once: two independent unpack chains in flight, no
+                         * divergent branch (a right edge of weight 0 reads a staged byte that may
+                         * lie past the row's end and contributes nothing) */
+                        const uint32_t raw_l = lds_u32_ordered (row + o_left), raw_r = lds_u32_ordered (row + o_end);
+                        accum_w (raw_l, wl);
+                        accum_w (raw_r, wr);
+                    }
+                    else
+                    {
+                        if (g == 0)
+                            accum_w (lds_u32_ordered (row + o_left), wl);
+                        if (g == G - 1 && wr > 0)
+                            accum_w (lds_u32_ordered (row + o_end), wr);
+                    }
                 }
                 else
                 {
