@@ -20,7 +20,8 @@ __all__ = ["PixelType", "ScaleCtx", "scale_simple", "scale_images", "lib", "plan
            "device_count", "set_stream", "set_device", "synchronize", "stats", "reset_stats",
            "force_kernel", "kernel_launches", "bytes_per_pixel", "LIB_PATH"]
 
-LIB_PATH = _build.LIB_PATH
+# SMOLSCALE_B200_LIB: load another build of the library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("SMOLSCALE_B200_LIB") or _build.LIB_PATH
 
 
 class PixelType(enum.IntEnum):

@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
         [cc, "-O2", "-g", "-Wall", "-Wextra", "-fPIC", "-fvisibility=hidden", "-pthread",
          "-I", INCLUDE, "-I", CSRC, "-I", os.path.join(cuda, "include"),
          "-c", os.path.join(CSRC, "smolscale-cuda.c"), "-o", obj_c],
-        [nvcc, "-std=c++17", "-O3", "-lineinfo"] + NVCC_ARCH +
+        [nvcc, "-std=c++17", "-O3", "-lineinfo"] + NVCC_ARCH + os.environ.get("SMOL_NVCC_FLAGS", "").split() +
         ["-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v" if verbose else "-warn-spills",
          "-I", INCLUDE, "-I", CSRC,
          "-c", os.path.join(CSRC, "smolscale-cuda-kernels.cu"), "-o", obj_cu],

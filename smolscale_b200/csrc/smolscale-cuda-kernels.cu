@@ -2288,6 +2288,10 @@ template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_scale (const BoxP
  * which is PRMT (c), IMAD, PRMT (address), LDS, IMAD, LEA.HI (accumulate) here.
  * WEIGHTED: the pixel is an edge of the span, each lane is scaled by w / 256 first (generic:1177-1192).
  * from_y / inv_y: this lane's table addresses for index 0. */
+/* most warps per CTA of the lean box kernel (one CTA per SM): fewer warps, more registers each */
+#ifndef SMOL_BOX3_MAX_WARPS
+#define SMOL_BOX3_MAX_WARPS 32
+#endif
 #define SMOL_BOX3_FROM_WIN 0x10000u
 
 #define SMOL_BOX3_INV_WIN  0x20000u
@@ -2365,7 +2369,7 @@ box3_accum (uint32_t raw, uint32_t w, uint32_t acc[4], const BoxParams &P, uint3
  * LUTM = 2: 512-thread CTAs with lane-replicated LUTs; LUTM = 0: 256-thread CTAs, plain LUTs;
  * LUTM = 3: one big CTA per SM, byte-addressed lane-replicated LUTs (see box3_accum). */
 template <int MODE, int LUTM, int BI>
-__global__ void __launch_bounds__ (LUTM == 1 || LUTM == 3 ? 1024 : LUTM == 2 ? 512 : 256, LUTM == 1 || LUTM == 3 ? 1 : LUTM == 2 ? 2 : 5)
+__global__ void __launch_bounds__ (LUTM == 3 ? SMOL_BOX3_MAX_WARPS * 32 : LUTM == 1 ? 1024 : LUTM == 2 ? 512 : 256, LUTM == 1 || LUTM == 3 ? 1 : LUTM == 2 ? 2 : 5)
 smol_box_kernel (const BoxParams P)
 {
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
@@ -4195,8 +4199,8 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
             /* without tables the buffers are simply contiguous ("lo" = all of them) */
             const size_t lo_room = has_lut ? 0x10000 - 0x480 : dyn_max, hi_room = has_lut ? dyn_max - (win_hi - 0x400) : 0;
             uint32_t lo = (uint32_t) (lo_room / per_warp), hi = (uint32_t) (hi_room / per_warp);
-            lo = lo > 32 ? 32 : lo;
-            hi = hi > 32 - lo ? 32 - lo : hi;
+            lo = lo > SMOL_BOX3_MAX_WARPS ? SMOL_BOX3_MAX_WARPS : lo;
+            hi = hi > SMOL_BOX3_MAX_WARPS - lo ? SMOL_BOX3_MAX_WARPS - lo : hi;
             /* Every work item costs the same and a warp takes ceil (items / warps) of them, so
              * the kernel's length is quantised: among the warp counts that fit (down to 5/8 of
              * the most) take the one that wastes the smallest share of its last round. */
