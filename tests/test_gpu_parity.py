@@ -365,14 +365,15 @@ def test_solid_colours(sb, restatement):
                     assert (out.reshape(-1, 4) == np.array([a, r, g, b], np.uint8)).all(), (a, r, g, b, wi, wo)
 
 
-def test_solid_colour_sweep(sb):
+def test_solid_colour_sweep(sb, restatement):
     """the reference's `check` mode (test.c:1128-1298) restated for the GPU path: solid
     colours, every Nth width 1..65535 -> 1 and 65535 -> every Nth width, horizontally and vertically
     (SMOL_SWEEP_STEP=1 for the exhaustive sweep; default stride keeps the run to seconds).  The
     reference's own bar is "output == the colour"; at exact integer box ratios the reference itself
     loses the last pixel, so the exact bar is applied where it holds (non-box ratios
-    and non-integer box ratios) and every result is additionally cross-checked between the H and V
-    directions, which must agree for a solid colour."""
+    and non-integer box ratios; where the tail clamp bites at a non-integer ratio too, the oracle
+    decides and only the last pixel may deviate) and every result is additionally cross-checked
+    between the H and V directions, which must agree for a solid colour."""
     step = int(os.environ.get("SMOL_SWEEP_STEP", "611"))
     colours = [(0xff, 0xff, 0xff, 0xff), (0x80, 0x40, 0x20, 0x10), (0x01, 0x00, 0x01, 0x00)]
     for col in colours:
@@ -384,8 +385,14 @@ def test_solid_colour_sweep(sb):
                 v = cuda_scale(sb, src, cases.ARGB8_P, 1, n_in, 4, cases.ARGB8_P, 1, n_out, 4, 0)
                 assert np.array_equal(h, v), (col, n_in, n_out)
                 is_box = n_in > 8 * n_out
-                if not is_box or n_in % n_out != 0:
-                    assert (h.reshape(-1, 4) == c).all(), (col, n_in, n_out)
+                if (not is_box or n_in % n_out != 0) and not (h.reshape(-1, 4) == c).all():
+                    # the reference's box tail clamp also bites at a few non-integer ratios
+                    # (65535 -> 8160 loses the last pixel): the oracle is the judge there, and
+                    # only the last output pixel may differ from the colour
+                    assert is_box, (col, n_in, n_out)
+                    want = restatement.scale_simple(src, cases.ARGB8_P, n_in, 1, n_in * 4, cases.ARGB8_P, n_out, 1, n_out * 4, 0)
+                    assert np.array_equal(h, want), (col, n_in, n_out)
+                    assert (h.reshape(-1, 4)[:-1] == c).all(), (col, n_in, n_out)
 
 
 def test_baseline_config_properties(sb, restatement):
