@@ -3706,6 +3706,11 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
                                                && (L.dst_image_stride & 3) == 0);
         if (T.src_u32_ok && dst_ok)
         {
+            /* one output pixel per thread reads its (ratio + 1)^2 source pixels through dependent
+             * table lookups: prefetching the rows into L2 on entry pays in every CTA, not only in
+             * the first wave (measured: 4K -> 720p 14.1 -> 13.4 us) */
+            if (T.prefetch)
+                T.prefetch = 0xffffffffu;
             uint32_t nbx = 32;
             while (nbx < 128 && nbx < d.w_out)
                 nbx *= 2;
