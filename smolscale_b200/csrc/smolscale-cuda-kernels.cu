@@ -2309,10 +2309,21 @@ __device__ __forceinline__ uint32_t prmt_raw (uint32_t a, uint32_t b, uint32_t s
  * ((c * (inv_div_p8[255] << 3)) >> 16 == c for every byte c), so the whole chain is a function of
  * the colour byte alone and the "from" table holds ((from_srgb[c] + 1) * 2041 - 1) >> 11 directly:
  * PRMT, LDS, add per channel. */
-template <int MODE, bool WEIGHTED, bool OPAQUE = false>
+/* AP: where alpha sits in a 32bpp source pixel, known at compile time so that the PRMT selectors
+ * are immediates (0: read them from the parameters; 1: last byte, colours in bytes 0..2; 2: first
+ * byte, colours in bytes 1..3). */
+template <int MODE, bool WEIGHTED, bool OPAQUE = false, int AP = 0>
 __device__ __forceinline__ void
 box3_accum (uint32_t raw, uint32_t w, uint32_t acc[4], const BoxParams &P, uint32_t from_y, uint32_t inv_y)
 {
+    const uint32_t sel_aaddr = AP == 1 ? 0x7634u : AP == 2 ? 0x7604u : P.sel_aaddr;
+    const uint32_t sel_alpha = AP == 1 ? 0x4443u : AP == 2 ? 0x4440u : P.sel_alpha;
+    const uint32_t sel_c0 = AP == 1 ? 0x4440u : AP == 2 ? 0x4441u : P.sel_c0;
+    const uint32_t sel_c1 = AP == 1 ? 0x4441u : AP == 2 ? 0x4442u : P.sel_c1;
+    const uint32_t sel_c2 = AP == 1 ? 0x4442u : AP == 2 ? 0x4443u : P.sel_c2;
+    const uint32_t sel_f0 = AP == 1 ? 0x7604u : AP == 2 ? 0x7614u : P.sel_f0;
+    const uint32_t sel_f1 = AP == 1 ? 0x7614u : AP == 2 ? 0x7624u : P.sel_f1;
+    const uint32_t sel_f2 = AP == 1 ? 0x7624u : AP == 2 ? 0x7634u : P.sel_f2;
     static_assert (MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U, "linear-light modes only");
     static_assert (!OPAQUE || MODE == BM_P8L_P, "opaque shortcut: premultiplied linear-light unpack");
     auto add = [&] (uint32_t &a, uint32_t v, int shift)
@@ -2326,14 +2337,14 @@ box3_accum (uint32_t raw, uint32_t w, uint32_t acc[4], const BoxParams &P, uint3
     if constexpr (OPAQUE)
     {
         add (acc[0], 255u, 0);
-        add (acc[1], lds_u32 (prmt_raw (raw, from_y, P.sel_f0)), 0);
-        add (acc[2], lds_u32 (prmt_raw (raw, from_y, P.sel_f1)), 0);
-        add (acc[3], lds_u32 (prmt_raw (raw, from_y, P.sel_f2)), 0);
+        add (acc[1], lds_u32 (prmt_raw (raw, from_y, sel_f0)), 0);
+        add (acc[2], lds_u32 (prmt_raw (raw, from_y, sel_f1)), 0);
+        add (acc[3], lds_u32 (prmt_raw (raw, from_y, sel_f2)), 0);
     }
     else if constexpr (MODE == BM_P8L_P)
     {
-        const uint2 im = lds_u64 (prmt_raw (raw, inv_y, P.sel_aaddr));
-        const uint32_t c[3] = { prmt_raw (raw, 0, P.sel_c0), prmt_raw (raw, 0, P.sel_c1), prmt_raw (raw, 0, P.sel_c2) };
+        const uint2 im = lds_u64 (prmt_raw (raw, inv_y, sel_aaddr));
+        const uint32_t c[3] = { prmt_raw (raw, 0, sel_c0), prmt_raw (raw, 0, sel_c1), prmt_raw (raw, 0, sel_c2) };
         add (acc[0], im.y, 3);                                      /* alpha = (8 a + 1) >> 3 */
 #pragma unroll
         for (int i = 0; i < 3; i++)
@@ -2344,9 +2355,9 @@ box3_accum (uint32_t raw, uint32_t w, uint32_t acc[4], const BoxParams &P, uint3
     }
     else
     {
-        const uint32_t alpha = prmt_raw (raw, 0, P.sel_alpha);
-        const uint32_t lin[3] = { lds_u32 (prmt_raw (raw, from_y, P.sel_f0)), lds_u32 (prmt_raw (raw, from_y, P.sel_f1)),
-                                  lds_u32 (prmt_raw (raw, from_y, P.sel_f2)) };
+        const uint32_t alpha = prmt_raw (raw, 0, sel_alpha);
+        const uint32_t lin[3] = { lds_u32 (prmt_raw (raw, from_y, sel_f0)), lds_u32 (prmt_raw (raw, from_y, sel_f1)),
+                                  lds_u32 (prmt_raw (raw, from_y, sel_f2)) };
         if constexpr (MODE == BM_P8L_U)
         {
             const uint32_t m = alpha * 8 + 1;
@@ -2617,18 +2628,24 @@ smol_box_kernel (const BoxParams P)
                 BoxPx<MODE> acc;
 #pragma unroll
                 for (int i = 0; i < (S128 ? 4 : 2); i++) acc.v[i] = 0;
+                /* The row's pixel walk, instantiated per alpha position for the 32bpp table modes
+                 * (immediate PRMT selectors; one uniform branch per row picks the instance). */
+                auto walk_row = [&] (auto ap_tag)
+                {
+                constexpr int AP = decltype (ap_tag)::value;
+                (void) AP;
                 /* unpack one pixel into the accumulators, table modes through box3_accum */
                 auto accum = [&] (uint32_t raw)
                 {
                     if constexpr (NEED_FROM)
-                        box3_accum<MODE, false, OPAQUE> (raw, 0, acc.v, P, from_y, inv_y);
+                        box3_accum<MODE, false, OPAQUE, AP> (raw, 0, acc.v, P, from_y, inv_y);
                     else
                         box_add<MODE> (acc, box_unpack<MODE, 0> (raw, P, nullptr, nullptr, nullptr));
                 };
                 auto accum_w = [&] (uint32_t raw, uint32_t w)
                 {
                     if constexpr (NEED_FROM)
-                        box3_accum<MODE, true, OPAQUE> (raw, w, acc.v, P, from_y, inv_y);
+                        box3_accum<MODE, true, OPAQUE, AP> (raw, w, acc.v, P, from_y, inv_y);
                     else
                         box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE, 0> (raw, P, nullptr, nullptr, nullptr), w));
                 };
@@ -2680,6 +2697,16 @@ smol_box_kernel (const BoxParams P)
                     if (g == G - 1 && wr > 0)
                         accum_w (fetch3 (hR), wr);
                 }
+                };
+                if constexpr (NEED_FROM && BI == 4)
+                {
+                    if (P.alpha_shift == 0)
+                        walk_row (std::integral_constant<int, 2> {});
+                    else
+                        walk_row (std::integral_constant<int, 1> {});
+                }
+                else
+                    walk_row (std::integral_constant<int, 0> {});
                 for (uint32_t m = G >> 1; m; m >>= 1)
                 {
 #pragma unroll
