@@ -26,8 +26,21 @@ int smol_cuda_device_count (void);
 void smol_cuda_set_device (int device);
 
 /* Stream (a cudaStream_t passed as void *) on which the calling thread's device-memory calls are
- * enqueued.  NULL = legacy default stream.  Thread-local. */
+ * enqueued.  NULL = legacy default stream.  Thread-local.  It must belong to the device that owns
+ * the buffers.  Calls with device memory on both sides return as soon as the kernel is enqueued;
+ * calls that mix a device buffer with a host buffer run their kernel on this stream too (so they
+ * are ordered after whatever produced the device buffer) and return when the result is complete.
+ * The first call for a new geometry uploads its filter tables outside any ongoing stream capture;
+ * the kernel launch itself is capturable (CUDA graphs). */
 void smol_cuda_set_stream (void *cuda_stream);
+
+/* How many GPUs ONE host-memory call may be spread over (default 1; 0 = every visible device;
+ * environment: SMOL_CUDA_MULTI_GPU=N|all).  With N > 1, smol_scale_simple / smol_scale_batch* on
+ * host buffers split their output rows into N bands; each device uploads only the source rows its
+ * band reads (band + filter halo) over its own PCIe link, scales them and writes its rows back.
+ * Results are bit-identical to the single-device path (disjoint row batches are independent in
+ * the reference too, smolscale.h:70-74).  Calls on device memory are unaffected.  Process-wide. */
+void smol_cuda_set_multi_gpu (int n_devices);
 
 /* Waits for all work this library has enqueued from the calling thread's stream. */
 void smol_cuda_synchronize (void);

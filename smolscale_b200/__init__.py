@@ -17,7 +17,7 @@ import os
 from . import _build
 
 __all__ = ["PixelType", "ScaleCtx", "scale_simple", "scale_images", "lib", "plan_query",
-           "device_count", "set_stream", "set_device", "synchronize", "stats", "reset_stats",
+           "device_count", "set_stream", "set_device", "synchronize", "set_multi_gpu", "stats", "reset_stats",
            "force_kernel", "kernel_launches", "bytes_per_pixel", "LIB_PATH"]
 
 # SMOLSCALE_B200_LIB: load another build of the library (A/B measurements of compile-time variants)
@@ -68,6 +68,7 @@ EXPORTED_SYMBOLS = [
     "smol_scale_simple", "smol_scale_new", "smol_scale_new_full", "smol_scale_destroy",
     "smol_scale_batch", "smol_scale_batch_full",
     "smol_cuda_device_count", "smol_cuda_set_device", "smol_cuda_set_stream", "smol_cuda_synchronize",
+    "smol_cuda_set_multi_gpu",
     "smol_cuda_scale_images", "smol_cuda_plan_query", "smol_cuda_band_source_rows",
     "smol_cuda_get_stats", "smol_cuda_reset_stats", "smol_cuda_force_kernel", "smol_cuda_get_kernel_launches",
 ]
@@ -101,6 +102,7 @@ def lib():
     L.smol_cuda_set_device.argtypes = [ctypes.c_int]
     L.smol_cuda_set_stream.argtypes = [ctypes.c_void_p]
     L.smol_cuda_synchronize.argtypes = []
+    L.smol_cuda_set_multi_gpu.argtypes = [ctypes.c_int]
     L.smol_cuda_scale_images.argtypes = [
         ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
         ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
@@ -232,6 +234,11 @@ def set_stream(cuda_stream):
 
 def synchronize():
     lib().smol_cuda_synchronize()
+
+
+def set_multi_gpu(n_devices):
+    """How many GPUs one host-memory call may be spread over (1 = off, 0 = all visible)."""
+    lib().smol_cuda_set_multi_gpu(n_devices)
 
 
 def stats():

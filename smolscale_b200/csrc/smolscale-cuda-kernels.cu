@@ -3371,25 +3371,72 @@ smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
     return SMOL_KERNEL_GENERAL;
 }
 
-static int g_num_sms = 0;
+/* Per-device launch state.  Function attributes and occupancy answers belong to a device (a
+ * context), and the library serves several devices from one process, so everything cached here is
+ * keyed by the current device's ordinal. */
+#define SMOL_KERNELS_MAX_DEVICES 16
+
+static int
+current_device ()
+{
+    int dev = 0;
+    if (cudaGetDevice (&dev) != cudaSuccess || dev < 0 || dev >= SMOL_KERNELS_MAX_DEVICES)
+        dev = 0;
+    return dev;
+}
 
 static int
 num_sms ()
 {
-    if (g_num_sms == 0)
+    static int sms[SMOL_KERNELS_MAX_DEVICES];
+    const int dev = current_device ();
+    int n = __atomic_load_n (&sms[dev], __ATOMIC_RELAXED);
+
+    if (n == 0)
     {
-        int dev = 0, n = 148;
-        if (cudaGetDevice (&dev) == cudaSuccess)
-            cudaDeviceGetAttribute (&n, cudaDevAttrMultiProcessorCount, dev);
-        g_num_sms = n > 0 ? n : 148;
+        n = 148;
+        cudaDeviceGetAttribute (&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0)
+            n = 148;
+        __atomic_store_n (&sms[dev], n, __ATOMIC_RELAXED);
     }
-    return g_num_sms;
+    return n;
+}
+
+/* Opts kernel `fn` in to `bytes` of dynamic shared memory on the current device, once per
+ * (device, kernel): a small lock-free set of (fn, device mask) pairs. */
+static cudaError_t
+smem_optin (const void *fn, int bytes)
+{
+    static struct { const void *fn; uint32_t done; } slots[512];
+    const int dev = current_device ();
+    uint32_t h = (uint32_t) ((reinterpret_cast<uintptr_t> (fn) >> 4) * 2654435761u) & 511u;
+
+    for (int probe = 0; probe < 512; probe++, h = (h + 1) & 511u)
+    {
+        const void *cur = __atomic_load_n (&slots[h].fn, __ATOMIC_ACQUIRE);
+        if (cur == nullptr)
+        {
+            const void *expected = nullptr;
+            if (!__atomic_compare_exchange_n (&slots[h].fn, &expected, fn, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)
+                && expected != fn)
+                continue;
+            cur = fn;
+        }
+        if (cur != fn)
+            continue;
+        if (__atomic_load_n (&slots[h].done, __ATOMIC_ACQUIRE) & (1u << dev))
+            return cudaSuccess;
+        const cudaError_t err = cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (err == cudaSuccess)
+            __atomic_fetch_or (&slots[h].done, 1u << dev, __ATOMIC_RELEASE);
+        return err;
+    }
+    return cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 /* See prefetch_l2 / in_first_wave: the number of CTAs of a launch that can be resident at once
  * (0 when SMOL_PDL_PREFETCH=0). */
-static int num_sms ();
-
 static uint32_t
 pdl_first_wave (uint32_t threads_per_cta, size_t smem_per_cta)
 {
@@ -3819,8 +3866,7 @@ launch_mag_fmt_io (const MagParams &M, dim3 grid, size_t smem, cudaStream_t stre
 {
     if (smem > 32 * 1024)        /* static shared memory counts against the 48 KB default too */
     {
-        cudaError_t err = cudaFuncSetAttribute (smol_mag_kernel<BI, BO, IU, OU, AF, FASTIO>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t err = smem_optin ((const void *) smol_mag_kernel<BI, BO, IU, OU, AF, FASTIO>, 200 * 1024);
         if (err != cudaSuccess)
             return err;
     }
@@ -3928,11 +3974,11 @@ launch_magb_fmt (const MagbParams &M, bool src32, dim3 grid, size_t smem, cudaSt
     if (src32)
     {
         if (smem > 40 * 1024)
-            cudaFuncSetAttribute (smol_magb_kernel<BI, BO, IU, OU, AF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            smem_optin ((const void *) smol_magb_kernel<BI, BO, IU, OU, AF, true>, 200 * 1024);
         return launch_pdl (smol_magb_kernel<BI, BO, IU, OU, AF, true>, M, grid, dim3 (256), smem, stream);
     }
     if (smem > 40 * 1024)
-        cudaFuncSetAttribute (smol_magb_kernel<BI, BO, IU, OU, AF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        smem_optin ((const void *) smol_magb_kernel<BI, BO, IU, OU, AF, false>, 200 * 1024);
     return launch_pdl (smol_magb_kernel<BI, BO, IU, OU, AF, false>, M, grid, dim3 (256), smem, stream);
 }
 
@@ -4263,7 +4309,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
             smem = has_lut ? (win_hi - 0x400) + hi * per_warp : (size_t) warps_per_cta * per_warp;
         }
         if (smem > 32 * 1024)        /* static shared memory counts against the 48 KB default too */
-            cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+            smem_optin (fn, 225 * 1024);
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, (int) warps_per_cta * 32, smem) != cudaSuccess || occ < 1)
             occ = 1;
@@ -4334,19 +4380,21 @@ launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
     else if (d.mid == SMOL_MID_P16)                 { variant = 3; fn = (const void *) smol_taps128_kernel<BM_P16_U, 4>; bytes = 0; }
     else                                            { variant = 4; fn = (const void *) smol_taps128_kernel<BM_P16L_U, 4>; bytes = one_tab; }
 
-    static int occ_cache[5][33];        /* resident CTAs per SM by variant and warps per CTA (0: not asked yet) */
+    /* resident CTAs per SM by device, variant and warps per CTA (0: not asked yet) */
+    static int occ_cache[SMOL_KERNELS_MAX_DEVICES][5][33];
+    const int dev = current_device ();
     uint32_t best_w = 32, best_occ = 1;
+    smem_optin (fn, 200 * 1024);
     {
         double best_eff = 0.0;
         for (uint32_t w = 32; w >= 20; w--)
         {
-            int occ = occ_cache[variant][w];
+            int occ = __atomic_load_n (&occ_cache[dev][variant][w], __ATOMIC_RELAXED);
             if (occ == 0)
             {
-                cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, (int) w * 32, bytes) != cudaSuccess || occ < 1)
                     occ = 1;
-                occ_cache[variant][w] = occ;
+                __atomic_store_n (&occ_cache[dev][variant][w], occ, __ATOMIC_RELAXED);
             }
             const uint64_t slots = (uint64_t) num_sms () * occ * w;
             const uint64_t rounds = (n_items + slots - 1) / slots;
@@ -4414,7 +4462,7 @@ launch_tile128 (const SmolLaunch &L, cudaStream_t stream)
     }
     dim3 grid ((d.w_out + M.tile_w - 1) / M.tile_w, (L.n_rows + M.tile_h - 1) / M.tile_h, L.n_images);
 
-#define TILE128_BO(MD, B, O) (cudaFuncSetAttribute (smol_tile128_kernel<MD, B, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), \
+#define TILE128_BO(MD, B, O) (smem_optin ((const void *) smol_tile128_kernel<MD, B, O>, 200 * 1024), \
                               launch_pdl (smol_tile128_kernel<MD, B, O>, M, grid, dim3 (512), smem, stream))
 #define TILE128(MD, B) (d.bpp_out == 3 ? TILE128_BO (MD, B, 3) : TILE128_BO (MD, B, 4))
     if (d.mid == SMOL_MID_P8L)

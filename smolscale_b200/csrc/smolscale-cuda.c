@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <cuda_runtime_api.h>
 
@@ -429,20 +430,23 @@ typedef struct
     uint32_t filter, dim_in, n_entries;
     uint32_t *dev;
     int refs;
+    int uncached;           /* allocated outside the cache (every slot pinned): freed with its last reference */
     uint64_t stamp;
 }
 TabEntry;
 
-#define SMOL_MAX_BANDS 8
+#define SMOL_MAX_BANDS 16
 
 typedef struct
 {
     cudaStream_t stream;                /* kernels (and everything, for small jobs) */
     cudaStream_t s_h2d, s_d2h;          /* copy streams of the banded pipeline */
-    cudaEvent_t ev_up[SMOL_MAX_BANDS], ev_done[SMOL_MAX_BANDS];
+    cudaEvent_t ev_up[SMOL_MAX_BANDS], ev_done[SMOL_MAX_BANDS], ev_down[SMOL_MAX_BANDS];
     int pipeline_ready;
-    void *d_in, *d_out;
+    void *d_in, *d_out;                 /* device staging */
     size_t d_in_cap, d_out_cap;
+    void *h_in, *h_out;                 /* pinned bounce buffers for pageable caller memory */
+    size_t h_in_cap, h_out_cap;
     int busy;
 }
 Lane;
@@ -450,6 +454,7 @@ Lane;
 typedef struct
 {
     int ready;
+    cudaStream_t s_upload;
     SmolDeviceLuts *luts;
     uint16_t *p8l_from_p, *p8l_from_u;
     TabEntry tabs[SMOL_TAB_CACHE_MAX];
@@ -491,6 +496,8 @@ device_count_locked (void)
     return g_device_count;
 }
 
+static void *device_upload (DeviceState *ds, const void *host, size_t bytes);
+
 /* Caller holds g_lock and has made `dev` current. */
 static DeviceState *
 device_state_locked (int dev)
@@ -515,8 +522,7 @@ device_state_locked (int dev)
         memcpy (h->inv_div_p16l, smol_lut_inv_div_p16l, sizeof (h->inv_div_p16l));
         memcpy (h->from_srgb, smol_lut_from_srgb, sizeof (h->from_srgb));
         memcpy (h->to_srgb, smol_lut_to_srgb, sizeof (h->to_srgb));
-        CK (cudaMalloc ((void **) &ds->luts, sizeof (*h)));
-        CK (cudaMemcpy (ds->luts, h, sizeof (*h), cudaMemcpyHostToDevice));
+        ds->luts = device_upload (ds, h, sizeof (*h));
         free (h);
         {
             /* Composite per-channel unpack tables for linear light, index (alpha << 8) | c:
@@ -536,16 +542,45 @@ device_state_locked (int dev)
                     tp[(a << 8) | c] = (uint16_t) ((((smol_lut_from_srgb[u] + 1u) * m - 1u) >> 11) & 0x7ff);
                     tu[(a << 8) | c] = (uint16_t) ((((smol_lut_from_srgb[c] + 1u) * m - 1u) >> 11) & 0x7ff);
                 }
-            CK (cudaMalloc ((void **) &ds->p8l_from_p, 65536 * sizeof (uint16_t)));
-            CK (cudaMalloc ((void **) &ds->p8l_from_u, 65536 * sizeof (uint16_t)));
-            CK (cudaMemcpy (ds->p8l_from_p, tp, 65536 * sizeof (uint16_t), cudaMemcpyHostToDevice));
-            CK (cudaMemcpy (ds->p8l_from_u, tu, 65536 * sizeof (uint16_t), cudaMemcpyHostToDevice));
+            ds->p8l_from_p = device_upload (ds, tp, 65536 * sizeof (uint16_t));
+            ds->p8l_from_u = device_upload (ds, tu, 65536 * sizeof (uint16_t));
             free (tp);
             free (tu);
         }
         ds->ready = 1;
     }
     return ds;
+}
+
+/* Allocation + upload of a small table on the current device.  Runs with the calling thread's
+ * stream-capture mode relaxed, so the first use of a geometry from inside a CUDA graph capture
+ * uploads for real instead of invalidating the capture (the kernel launch that follows is what
+ * gets captured).  The copy goes through a private stream: nothing here touches the caller's
+ * stream or the legacy default stream. */
+static void *
+device_upload (DeviceState *ds, const void *host, size_t bytes)
+{
+    enum cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+    void *dev = NULL;
+
+    CK (cudaThreadExchangeStreamCaptureMode (&mode));
+    if (!ds->s_upload)
+        CK (cudaStreamCreateWithFlags (&ds->s_upload, cudaStreamNonBlocking));
+    CK (cudaMalloc (&dev, bytes));
+    CK (cudaMemcpyAsync (dev, host, bytes, cudaMemcpyHostToDevice, ds->s_upload));
+    CK (cudaStreamSynchronize (ds->s_upload));
+    CK (cudaThreadExchangeStreamCaptureMode (&mode));
+    return dev;
+}
+
+static void
+device_release (void *dev)
+{
+    enum cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+
+    CK (cudaThreadExchangeStreamCaptureMode (&mode));
+    CK (cudaFree (dev));                /* implicit device synchronisation: nothing can still read it */
+    CK (cudaThreadExchangeStreamCaptureMode (&mode));
 }
 
 /* Looks up / uploads one axis table.  Caller holds g_lock, device is current. */
@@ -578,11 +613,21 @@ tab_acquire_locked (DeviceState *ds, const AxisPlan *ap)
 
     if (!free_slot)
     {
-        if (!victim)
-            smol_fatal ("filter table cache exhausted (too many live contexts)", NULL);
-        CK (cudaFree (victim->dev));    /* implicit device synchronisation: nothing can still read it */
-        victim->used = 0;
-        free_slot = victim;
+        if (victim)
+        {
+            device_release (victim->dev);
+            victim->used = 0;
+            free_slot = victim;
+        }
+        else
+        {
+            /* every slot is pinned by a live context (the reference has no limit on those): this
+             * table lives outside the cache and goes away with its last reference */
+            free_slot = calloc (1, sizeof (*free_slot));
+            if (!free_slot)
+                smol_fatal ("out of memory", NULL);
+            free_slot->uncached = 1;
+        }
     }
 
     free_slot->used = 1;
@@ -592,11 +637,27 @@ tab_acquire_locked (DeviceState *ds, const AxisPlan *ap)
     free_slot->n_entries = ap->n_entries;
     free_slot->refs = 1;
     free_slot->stamp = ++ds->clock;
-    CK (cudaMalloc ((void **) &free_slot->dev, (size_t) ap->n_entries * sizeof (uint32_t)));
-    CK (cudaMemcpy (free_slot->dev, ap->dev_entries, (size_t) ap->n_entries * sizeof (uint32_t),
-                    cudaMemcpyHostToDevice));
+    free_slot->dev = device_upload (ds, ap->dev_entries, (size_t) ap->n_entries * sizeof (uint32_t));
     __atomic_add_fetch (&g_stat_uploads, 1, __ATOMIC_RELAXED);
     return free_slot;
+}
+
+/* Caller holds g_lock.  `dev` is the ordinal the table lives on. */
+static void
+tab_release_locked (TabEntry *t, int dev)
+{
+    if (--t->refs == 0 && t->uncached)
+    {
+        int prev = -1;
+
+        CK (cudaGetDevice (&prev));
+        if (prev != dev)
+            CK (cudaSetDevice (dev));
+        device_release (t->dev);
+        if (prev != dev)
+            CK (cudaSetDevice (prev));
+        free (t);
+    }
 }
 
 static Lane *
@@ -685,9 +746,9 @@ shared_plan_drop_locked (SharedPlan *sp)
     for (i = 0; i < SMOL_MAX_DEVICES; i++)
     {
         if (sp->tab_x[i])
-            sp->tab_x[i]->refs--;
+            tab_release_locked (sp->tab_x[i], i);
         if (sp->tab_y[i])
-            sp->tab_y[i]->refs--;
+            tab_release_locked (sp->tab_y[i], i);
     }
     job_plan_clear (&sp->plan);
     free (sp);
@@ -846,10 +907,14 @@ ctx_device_tables (SmolScaleCtx *ctx, int dev, SmolLaunch *L)
  * Row rendering                                                                              *
  * ------------------------------------------------------------------------------------------ */
 
+/* Where a caller's buffer lives. */
+enum { SMOL_MEM_PAGEABLE = 0, SMOL_MEM_PINNED = 1, SMOL_MEM_DEVICE = 2 };
+
 typedef struct
 {
     int is_device;      /* device or managed: a kernel can dereference it */
     int device;
+    int mem;            /* SMOL_MEM_* */
 }
 PtrClass;
 
@@ -857,7 +922,7 @@ static PtrClass
 classify_pointer (const void *p)
 {
     struct cudaPointerAttributes attr;
-    PtrClass pc = { 0, -1 };
+    PtrClass pc = { 0, -1, SMOL_MEM_PAGEABLE };
     cudaError_t e;
 
     if (!p)
@@ -872,7 +937,10 @@ classify_pointer (const void *p)
     {
         pc.is_device = 1;
         pc.device = attr.device;
+        pc.mem = SMOL_MEM_DEVICE;
     }
+    else if (attr.type == cudaMemoryTypeHost)
+        pc.mem = SMOL_MEM_PINNED;
     return pc;
 }
 
@@ -929,17 +997,478 @@ copy_rows_async (void *dst, size_t dpitch, const void *src, size_t spitch,
     }
 }
 
+/* ---- worker pool -------------------------------------------------------------------------- *
+ * A few persistent host threads shared by everything in this file that wants more than the
+ * calling thread: bouncing pageable caller memory through pinned buffers (one memcpy thread
+ * moves ~10 GB/s, a PCIe 5 x16 link 55), and driving one device each when a host-memory call is
+ * split across several GPUs.  pool_run() runs task 0 on the calling thread and, while waiting
+ * for the others, helps with whatever is queued -- so nested use cannot deadlock. */
+
+typedef struct PoolGroup { int pending; } PoolGroup;
+
+typedef struct PoolTask
+{
+    void (*fn) (void *);
+    void *arg;
+    PoolGroup *grp;
+    struct PoolTask *next;
+}
+PoolTask;
+
+#define SMOL_POOL_MAX 32
+
+static pthread_mutex_t g_pool_lock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_pool_cond = PTHREAD_COND_INITIALIZER;
+static PoolTask *g_pool_head, *g_pool_tail;
+static int g_pool_threads, g_pool_limit = -1;
+
+static void
+pool_finish_locked (PoolTask *t)
+{
+    if (--t->grp->pending == 0)
+        pthread_cond_broadcast (&g_pool_cond);
+}
+
+static void *
+pool_main (void *unused)
+{
+    (void) unused;
+    pthread_mutex_lock (&g_pool_lock);
+    for (;;)
+    {
+        PoolTask *t;
+
+        while (!g_pool_head)
+            pthread_cond_wait (&g_pool_cond, &g_pool_lock);
+        t = g_pool_head;
+        g_pool_head = t->next;
+        if (!g_pool_head)
+            g_pool_tail = NULL;
+        pthread_mutex_unlock (&g_pool_lock);
+        t->fn (t->arg);
+        pthread_mutex_lock (&g_pool_lock);
+        pool_finish_locked (t);
+    }
+    return NULL;
+}
+
+static int
+pool_limit (void)
+{
+    if (g_pool_limit < 0)
+    {
+        const char *e = getenv ("SMOL_CUDA_HOST_THREADS");
+        long n = e ? atol (e) : sysconf (_SC_NPROCESSORS_ONLN) / 2;
+
+        if (n < 1)
+            n = 1;
+        if (n > SMOL_POOL_MAX)
+            n = SMOL_POOL_MAX;
+        g_pool_limit = (int) n;
+    }
+    return g_pool_limit;
+}
+
+/* Runs fn (args + i * arg_size) for i in [0, n) and returns when all are done. */
+static void
+pool_run (void (*fn) (void *), void *args, size_t arg_size, int n)
+{
+    PoolTask tasks[SMOL_POOL_MAX * 2];
+    PoolGroup grp;
+    int i;
+
+    if (n > SMOL_POOL_MAX * 2)
+        smol_fatal ("pool_run: too many tasks", NULL);
+    if (n <= 1)
+    {
+        if (n == 1)
+            fn (args);
+        return;
+    }
+    grp.pending = n - 1;
+    pthread_mutex_lock (&g_pool_lock);
+    while (g_pool_threads < n - 1 && g_pool_threads < pool_limit ())
+    {
+        pthread_t th;
+        pthread_attr_t at;
+
+        pthread_attr_init (&at);
+        pthread_attr_setdetachstate (&at, PTHREAD_CREATE_DETACHED);
+        if (pthread_create (&th, &at, pool_main, NULL) != 0)
+        {
+            pthread_attr_destroy (&at);
+            break;
+        }
+        pthread_attr_destroy (&at);
+        g_pool_threads++;
+    }
+    for (i = 1; i < n; i++)
+    {
+        PoolTask *t = &tasks[i];
+
+        t->fn = fn;
+        t->arg = (char *) args + (size_t) i * arg_size;
+        t->grp = &grp;
+        t->next = NULL;
+        if (g_pool_tail)
+            g_pool_tail->next = t;
+        else
+            g_pool_head = t;
+        g_pool_tail = t;
+    }
+    pthread_cond_broadcast (&g_pool_cond);
+    pthread_mutex_unlock (&g_pool_lock);
+
+    fn (args);
+
+    pthread_mutex_lock (&g_pool_lock);
+    while (grp.pending > 0)
+    {
+        PoolTask *t = g_pool_head;
+
+        if (t)
+        {
+            g_pool_head = t->next;
+            if (!g_pool_head)
+                g_pool_tail = NULL;
+            pthread_mutex_unlock (&g_pool_lock);
+            t->fn (t->arg);
+            pthread_mutex_lock (&g_pool_lock);
+            pool_finish_locked (t);
+        }
+        else
+            pthread_cond_wait (&g_pool_cond, &g_pool_lock);
+    }
+    pthread_mutex_unlock (&g_pool_lock);
+}
+
+typedef struct
+{
+    char *dst;
+    const char *src;
+    size_t dpitch, spitch, width_bytes, n_rows;
+}
+RowCopy;
+
+static void
+row_copy_task (void *arg)
+{
+    const RowCopy *c = arg;
+    size_t r;
+
+    if (c->dpitch == c->width_bytes && c->spitch == c->width_bytes)
+        memcpy (c->dst, c->src, c->width_bytes * c->n_rows);
+    else
+        for (r = 0; r < c->n_rows; r++)
+            memcpy (c->dst + r * c->dpitch, c->src + r * c->spitch, c->width_bytes);
+}
+
+/* Host-to-host row copy spread over the pool (about 1 MB per task). */
+static void
+copy_rows_host (void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t n_rows)
+{
+    RowCopy parts[SMOL_POOL_MAX];
+    size_t total = width_bytes * n_rows, per, r;
+    int n = (int) (total >> 20), i;
+
+    if (n_rows == 0 || width_bytes == 0)
+        return;
+    if (n > pool_limit ())
+        n = pool_limit ();
+    if ((size_t) n > n_rows)
+        n = (int) n_rows;
+    if (n < 1)
+        n = 1;
+    per = (n_rows + n - 1) / n;
+    for (i = 0, r = 0; i < n && r < n_rows; i++, r += per)
+    {
+        parts[i].dst = (char *) dst + r * dpitch;
+        parts[i].src = (const char *) src + r * spitch;
+        parts[i].dpitch = dpitch;
+        parts[i].spitch = spitch;
+        parts[i].width_bytes = width_bytes;
+        parts[i].n_rows = n_rows - r < per ? n_rows - r : per;
+    }
+    pool_run (row_copy_task, parts, sizeof (parts[0]), i);
+}
+
+static void
+lane_reserve_pinned (void **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap)
+        return;
+    if (*buf)
+        CK (cudaFreeHost (*buf));
+    need = (need + ((size_t) 1 << 20) - 1) & ~(((size_t) 1 << 20) - 1);
+    CK (cudaHostAlloc (buf, need, cudaHostAllocDefault));
+    *cap = need;
+}
+
+/* Source rows a band must have on the device before its kernel runs: what it reads, plus the
+ * row below for the copy filter -- the taps kernels fetch row r + 1 (clamped to the image) with
+ * weight zero rather than branch on it, so it has to be addressable. */
+static void
+plan_staged_rows (const JobPlan *jp, uint32_t first, uint32_t n, uint32_t *r0, uint32_t *nr)
+{
+    plan_source_rows (jp, first, n, r0, nr);
+    if (n > 0 && jp->ay.kind == SMOL_AXIS_TAPS && jp->ay.filter != SMOL_CUDA_AXIS_BILINEAR
+        && *r0 + *nr < jp->d.h_in)
+        (*nr)++;
+}
+
+/* One band of output rows of a call that involves host memory (or a row callback), rendered on
+ * device `dev`: stage the source rows the band reads, run the kernel(s), bring the rows back,
+ * wait.  Large bands run as a pipeline of sub-bands so H2D, kernel and D2H overlap. */
+static void
+render_staged (SmolScaleCtx *ctx, int dev, void *outrows_dest, uint32_t first_row, uint32_t n_rows,
+               PtrClass pc_in, PtrClass pc_out, cudaStream_t caller_stream)
+{
+    const SmolJobDesc *d = &ctx->sp->plan.d;
+    const size_t in_row_bytes = (size_t) d->w_in * d->bpp_in;
+    const size_t out_row_bytes = (size_t) d->w_out * d->bpp_out;
+    const size_t in_pitch = align16 (in_row_bytes), out_pitch = align16 (out_row_bytes);
+    const int bounce_in = !pc_in.is_device && pc_in.mem == SMOL_MEM_PAGEABLE;
+    const int bounce_out = !pc_out.is_device && pc_out.mem == SMOL_MEM_PAGEABLE;
+    SmolLaunch L;
+    Lane *lane;
+    cudaStream_t s;
+    size_t staged_bytes = 0;
+    uint32_t n_bands = 1, rows_per_band, b, r0, nr;
+    int prev_dev = -1;
+
+    CK (cudaGetDevice (&prev_dev));
+    if (dev != prev_dev)
+        CK (cudaSetDevice (dev));
+
+    memset (&L, 0, sizeof (L));
+    L.d = *d;
+    L.n_images = 1;
+    ctx_device_tables (ctx, dev, &L);
+
+    lane = lane_acquire (dev);
+    /* A caller's device buffer is ordered by the caller's stream (whatever produced the input
+     * was enqueued there, whatever consumes the output will be): the kernel goes on that stream.
+     * Pure host-memory calls use the lane's own stream so concurrent callers overlap. */
+    s = (pc_in.is_device || pc_out.is_device) ? caller_stream : lane->stream;
+
+    plan_staged_rows (&ctx->sp->plan, first_row, n_rows, &r0, &nr);
+
+    if (pc_in.is_device)
+    {
+        L.src = (const uint8_t *) ctx->pixels_in;
+        L.src_pitch = ctx->rowstride_in;
+    }
+    else
+    {
+        lane_reserve (&lane->d_in, &lane->d_in_cap, in_pitch * nr + 16);
+        /* the kernel addresses rows from row 0 of the image; only rows [r0, r0 + nr) are read */
+        L.src = (const uint8_t *) lane->d_in - (size_t) r0 * in_pitch;
+        L.src_pitch = (uint32_t) in_pitch;
+        staged_bytes += in_row_bytes * nr;
+        if (bounce_in)
+            lane_reserve_pinned (&lane->h_in, &lane->h_in_cap, in_row_bytes * nr);
+    }
+    if (pc_out.is_device)
+    {
+        L.dst = (uint8_t *) outrows_dest;
+        L.dst_pitch = ctx->rowstride_out;
+    }
+    else
+    {
+        lane_reserve (&lane->d_out, &lane->d_out_cap, out_pitch * n_rows + 16);
+        L.dst = (uint8_t *) lane->d_out;
+        L.dst_pitch = (uint32_t) out_pitch;
+        staged_bytes += out_row_bytes * n_rows;
+        if (bounce_out)
+            lane_reserve_pinned (&lane->h_out, &lane->h_out_cap, out_row_bytes * n_rows);
+    }
+
+    /* Large host-memory jobs run as a pipeline of row bands: while band b is being scaled,
+     * band b + 1's source rows are already crossing PCIe and band b - 1's output rows are on
+     * their way back (H2D and D2H overlap: the link is full duplex).  Bands share the staged
+     * source image, so each source row is uploaded exactly once.  Pageable caller memory is
+     * bounced through the lane's pinned buffers by the worker pool, band by band, so the host
+     * copies overlap the transfers too. */
+    if (staged_bytes >= ((size_t) 4 << 20) && n_rows >= 2 * SMOL_MAX_BANDS)
+    {
+        n_bands = (uint32_t) (staged_bytes >> ((bounce_in || bounce_out) ? 21 : 22));
+        if (n_bands > ((bounce_in || bounce_out) ? SMOL_MAX_BANDS : SMOL_MAX_BANDS / 2))
+            n_bands = (bounce_in || bounce_out) ? SMOL_MAX_BANDS : SMOL_MAX_BANDS / 2;
+        if (n_bands < 2)
+            n_bands = 2;
+    }
+    rows_per_band = (n_rows + n_bands - 1) / n_bands;
+
+    if ((n_bands > 1 || bounce_out) && !lane->pipeline_ready)
+    {
+        CK (cudaStreamCreateWithFlags (&lane->s_h2d, cudaStreamNonBlocking));
+        CK (cudaStreamCreateWithFlags (&lane->s_d2h, cudaStreamNonBlocking));
+        for (b = 0; b < SMOL_MAX_BANDS; b++)
+        {
+            CK (cudaEventCreateWithFlags (&lane->ev_up[b], cudaEventDisableTiming));
+            CK (cudaEventCreateWithFlags (&lane->ev_done[b], cudaEventDisableTiming));
+            CK (cudaEventCreateWithFlags (&lane->ev_down[b], cudaEventDisableTiming | cudaEventBlockingSync));
+        }
+        lane->pipeline_ready = 1;
+    }
+
+    {
+        const uint8_t *dst_base = L.dst;
+        uint32_t uploaded_end = r0;     /* source rows [r0, uploaded_end) are on the device */
+        uint32_t band_first_of[SMOL_MAX_BANDS], band_rows_of[SMOL_MAX_BANDS];
+        uint32_t n_done = 0, drained = 0;
+        cudaStream_t s_up = n_bands > 1 ? lane->s_h2d : s;
+        cudaStream_t s_down = n_bands > 1 ? lane->s_d2h : s;
+
+        for (b = 0; b < n_bands; b++)
+        {
+            const uint32_t band_first = first_row + b * rows_per_band;
+            uint32_t band_rows, br0, bnr;
+
+            if (band_first >= first_row + n_rows)
+                break;
+            band_rows = first_row + n_rows - band_first;
+            if (band_rows > rows_per_band)
+                band_rows = rows_per_band;
+            band_first_of[b] = band_first;
+            band_rows_of[b] = band_rows;
+            n_done = b + 1;
+
+            if (!pc_in.is_device)
+            {
+                plan_staged_rows (&ctx->sp->plan, band_first, band_rows, &br0, &bnr);
+                if (br0 + bnr > uploaded_end)
+                {
+                    const uint32_t from = uploaded_end, cnt = br0 + bnr - uploaded_end;
+                    const char *rows = ctx->pixels_in + (size_t) from * ctx->rowstride_in;
+                    size_t rows_pitch = ctx->rowstride_in;
+
+                    if (bounce_in)
+                    {
+                        char *bounce = (char *) lane->h_in + (size_t) (from - r0) * in_row_bytes;
+
+                        copy_rows_host (bounce, in_row_bytes, rows, rows_pitch, in_row_bytes, cnt);
+                        rows = bounce;
+                        rows_pitch = in_row_bytes;
+                    }
+                    copy_rows_async ((char *) lane->d_in + (size_t) (from - r0) * in_pitch, in_pitch,
+                                     rows, rows_pitch, in_row_bytes, cnt, cudaMemcpyHostToDevice, s_up);
+                    __atomic_add_fetch (&g_stat_h2d, in_row_bytes * cnt, __ATOMIC_RELAXED);
+                    uploaded_end = br0 + bnr;
+                }
+                if (n_bands > 1)
+                {
+                    CK (cudaEventRecord (lane->ev_up[b], s_up));
+                    CK (cudaStreamWaitEvent (s, lane->ev_up[b], 0));
+                }
+            }
+
+            L.first_row = band_first;
+            L.n_rows = band_rows;
+            L.dst = (uint8_t *) dst_base + (size_t) (band_first - first_row) * L.dst_pitch;
+            launch_checked (&L, s);
+
+            if (!pc_out.is_device)
+            {
+                char *to = (char *) outrows_dest + (size_t) (band_first - first_row) * ctx->rowstride_out;
+                size_t to_pitch = ctx->rowstride_out;
+
+                if (n_bands > 1)
+                {
+                    CK (cudaEventRecord (lane->ev_done[b], s));
+                    CK (cudaStreamWaitEvent (s_down, lane->ev_done[b], 0));
+                }
+                if (bounce_out)
+                {
+                    to = (char *) lane->h_out + (size_t) (band_first - first_row) * out_row_bytes;
+                    to_pitch = out_row_bytes;
+                }
+                copy_rows_async (to, to_pitch, L.dst, L.dst_pitch,
+                                 out_row_bytes, band_rows, cudaMemcpyDeviceToHost, s_down);
+                __atomic_add_fetch (&g_stat_d2h, out_row_bytes * band_rows, __ATOMIC_RELAXED);
+                if (bounce_out)
+                    CK (cudaEventRecord (lane->ev_down[b], s_down));
+            }
+
+            /* pageable destination: hand over bands that have already landed (two behind) */
+            if (bounce_out)
+                for (; drained + 2 <= b; drained++)
+                {
+                    CK (cudaEventSynchronize (lane->ev_down[drained]));
+                    copy_rows_host ((char *) outrows_dest + (size_t) (band_first_of[drained] - first_row) * ctx->rowstride_out,
+                                    ctx->rowstride_out,
+                                    (char *) lane->h_out + (size_t) (band_first_of[drained] - first_row) * out_row_bytes,
+                                    out_row_bytes, out_row_bytes, band_rows_of[drained]);
+                }
+        }
+        if (bounce_out)
+            for (; drained < n_done; drained++)
+            {
+                CK (cudaEventSynchronize (lane->ev_down[drained]));
+                copy_rows_host ((char *) outrows_dest + (size_t) (band_first_of[drained] - first_row) * ctx->rowstride_out,
+                                ctx->rowstride_out,
+                                (char *) lane->h_out + (size_t) (band_first_of[drained] - first_row) * out_row_bytes,
+                                out_row_bytes, out_row_bytes, band_rows_of[drained]);
+            }
+        if (n_bands > 1)
+            CK (cudaStreamSynchronize (s_down));
+        CK (cudaStreamSynchronize (s));
+    }
+
+    lane_release (lane);
+    if (dev != prev_dev)
+        CK (cudaSetDevice (prev_dev));
+}
+
+/* ---- splitting one host-memory call across several GPUs ------------------------------------ */
+
+static int g_multi_gpu = -1;        /* devices a host-memory call may be spread over (1 = off) */
+
+static int
+multi_gpu_devices (void)
+{
+    int n = __atomic_load_n (&g_multi_gpu, __ATOMIC_RELAXED);
+
+    if (n < 0)
+    {
+        const char *e = getenv ("SMOL_CUDA_MULTI_GPU");
+
+        n = 1;
+        if (e && *e)
+            n = (strcmp (e, "all") == 0) ? SMOL_MAX_DEVICES : atoi (e);
+        if (n < 1)
+            n = 1;
+        __atomic_store_n (&g_multi_gpu, n, __ATOMIC_RELAXED);
+    }
+    return n < g_device_count ? n : g_device_count;
+}
+
+typedef struct
+{
+    SmolScaleCtx *ctx;
+    int dev;
+    void *dest;
+    uint32_t first_row, n_rows;
+    PtrClass pc_in, pc_out;
+}
+DeviceBand;
+
+static void
+device_band_task (void *arg)
+{
+    DeviceBand *t = arg;
+
+    render_staged (t->ctx, t->dev, t->dest, t->first_row, t->n_rows, t->pc_in, t->pc_out, NULL);
+}
+
 static void
 do_rows (const SmolScaleCtx *cctx, void *outrows_dest, uint32_t first_row, uint32_t n_rows)
 {
     SmolScaleCtx *ctx = (SmolScaleCtx *) cctx;
     const SmolJobDesc *d = &ctx->sp->plan.d;
-    const size_t in_row_bytes = (size_t) d->w_in * d->bpp_in;
     const size_t out_row_bytes = (size_t) d->w_out * d->bpp_out;
     PtrClass pc_in, pc_out;
-    SmolLaunch L;
     int prev_dev = -1, dev;
-    uint32_t r0, nr;
 
     if (n_rows == 0)
         return;
@@ -965,182 +1494,105 @@ do_rows (const SmolScaleCtx *cctx, void *outrows_dest, uint32_t first_row, uint3
         dev = pc_in.device;
     else
         dev = tl_device >= 0 ? tl_device : prev_dev;
-    if (dev != prev_dev)
-        CK (cudaSetDevice (dev));
-
-    memset (&L, 0, sizeof (L));
-    L.d = *d;
-    L.n_images = 1;
-    L.first_row = first_row;
-    L.n_rows = n_rows;
-    ctx_device_tables (ctx, dev, &L);
+    if (dev < 0 || dev >= g_device_count)
+        smol_fatal ("buffer lives on a device this library cannot use (more than 16 devices?)", NULL);
 
     if (pc_in.is_device && pc_out.is_device && !ctx->post_row_func)
     {
         /* Everything already lives on the GPU: enqueue and return (stream-ordered). */
+        SmolLaunch L;
+
+        if (dev != prev_dev)
+            CK (cudaSetDevice (dev));
+        memset (&L, 0, sizeof (L));
+        L.d = *d;
+        L.n_images = 1;
+        L.first_row = first_row;
+        L.n_rows = n_rows;
+        ctx_device_tables (ctx, dev, &L);
         L.src = (const uint8_t *) ctx->pixels_in;
         L.src_pitch = ctx->rowstride_in;
         L.dst = (uint8_t *) outrows_dest;
         L.dst_pitch = ctx->rowstride_out;
         launch_checked (&L, (cudaStream_t) tl_stream);
+        if (dev != prev_dev)
+            CK (cudaSetDevice (prev_dev));
+        return;
     }
-    else
+
     {
-        Lane *lane = lane_acquire (dev);
-        cudaStream_t s = lane->stream;
+        /* Host memory on both sides and several GPUs allowed: every device renders a band of
+         * output rows from its own upload of just the source rows that band reads, over its own
+         * PCIe link (the reference's row-batch contract, smolscale.h:70-74, makes bands
+         * independent).  Worth it from ~8 MB of transfers per device. */
+        const size_t moved = (size_t) d->w_in * d->bpp_in * d->h_in * n_rows / d->h_out + out_row_bytes * n_rows;
+        int n_dev = (!pc_in.is_device && !pc_out.is_device) ? multi_gpu_devices () : 1;
 
-        plan_source_rows (&ctx->sp->plan, first_row, n_rows, &r0, &nr);
+        while (n_dev > 1 && (moved / n_dev < ((size_t) 8 << 20) || n_rows / n_dev < 16))
+            n_dev--;
+        if (n_dev > 1)
+        {
+            DeviceBand bands[SMOL_MAX_DEVICES];
+            const uint32_t per = (n_rows + n_dev - 1) / n_dev;
+            int i, n = 0;
 
-        const size_t in_pitch = align16 (in_row_bytes), out_pitch = align16 (out_row_bytes);
-        size_t staged_bytes = 0;
-        uint32_t n_bands = 1, rows_per_band, b;
-
-        if (pc_in.is_device)
-        {
-            L.src = (const uint8_t *) ctx->pixels_in;
-            L.src_pitch = ctx->rowstride_in;
-        }
-        else
-        {
-            lane_reserve (&lane->d_in, &lane->d_in_cap, in_pitch * nr + 16);
-            /* the kernel addresses rows from row 0 of the image; only rows [r0, r0 + nr) are read */
-            L.src = (const uint8_t *) lane->d_in - (size_t) r0 * in_pitch;
-            L.src_pitch = (uint32_t) in_pitch;
-            staged_bytes += in_row_bytes * nr;
-        }
-        if (pc_out.is_device)
-        {
-            L.dst = (uint8_t *) outrows_dest;
-            L.dst_pitch = ctx->rowstride_out;
-        }
-        else
-        {
-            lane_reserve (&lane->d_out, &lane->d_out_cap, out_pitch * n_rows + 16);
-            L.dst = (uint8_t *) lane->d_out;
-            L.dst_pitch = (uint32_t) out_pitch;
-            staged_bytes += out_row_bytes * n_rows;
-        }
-
-        /* Large host-memory jobs run as a pipeline of row bands: while band b is being scaled,
-         * band b + 1's source rows are already crossing PCIe and band b - 1's output rows are on
-         * their way back (H2D and D2H overlap: the link is full duplex).  Bands share the staged
-         * source image, so each source row is uploaded exactly once. */
-        if (staged_bytes >= ((size_t) 4 << 20) && n_rows >= 2 * SMOL_MAX_BANDS)
-        {
-            n_bands = (uint32_t) (staged_bytes >> 22);
-            if (n_bands > SMOL_MAX_BANDS)
-                n_bands = SMOL_MAX_BANDS;
-            if (n_bands < 2)
-                n_bands = 2;
-        }
-        rows_per_band = (n_rows + n_bands - 1) / n_bands;
-
-        if (n_bands > 1 && !lane->pipeline_ready)
-        {
-            CK (cudaStreamCreateWithFlags (&lane->s_h2d, cudaStreamNonBlocking));
-            CK (cudaStreamCreateWithFlags (&lane->s_d2h, cudaStreamNonBlocking));
-            for (b = 0; b < SMOL_MAX_BANDS; b++)
+            for (i = 0; i < n_dev; i++)
             {
-                CK (cudaEventCreateWithFlags (&lane->ev_up[b], cudaEventDisableTiming));
-                CK (cudaEventCreateWithFlags (&lane->ev_done[b], cudaEventDisableTiming));
-            }
-            lane->pipeline_ready = 1;
-        }
+                const uint32_t at = (uint32_t) i * per;
 
-        {
-            const uint8_t *dst_base = L.dst;
-            uint32_t uploaded_end = r0;     /* source rows [r0, uploaded_end) are on the device */
-            cudaStream_t s_up = n_bands > 1 ? lane->s_h2d : s;
-            cudaStream_t s_down = n_bands > 1 ? lane->s_d2h : s;
-
-            for (b = 0; b < n_bands; b++)
-            {
-                const uint32_t band_first = first_row + b * rows_per_band;
-                uint32_t band_rows, br0, bnr;
-
-                if (band_first >= first_row + n_rows)
+                if (at >= n_rows)
                     break;
-                band_rows = first_row + n_rows - band_first;
-                if (band_rows > rows_per_band)
-                    band_rows = rows_per_band;
-
-                if (!pc_in.is_device)
-                {
-                    plan_source_rows (&ctx->sp->plan, band_first, band_rows, &br0, &bnr);
-                    if (br0 + bnr > uploaded_end)
-                    {
-                        const uint32_t from = uploaded_end, cnt = br0 + bnr - uploaded_end;
-
-                        copy_rows_async ((char *) lane->d_in + (size_t) (from - r0) * in_pitch, in_pitch,
-                                         ctx->pixels_in + (size_t) from * ctx->rowstride_in, ctx->rowstride_in,
-                                         in_row_bytes, cnt, cudaMemcpyHostToDevice, s_up);
-                        __atomic_add_fetch (&g_stat_h2d, in_row_bytes * cnt, __ATOMIC_RELAXED);
-                        uploaded_end = br0 + bnr;
-                    }
-                    if (n_bands > 1)
-                    {
-                        CK (cudaEventRecord (lane->ev_up[b], s_up));
-                        CK (cudaStreamWaitEvent (s, lane->ev_up[b], 0));
-                    }
-                }
-
-                L.first_row = band_first;
-                L.n_rows = band_rows;
-                L.dst = (uint8_t *) dst_base + (size_t) (band_first - first_row) * L.dst_pitch;
-                launch_checked (&L, s);
-
-                if (!pc_out.is_device)
-                {
-                    if (n_bands > 1)
-                    {
-                        CK (cudaEventRecord (lane->ev_done[b], s));
-                        CK (cudaStreamWaitEvent (s_down, lane->ev_done[b], 0));
-                    }
-                    copy_rows_async ((char *) outrows_dest + (size_t) (band_first - first_row) * ctx->rowstride_out,
-                                     ctx->rowstride_out, L.dst, L.dst_pitch,
-                                     out_row_bytes, band_rows, cudaMemcpyDeviceToHost, s_down);
-                    __atomic_add_fetch (&g_stat_d2h, out_row_bytes * band_rows, __ATOMIC_RELAXED);
-                }
+                bands[n].ctx = ctx;
+                bands[n].dev = (dev + i) % g_device_count;
+                bands[n].dest = (char *) outrows_dest + (size_t) at * ctx->rowstride_out;
+                bands[n].first_row = first_row + at;
+                bands[n].n_rows = n_rows - at < per ? n_rows - at : per;
+                bands[n].pc_in = pc_in;
+                bands[n].pc_out = pc_out;
+                n++;
             }
-            if (n_bands > 1)
-                CK (cudaStreamSynchronize (s_down));
-            CK (cudaStreamSynchronize (s));
+            pool_run (device_band_task, bands, sizeof (bands[0]), n);
         }
-
-        if (ctx->post_row_func)
-        {
-            /* reference smolscale.c:502-503: once per finished row, on the calling thread */
-            uint32_t i;
-
-            if (!pc_out.is_device)
-            {
-                for (i = 0; i < n_rows; i++)
-                    ctx->post_row_func ((uint32_t *) ((char *) outrows_dest + (size_t) i * ctx->rowstride_out),
-                                        (int) d->w_out, ctx->user_data);
-            }
-            else
-            {
-                /* device destination: bounce each row through host memory */
-                uint32_t *tmp = malloc (align16 (out_row_bytes) + 16);
-
-                if (!tmp)
-                    smol_fatal ("out of memory", NULL);
-                for (i = 0; i < n_rows; i++)
-                {
-                    char *row = (char *) outrows_dest + (size_t) i * ctx->rowstride_out;
-
-                    CK (cudaMemcpy (tmp, row, out_row_bytes, cudaMemcpyDeviceToHost));
-                    ctx->post_row_func (tmp, (int) d->w_out, ctx->user_data);
-                    CK (cudaMemcpy (row, tmp, out_row_bytes, cudaMemcpyHostToDevice));
-                }
-                free (tmp);
-            }
-        }
-        lane_release (lane);
+        else
+            render_staged (ctx, dev, outrows_dest, first_row, n_rows, pc_in, pc_out, (cudaStream_t) tl_stream);
     }
 
-    if (dev != prev_dev)
-        CK (cudaSetDevice (prev_dev));
+    if (ctx->post_row_func)
+    {
+        /* reference smolscale.c:502-503: once per finished row, on the calling thread */
+        uint32_t i;
+
+        if (!pc_out.is_device)
+        {
+            for (i = 0; i < n_rows; i++)
+                ctx->post_row_func ((uint32_t *) ((char *) outrows_dest + (size_t) i * ctx->rowstride_out),
+                                    (int) d->w_out, ctx->user_data);
+        }
+        else
+        {
+            /* device destination: bounce each row through host memory, on the caller's stream */
+            uint32_t *tmp = malloc (align16 (out_row_bytes) + 16);
+            cudaStream_t s = (cudaStream_t) tl_stream;
+
+            if (!tmp)
+                smol_fatal ("out of memory", NULL);
+            if (dev != prev_dev)
+                CK (cudaSetDevice (dev));
+            for (i = 0; i < n_rows; i++)
+            {
+                char *row = (char *) outrows_dest + (size_t) i * ctx->rowstride_out;
+
+                CK (cudaMemcpyAsync (tmp, row, out_row_bytes, cudaMemcpyDeviceToHost, s));
+                CK (cudaStreamSynchronize (s));
+                ctx->post_row_func (tmp, (int) d->w_out, ctx->user_data);
+                CK (cudaMemcpyAsync (row, tmp, out_row_bytes, cudaMemcpyHostToDevice, s));
+                CK (cudaStreamSynchronize (s));
+            }
+            if (dev != prev_dev)
+                CK (cudaSetDevice (prev_dev));
+            free (tmp);
+        }
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ *
@@ -1237,6 +1689,14 @@ smol_cuda_set_stream (void *cuda_stream)
 }
 
 SMOL_EXPORT void
+smol_cuda_set_multi_gpu (int n_devices)
+{
+    if (n_devices < 1)
+        n_devices = SMOL_MAX_DEVICES;       /* 0 / negative: every visible device */
+    __atomic_store_n (&g_multi_gpu, n_devices, __ATOMIC_RELAXED);
+}
+
+SMOL_EXPORT void
 smol_cuda_synchronize (void)
 {
     CK (cudaStreamSynchronize ((cudaStream_t) tl_stream));
@@ -1267,6 +1727,8 @@ smol_cuda_scale_images (const void *pixels_in, size_t image_stride_in,
                    with_srgb, NULL, NULL);
     CK (cudaGetDevice (&prev_dev));
     dev = pc_out.device;
+    if (dev < 0 || dev >= SMOL_MAX_DEVICES)
+        smol_fatal ("buffer lives on a device this library cannot use (more than 16 devices?)", NULL);
     if (dev != prev_dev)
         CK (cudaSetDevice (dev));
 
