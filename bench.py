@@ -8,22 +8,31 @@ What is measured
   metric   output Mpix/s (BASELINE.json: "output Mpix/s and achieved HBM GB/s (% of peak)")
   workload BASELINE.json configs[1]: 3840x2160 BGRA8 premultiplied -> 1920x1080 BGRA8 unassociated
            (bilinear, 2:1, unpremultiply in the pack stage).  Other configs: --config cfg1|cfg3|cfg4|cfg5.
-  step     one pass over a batch of FRAMES distinct synthetic frames (default 16 x 33 MB = 531 MB of
-           input, larger than the 126 MB L2, so every launch streams from HBM; no flush needed).
-  value    whole-job output Mpix/s with inputs resident in HBM (device pointers, stream-ordered
-           launches, optionally replayed as one CUDA graph per step).
+  step     PASSES passes over a set of FRAMES distinct synthetic frames (default 16 x 33 MB = 531 MB of
+           input, larger than the 126 MB L2, so every launch streams from HBM; no flush needed).  PASSES is
+           chosen so the timed region (K steps) lasts about half a second: a sustained rate, not a burst.
+  value    whole-job output Mpix/s with inputs resident in HBM (device pointers, one smol_scale_simple
+           per frame, the FRAMES launches captured once as a CUDA graph and replayed).
   e2e      same metric through the public C API with PINNED HOST buffers: every frame is copied
-           host->device, scaled and copied back inside the timed region.
+           host->device, scaled and copied back inside the timed region ("pageable": malloc'd buffers).
   roofline achieved = algorithmic bytes per launch (h_in*w_in*bpp_in + h_out*w_out*bpp_out)
            / average launch duration in the timed region (CUDA events on the launching stream).
   cpu_baseline  the reference's AVX2 build (oracle/_ref, else the plain-C oracle port) on the
            box's host cores, row bands across T threads (test.c:838-883 pattern), bounded sample.
+  direct_launch  the same frames driven by a C loop over smol_scale_simple without a graph
+           (tools/call_overhead, N = 1 only): what a C caller sees per call.
+  multi_gpu  the BASELINE configurations that name a multi-GPU split, at this N: cfg 3 and cfg 4 with every
+           frame's output ROW BANDS sharded across the ranks (strong scaling; each rank holds only its
+           band's source rows + halo, the rest of its copy of the source is poisoned), cfg 5 with 4096
+           thumbnails IMAGE-sharded (smol_cuda_scale_images); each with the gathered result checked
+           against the committed reference digests (tests/golden/digests.json).
 
 Multi-GPU: frames are independent, so ranks shard by frame with no data-path collective
-(weak scaling: every rank processes FRAMES frames per step); value = all frames / max-over-ranks time.
+(weak scaling: every rank processes the same number of frames per step); value = all frames /
+max-over-ranks time.  torch.distributed carries only the barrier, the MAX and the result gathers.
 """
 import argparse
-import ctypes
+import hashlib
 import json
 import os
 import subprocess
@@ -48,6 +57,8 @@ CONFIGS = {
     "cfg4": (RGB8, 1024, 768, RGB8, 4096, 3072, 0, False, 16, "1024x768 RGB8 -> 4096x3072 bilinear upscale"),
     "cfg5": (ARGB8_P, 2048, 2048, ARGB8_P, 256, 256, 0, True, 64, "2048x2048 ARGB8 -> 256x256 thumbnails (batched launch)"),
 }
+GOLDEN_NAME = {"cfg1": "cfg1_1080p_to_540p_rgba_premul_seed0", "cfg2": "cfg2_4k_to_1080p_bgra_p_to_u_seed0",
+               "cfg3": "cfg3_8k_to_800x450_box_srgb_seed0", "cfg4": "cfg4_rgb_1024x768_to_4096x3072_seed0"}
 
 TYPE_NAMES = ["RGBA8_P", "BGRA8_P", "ARGB8_P", "ABGR8_P", "RGBA8_U", "BGRA8_U", "ARGB8_U", "ABGR8_U", "RGB8", "BGR8"]
 
@@ -90,6 +101,11 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def golden_digest(name):
+    with open(os.path.join(ROOT, "tests", "golden", "digests.json")) as f:
+        return json.load(f)["digests"][name]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -106,7 +122,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -114,25 +130,29 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Statistics over the samples taken inside [t0, t1] (all samples if none fall inside)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if t0 is not None and t0 <= t <= t1 + 0.06]
+        lines = inside or [ln for (_, ln) in self.lines]
+        sm, smax, power, reasons = [], [], [], set()
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
                 sm.append(float(f[1]))
                 smax.append(float(f[2]))
+                power.append(float(f[3]))
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
@@ -140,25 +160,38 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(power) if power else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
-def synth_frames_device(torch, cfg, n_frames, seed, device):
-    """n_frames distinct synthetic frames in one device buffer (frame i at i * frame_bytes)."""
+def synth_frames_host(cfg, n_frames, seed):
+    """n_frames distinct synthetic frames, generated on the HOST so that the GPU arm and the reference arm
+    see identical bytes: uniform random, then colour := round(colour * alpha / 255) where the type is
+    premultiplied.  Returns a (n_frames, frame_bytes) uint8 array."""
     ti, wi, hi = cfg[0], cfg[1], cfg[2]
     premul = cfg[7]
     b = bpp(ti)
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    buf = torch.randint(0, 256, (n_frames, hi, wi, b), dtype=torch.uint8, device=device, generator=g)
+    rng = np.random.default_rng([seed, wi, hi, ti])
+    buf = rng.integers(0, 256, size=(n_frames, hi * wi, b), dtype=np.uint8)
     ai = alpha_index(ti)
     if premul and ai is not None:
-        # premultiplied-valid pixels: colour = round(colour * alpha / 255)   (SURVEY 8d)
-        al = buf[..., ai:ai + 1].to(torch.int32)
-        col = (buf.to(torch.int32) * al + 127) // 255
-        col[..., ai:ai + 1] = al
-        buf = col.to(torch.uint8)
-    return buf.contiguous()
+        for f in range(n_frames):
+            px = buf[f]
+            al = px[:, ai].astype(np.uint16)
+            for c in range(4):
+                if c != ai:
+                    px[:, c] = ((px[:, c].astype(np.uint16) * al + 127) // 255).astype(np.uint8)
+    return buf.reshape(n_frames, hi * wi * b)
+
+
+def cfg_config_block(cfg_name, cfg, frames):
+    """The `config` object: identical in the GPU arm and the reference arm."""
+    ti, wi, hi, to, wo, ho, srgb, premul, frames_default, desc = cfg
+    in_bytes, out_bytes = wi * hi * bpp(ti), wo * ho * bpp(to)
+    return {"workload": desc, "config": cfg_name, "types": "%s->%s" % (TYPE_NAMES[ti], TYPE_NAMES[to]), "srgb": srgb,
+            "distinct_frames": frames,
+            "l2": "inputs larger than L2: the step cycles through %d distinct frames = %.0f MB in + %.0f MB out"
+                  % (frames, frames * in_bytes / 1e6, frames * out_bytes / 1e6)}
 
 
 def run_reference_arm(args, cfg_name, cfg, rank, world):
@@ -176,9 +209,9 @@ def run_reference_arm(args, cfg_name, cfg, rank, world):
     else:
         lib_path, kind, label = None, "port", "plain-C oracle port (oracle/liboracle.so), single thread"
     cores = os.cpu_count() or 1
+    distinct = args.frames or frames_default
     frames = args.cpu_frames
-    rng = np.random.default_rng(1)
-    src = rng.integers(0, 256, size=(2, hi * wi * bpp(ti)), dtype=np.uint8)
+    src = synth_frames_host(cfg, distinct, 1234)         # the same frames rank 0 of the GPU arm scales
     out = np.zeros(ho * wo * bpp(to), np.uint8)
 
     def one_step():
@@ -186,17 +219,17 @@ def run_reference_arm(args, cfg_name, cfg, rank, world):
         if lib_path:
             h = run_reference_arm.harness
             for f in range(frames):
-                h.scale_threaded(src[f & 1], ti, wi, hi, wi * bpp(ti), out, to, wo, ho, wo * bpp(to), srgb, cores, 1)
+                h.scale_threaded(src[f % distinct], ti, wi, hi, wi * bpp(ti), out, to, wo, ho, wo * bpp(to), srgb, cores, 1)
         else:
             chk = oracle.restatement()
             for f in range(frames):
-                chk._simple(src[f & 1].ctypes.data, ti, wi, hi, wi * bpp(ti), out.ctypes.data, to, wo, ho,
+                chk._simple(src[f % distinct].ctypes.data, ti, wi, hi, wi * bpp(ti), out.ctypes.data, to, wo, ho,
                             wo * bpp(to), srgb)
         return time.perf_counter() - t0
 
     if lib_path:
         run_reference_arm.harness = oracle.Harness(lib_path)
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         one_step()
     t = sum(one_step() for _ in range(args.steps))
     ms_per_step = t / args.steps * 1e3
@@ -204,33 +237,32 @@ def run_reference_arm(args, cfg_name, cfg, rank, world):
     used = cores if lib_path else 1
     line = {
         "impl": "reference", "metric": "output Mpix/s", "value": round(value, 2), "unit": "Mpix/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": desc, "config": cfg_name, "frames_per_step": frames,
-                   "types": "%s->%s" % (TYPE_NAMES[ti], TYPE_NAMES[to]), "srgb": srgb},
+        "config": cfg_config_block(cfg_name, cfg, distinct),
         "cpu_baseline": {"value": round(value, 2), "unit": "Mpix/s", "cores": used, "kind": kind,
-                         "sample": "%d frames per step, %s, %d row-band threads" % (frames, label, used)},
+                         "sample": "%d frames per step (cycling through the %d distinct frames), %s, %d row-band threads"
+                                   % (frames, distinct, label, used)},
         "e2e": {"value": round(value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_sample(cfg, budget_s=12.0):
+def cpu_baseline_sample(cfg, src, budget_s=12.0):
     """Bounded sample of the same workload on the host cores (rank 0, N=1 only)."""
     import oracle
     ti, wi, hi, to, wo, ho, srgb = cfg[:7]
     avx2_path = os.path.join(ROOT, "oracle", "_ref", "libsmolref_avx2.so")
     cores = os.cpu_count() or 1
-    rng = np.random.default_rng(1)
-    src = rng.integers(0, 256, size=hi * wi * bpp(ti), dtype=np.uint8)
     out = np.zeros(ho * wo * bpp(to), np.uint8)
+    n_src = src.shape[0]
     if os.path.exists(avx2_path):
         h = oracle.Harness(avx2_path)
-        h.scale_threaded(src, ti, wi, hi, wi * bpp(ti), out, to, wo, ho, wo * bpp(to), srgb, cores, 1)
+        h.scale_threaded(src[0], ti, wi, hi, wi * bpp(ti), out, to, wo, ho, wo * bpp(to), srgb, cores, 1)
         n, t0 = 0, time.perf_counter()
         while True:
-            h.scale_threaded(src, ti, wi, hi, wi * bpp(ti), out, to, wo, ho, wo * bpp(to), srgb, cores, 1)
+            h.scale_threaded(src[n % n_src], ti, wi, hi, wi * bpp(ti), out, to, wo, ho, wo * bpp(to), srgb, cores, 1)
             n += 1
             el = time.perf_counter() - t0
             if el * cores > budget_s or n >= 400:
@@ -242,13 +274,207 @@ def cpu_baseline_sample(cfg, budget_s=12.0):
     chk = oracle.restatement()
     n, t0 = 0, time.perf_counter()
     while True:
-        chk._simple(src.ctypes.data, ti, wi, hi, wi * bpp(ti), out.ctypes.data, to, wo, ho, wo * bpp(to), srgb)
+        chk._simple(src[n % n_src].ctypes.data, ti, wi, hi, wi * bpp(ti), out.ctypes.data, to, wo, ho, wo * bpp(to), srgb)
         n += 1
         el = time.perf_counter() - t0
         if el > budget_s or n >= 100:
             break
     return {"value": round(n * wo * ho / 1e6 / el, 2), "unit": "Mpix/s", "cores": 1, "kind": "port",
             "sample": "%d frames, plain-C oracle port, 1 thread, %.2f s wall" % (n, el)}
+
+
+def direct_launch_from_c():
+    """tools/call_overhead: a C loop over smol_scale_simple on device-resident frames, no graph."""
+    exe = os.path.join(ROOT, "tools", "call_overhead")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe, os.path.join(ROOT, "smolscale_b200", "libsmolscale_cuda.so")], capture_output=True,
+                             text=True, timeout=120).stdout
+        return {j["job"]: {"host_us_per_call": j["smol_scale_simple_enqueue_us"], "us_per_frame": j["smol_scale_simple_us_incl_gpu"]}
+                for j in json.loads(out)["jobs"]}
+    except Exception as e:
+        return {"error": str(e)}
+
+
+class Dist:
+    """The little bench.py needs from torch.distributed (nothing on the data path)."""
+
+    def __init__(self, torch, world, device):
+        self.torch, self.world, self.device = torch, world, device
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=device)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+
+    def max(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.device)
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min(self, x):
+        return -self.max(-x)
+
+    def gather_bytes(self, t):
+        """all ranks' equal-sized uint8 tensors, concatenated in rank order"""
+        if not self.dist:
+            return t
+        out = self.torch.empty(self.world * t.numel(), dtype=self.torch.uint8, device=self.device)
+        self.dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def timed_graph(torch, D, stream, enqueue, steps, warmup, passes=1):
+    """Captures enqueue() once, replays it `passes` times per step; returns (ms per step, max over ranks)."""
+    with torch.cuda.stream(stream):
+        enqueue()
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            enqueue()
+        for _ in range(warmup):
+            graph.replay()
+        stream.synchronize()
+        D.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps * passes):
+            graph.replay()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        D.barrier()
+    return D.max(ms) / steps
+
+
+def multi_gpu_row_bands(torch, D, sb, cfg_name, rank, world, device, stream, frames, steps):
+    """cfg3 / cfg4: every frame's output rows split into `world` bands (strong scaling).  Frame 0 is the
+    image of the committed reference digest; each rank keeps ONLY the source rows its band reads
+    (smol_cuda_band_source_rows) -- everything else in its copy of the source is 0xA5 -- and the bands
+    gathered from all ranks must hash to the reference's digest."""
+    import cases
+    from smolscale_b200 import sharding
+    ti, wi, hi, to, wo, ho, srgb, premul, _, desc = CONFIGS[cfg_name]
+    g = golden_digest(GOLDEN_NAME[cfg_name])
+    gti, gwi, ghi, gsi, gto, gwo, gho, gso, gsrgb, gmode, gseed = g["job"]
+    assert (gti, gwi, ghi, gto, gwo, gho, gsrgb) == (ti, wi, hi, to, wo, ho, srgb)
+    si, so = gsi, gso
+    in_bytes, out_bytes = si * hi, so * ho
+    first, n = sharding.row_band(ho, rank, world)
+    per = (ho + world - 1) // world
+
+    ctx = sb.ScaleCtx(None, ti, wi, hi, si, None, to, wo, ho, so, srgb)
+    r0, nr = ctx.band_source_rows(first, n) if n else (0, 0)
+    ctx.destroy()
+
+    d_in = torch.full((frames, in_bytes), 0xA5, dtype=torch.uint8, device=device)
+    golden_src = cases.make_image(ti, wi, hi, si, gmode, gseed)
+    if nr:
+        d_in[0, r0 * si:(r0 + nr) * si] = torch.from_numpy(golden_src[r0 * si:(r0 + nr) * si]).to(device)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(99 + rank)
+        for f in range(1, frames):
+            d_in[f, r0 * si:(r0 + nr) * si] = torch.randint(0, 256, (nr * si,), dtype=torch.uint8, device=device, generator=gen)
+    d_out = torch.zeros((frames, per * so), dtype=torch.uint8, device=device)
+
+    def enqueue():
+        for f in range(frames):
+            c = sb.ScaleCtx(d_in[f].data_ptr(), ti, wi, hi, si, None, to, wo, ho, so, srgb)
+            if n:
+                c.batch_full(d_out[f].data_ptr(), first, n)
+            c.destroy()
+
+    sb.set_stream(stream.cuda_stream)
+    ms = timed_graph(torch, D, stream, enqueue, steps, 3)
+    torch.cuda.synchronize()
+
+    gathered = D.gather_bytes(d_out[0]).cpu().numpy()
+    whole = np.concatenate([gathered[r * per * so: r * per * so + sharding.row_band(ho, r, world)[1] * so] for r in range(world)])
+    ok = hashlib.sha256(whole[:so * (ho - 1) + wo * bpp(to)].tobytes()).hexdigest() == g["sha256"]
+    band_bytes = nr * wi * bpp(ti) + n * wo * bpp(to)
+    us_per_frame = ms * 1e3 / frames
+    rows = D.gather_bytes(torch.tensor([r0, nr, first, n], dtype=torch.int32, device=device).view(torch.uint8))
+    rows = rows.cpu().numpy().view(np.int32).reshape(world, 4)
+    return {
+        "workload": desc, "split": "output row bands, one band per GPU, no collective", "scaling": "strong",
+        "frames_per_step": frames, "steps": steps,
+        "value": round(frames * wo * ho / 1e6 / (ms / 1e3), 2), "unit": "Mpix/s",
+        "us_per_frame": round(us_per_frame, 3),
+        "per_rank_hbm_gbs": round(D.min(band_bytes / (us_per_frame * 1e-6) / 1e9), 1),
+        "band_algorithmic_bytes_this_rank": int(band_bytes),
+        "source_rows_per_rank": [{"rank": int(r), "first": int(a), "count": int(b), "of": hi, "output_rows": [int(c), int(e)]}
+                                 for r, (a, b, c, e) in enumerate(rows)],
+        "rows_outside_the_band": "poisoned with 0xA5 in every rank's copy of the source",
+        "parity": {"gathered_sha256_matches_reference_digest": bool(ok), "digest": GOLDEN_NAME[cfg_name]},
+    }
+
+
+def multi_gpu_thumbnails(torch, D, sb, rank, world, device, stream, n_images, steps, chk):
+    """cfg5 as BASELINE.json states it: n_images (4096) synthetic 2048x2048 ARGB8 images -> 256x256,
+    image-sharded: rank r scales images [r * n / N, (r + 1) * n / N) with smol_cuda_scale_images.
+    Image g is base image (g % 16) rolled down by 8 * (g // 16) rows (all distinct); the base images are
+    the ones of the committed reference digests (seeds 0..2) and 13 more checked against the oracle.
+    An exact 8:1 reduction maps a roll by 8k source rows to a roll by k output rows, which pins EVERY
+    one of the n_images results, on the device, without 4096 oracle runs."""
+    import cases
+    from smolscale_b200 import sharding
+    ti, wi, hi, to, wo, ho, srgb, premul, _, desc = CONFIGS["cfg5"]
+    si, so = wi * 4, wo * 4
+    in_bytes, out_bytes = si * hi, so * ho
+    n_base = 16
+    first, n = sharding.image_shard(n_images, rank, world)
+
+    base_host = [cases.make_image(ti, wi, hi, si, "premul", seed=s) for s in range(n_base)]
+    base = torch.stack([torch.from_numpy(b) for b in base_host]).to(device).view(n_base, hi, si)
+    d_in = torch.empty((n, hi, si), dtype=torch.uint8, device=device)
+    for i in range(n):
+        g = first + i
+        d_in[i] = torch.roll(base[g % n_base], shifts=(8 * (g // n_base)) % hi, dims=0)
+    d_out = torch.zeros((n, ho, so), dtype=torch.uint8, device=device)
+
+    def enqueue():
+        sb.scale_images(d_in.data_ptr(), in_bytes, ti, wi, hi, si, d_out.data_ptr(), out_bytes, to, wo, ho, so, srgb, n)
+
+    sb.set_stream(stream.cuda_stream)
+    ms = timed_graph(torch, D, stream, enqueue, steps, 3)
+    torch.cuda.synchronize()
+
+    # expected results: the oracle on the 16 base images (3 of them also pinned by committed digests)
+    want_base = [chk.scale_simple(b, ti, wi, hi, si, to, wo, ho, so, srgb) for b in base_host]
+    digests_ok = all(hashlib.sha256(want_base[s].tobytes()).hexdigest() ==
+                     golden_digest("cfg5_2048sq_to_256sq_argb_seed%d" % s)["sha256"] for s in range(3))
+    wb = torch.stack([torch.from_numpy(w) for w in want_base]).to(device).view(n_base, ho, so)
+    bad = 0
+    for i in range(n):
+        g = first + i
+        bad += int(not torch.equal(d_out[i], torch.roll(wb[g % n_base], shifts=(g // n_base) % ho, dims=0)))
+    checksum = int(d_out.view(-1).to(torch.int64).sum().item())
+    all_bad = D.max(float(bad))
+    sums = D.gather_bytes(torch.tensor([checksum], dtype=torch.int64, device=device).view(torch.uint8)).cpu().numpy().view(np.int64)
+    alg = n * (in_bytes + out_bytes)
+    return {
+        "workload": "%d synthetic 2048x2048 ARGB8 images -> 256x256 thumbnails" % n_images,
+        "split": "by image: %d per GPU, one smol_cuda_scale_images launch per rank and step, no collective" % n,
+        "scaling": "strong", "images": n_images, "steps": steps,
+        "value": round(n_images * wo * ho / 1e6 / (ms / 1e3), 2), "unit": "Mpix/s",
+        "ms_per_pass": round(ms, 4),
+        "per_rank_hbm_gbs": round(D.min(alg / (ms * 1e-3) / 1e9), 1),
+        "parity": {"images_checked": n_images, "mismatching_images_max_over_ranks": int(all_bad),
+                   "oracle_matches_reference_digests_seed0_2": bool(digests_ok),
+                   "all_results_pinned": bool(all_bad == 0 and digests_ok),
+                   "sum_of_output_bytes_all_ranks": int(sums.sum())},
+    }
 
 
 def main():
@@ -258,19 +484,26 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
-    ap.add_argument("--frames", type=int, default=0, help="frames per step (0 = config default)")
+    ap.add_argument("--frames", type=int, default=0, help="distinct frames the step cycles through (0 = config default)")
+    ap.add_argument("--passes", type=int, default=0,
+                    help="passes over the frames per step (0 = as many as make the timed region last ~0.5 s)")
     ap.add_argument("--cpu-frames", type=int, default=24, help="--impl reference: frames per step")
     ap.add_argument("--no-graph", action="store_true", help="launch directly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-multi-gpu", action="store_true", help="skip the cfg3 / cfg4 / cfg5 multi_gpu section")
+    ap.add_argument("--quick", action="store_true", help="device-resident figure only (kernel experiments)")
+    ap.add_argument("--thumbnails", type=int, default=4096, help="images in the multi_gpu cfg5 run")
     ap.add_argument("--kernel", type=int, default=0, help="force a kernel family (testing)")
     ap.add_argument("--e2e-threads", type=int, default=3, help="caller threads of the end-to-end (host memory) leg")
     ap.add_argument("--shard", default="frames", choices=["frames", "rows"],
-                    help="multi-GPU partitioning: frames (weak scaling, default) or output row bands of every "
-                         "frame (strong scaling; BASELINE configs 3 and 4)")
+                    help="multi-GPU partitioning of the main workload: frames (weak scaling, default) or output row "
+                         "bands of every frame (strong scaling)")
     ap.add_argument("--batched", action="store_true",
-                    help="submit all frames of a step in one launch (smol_cuda_scale_images); default for cfg5")
+                    help="submit all frames of a pass in one launch (smol_cuda_scale_images); default for cfg5")
     args = ap.parse_args()
+    if args.quick:
+        args.no_e2e = args.no_multi_gpu = args.no_cpu_baseline = True
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -283,15 +516,14 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
     import smolscale_b200 as sb
 
     if not torch.cuda.is_available() or sb.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    D = Dist(torch, world, device)
+    warmup = max(args.warmup, 3)
 
     ti, wi, hi, to, wo, ho, srgb, premul, frames_default, desc = cfg
     frames = args.frames or frames_default
@@ -299,7 +531,8 @@ def main():
     in_bytes, out_bytes = si * hi, so * ho
     alg_bytes = in_bytes + out_bytes
 
-    d_in = synth_frames_device(torch, cfg, frames, 1234 + rank, device).view(-1)
+    h_src = synth_frames_host(cfg, frames, 1234 + rank)
+    d_in = torch.from_numpy(h_src).to(device).view(-1)
     d_out = torch.zeros(frames * out_bytes, dtype=torch.uint8, device=device)
     if args.kernel:
         sb.force_kernel(args.kernel)
@@ -310,10 +543,8 @@ def main():
     from smolscale_b200 import sharding
     band_first, band_rows = sharding.row_band(ho, rank, world) if args.shard == "rows" else (0, ho)
 
-    def enqueue_step():
+    def enqueue_pass():
         if args.shard == "rows":
-            # every rank renders its own output row band of every frame (smol_scale_batch_full on a
-            # shared-geometry context); it reads only that band's source rows + filter halo
             for f in range(frames):
                 ctx = sb.ScaleCtx(d_in.data_ptr() + f * in_bytes, ti, wi, hi, si, None, to, wo, ho, so, srgb)
                 ctx.batch_full(d_out.data_ptr() + f * out_bytes + band_first * so, band_first, band_rows)
@@ -328,83 +559,101 @@ def main():
 
     with torch.cuda.stream(stream):
         sb.set_stream(stream.cuda_stream)
-        enqueue_step()                      # first touch: table upload, module load
+        enqueue_pass()                      # first touch: table upload, module load
         stream.synchronize()
         graph = None
         if not args.no_graph:
             try:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=stream):
-                    enqueue_step()
+                    enqueue_pass()
             except Exception as e:          # fall back to direct launches
                 sys.stderr.write("bench: CUDA graph capture unavailable (%s); launching directly\n" % (e,))
                 graph = None
                 torch.cuda.synchronize()
         sb.set_stream(stream.cuda_stream)
 
-        def step():
+        def one_pass():
             if graph is not None:
                 graph.replay()
             else:
-                enqueue_step()
+                enqueue_pass()
 
-        for _ in range(max(args.warmup, 3)):
+        # how many passes make a step long enough for a sustained figure (~0.5 s over the K timed steps)
+        passes = args.passes
+        if passes <= 0:
+            for _ in range(3):
+                one_pass()
+            stream.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(8):
+                one_pass()
+            e1.record(stream)
+            stream.synchronize()
+            pass_ms = D.max(e0.elapsed_time(e1) / 8)
+            passes = int(min(4096, max(1, round(500.0 / max(args.steps, 1) / max(pass_ms, 1e-3)))))
+
+        def step():
+            for _ in range(passes):
+                one_pass()
+
+        for _ in range(warmup):
             step()
         stream.synchronize()
 
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        if world > 1:
-            dist.barrier()
+            time.sleep(0.06)
+        D.barrier()
         torch.cuda.synchronize()
         sb.reset_stats()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.perf_counter()
         ev0.record(stream)
         for _ in range(args.steps):
             step()
         ev1.record(stream)
         torch.cuda.synchronize()
+        t_wall1 = time.perf_counter()
         elapsed_ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            dist.barrier()
-        clocks = sampler.stop() if rank == 0 else None
+        D.barrier()
+        clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
         launches_direct = sb.stats()["kernel_launches"]
 
-    launches_per_step = 1 if batched else frames
+    launches_per_pass = 1 if batched else frames
     # launches counted by the library when launching directly; when a graph replays them the
     # library is not re-entered, so count what the graph contains
-    gpu_launches = launches_direct if graph is None else launches_per_step * args.steps
+    gpu_launches = launches_direct if graph is None else launches_per_pass * passes * args.steps
 
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+    elapsed_ms = D.max(elapsed_ms)
     ms_per_step = elapsed_ms / args.steps
     strong = args.shard == "rows"
-    value = (1 if strong else world) * frames * wo * ho / 1e6 / (ms_per_step / 1e3)
+    value = (1 if strong else world) * frames * passes * wo * ho / 1e6 / (ms_per_step / 1e3)
 
-    # ---- correctness guard: one frame of the timed output against the oracle (rank 0) ----
+    # ---- correctness guard: rows of the timed output against the oracle (rank 0) ----
     check = None
+    chk = None
     if rank == 0:
         try:
             import oracle
+            chk = oracle.restatement()
             f = frames - 1
-            src = d_in[f * in_bytes:(f + 1) * in_bytes].cpu().numpy()
             got = d_out[f * out_bytes:(f + 1) * out_bytes].cpu().numpy()
             y0 = band_first + band_rows // 2
             rows = min(4, band_first + band_rows - y0)
-            want = oracle.restatement().scale_rows(src, ti, wi, hi, si, to, wo, ho, y0, rows, so, srgb)
+            want = chk.scale_rows(h_src[f], ti, wi, hi, si, to, wo, ho, y0, rows, so, srgb)
             check = bool(np.array_equal(want, got[y0 * so:y0 * so + want.size]))
         except Exception as e:
             check = "unchecked: %s" % (e,)
 
-    # ---- end to end through the public API with pinned host buffers ----
+    # ---- end to end through the public API with host buffers ----
     e2e = None
     if not args.no_e2e:
         e2e_frames = min(frames, 8)
         h_in = torch.empty(e2e_frames * in_bytes, dtype=torch.uint8).pin_memory()
-        h_in.copy_(d_in[:e2e_frames * in_bytes])
+        h_in.copy_(torch.from_numpy(h_src[:e2e_frames]).view(-1))
         h_out = torch.zeros(e2e_frames * out_bytes, dtype=torch.uint8).pin_memory()
         sb.set_device(local_rank)
 
@@ -415,63 +664,91 @@ def main():
         import concurrent.futures
         pool = concurrent.futures.ThreadPoolExecutor(max_workers=args.e2e_threads)
 
-        def e2e_one(f):
-            sb.set_device(local_rank)
-            sb.scale_simple(h_in.data_ptr() + f * in_bytes, ti, wi, hi, si,
-                            h_out.data_ptr() + f * out_bytes, to, wo, ho, so, srgb)
+        def run_e2e(src_ptr, dst_ptr, barrier=True):
+            def one(f):
+                sb.set_device(local_rank)
+                sb.scale_simple(src_ptr + f * in_bytes, ti, wi, hi, si, dst_ptr + f * out_bytes, to, wo, ho, so, srgb)
 
-        def e2e_step():
-            list(pool.map(e2e_one, range(e2e_frames)))
+            def e2e_step():
+                list(pool.map(one, range(e2e_frames)))
 
-        for _ in range(2):
-            e2e_step()
-        if world > 1:
-            dist.barrier()
-        k = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(k):
-            e2e_step()
-        e2e_s = time.perf_counter() - t0
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
-        e2e = {"value": round(world * k * e2e_frames * wo * ho / 1e6 / e2e_s, 2), "unit": "Mpix/s",
+            for _ in range(2):
+                e2e_step()
+            if barrier:
+                D.barrier()
+            k = max(3, min(args.steps, 10))
+            t0 = time.perf_counter()
+            for _ in range(k):
+                e2e_step()
+            s = D.max(time.perf_counter() - t0)
+            return world * k * e2e_frames * wo * ho / 1e6 / s
+
+        v_pinned = run_e2e(h_in.data_ptr(), h_out.data_ptr())
+        e2e = {"value": round(v_pinned, 2), "unit": "Mpix/s",
                "h2d_bytes_per_step": e2e_frames * in_bytes, "d2h_bytes_per_step": e2e_frames * out_bytes,
                "frames_per_step": e2e_frames,
                "api": "smol_scale_simple, pinned host pointers, synchronous calls from %d caller threads" % args.e2e_threads}
         if rank == 0 and check is True:
             same = torch.equal(h_out[:out_bytes].to(device), d_out[:out_bytes])
             e2e["matches_device_path"] = bool(same)
+        # what an unmodified reference caller passes: malloc'd (pageable) buffers, bounced through the
+        # library's pinned ring by its worker pool
+        p_in = np.ascontiguousarray(h_src[:e2e_frames]).reshape(-1)
+        p_out = np.zeros(e2e_frames * out_bytes, np.uint8)
+        v_pageable = run_e2e(p_in.ctypes.data, p_out.ctypes.data)
+        e2e["pageable"] = {"value": round(v_pageable, 2), "unit": "Mpix/s",
+                           "api": "same calls on malloc'd buffers (what verify.c / test.c pass)",
+                           "matches_pinned_result": bool(np.array_equal(p_out, h_out.numpy()))}
+        pool.shutdown()
+
+    # ---- the BASELINE configurations that name a multi-GPU split, at this N ----
+    multi = None
+    if not args.no_multi_gpu and not args.kernel:
+        del d_in, d_out
+        torch.cuda.empty_cache()
+        try:
+            if chk is None:
+                import oracle
+                chk = oracle.restatement()
+            multi = {"n_gpus": world,
+                     "cfg3_row_bands": multi_gpu_row_bands(torch, D, sb, "cfg3", rank, world, device, stream, 4, 10),
+                     "cfg4_row_bands": multi_gpu_row_bands(torch, D, sb, "cfg4", rank, world, device, stream, 16, 10),
+                     "cfg5_image_shards": multi_gpu_thumbnails(torch, D, sb, rank, world, device, stream,
+                                                               args.thumbnails, 3, chk)}
+            if world >= 8:
+                multi["note"] = ("cfg4 at 8 GPUs is ~5 MB per GPU and frame: sub-microsecond of DRAM time, so the figure "
+                                 "is the throughput of a queue of frames, not the latency of one")
+        except Exception as e:          # never lose the headline line to the side measurements
+            multi = {"error": "%s: %s" % (type(e).__name__, e)}
+        sb.set_stream(None)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        D.close()
         return
 
     peak, peak_src = measured_peak_gbs()
-    kernel_ms = elapsed_ms / (args.steps * launches_per_step)
+    kernel_ms = elapsed_ms / (args.steps * passes * launches_per_pass)
     alg_per_launch = alg_bytes * (frames if batched else 1)
     if strong:
         alg_per_launch = alg_bytes / world
     achieved = alg_per_launch / (kernel_ms * 1e-3) / 1e9
     plan = sb.plan_query(ti, wi, hi, to, wo, ho, srgb)
-    traffic, traffic_src = ncu_traffic_bytes(cfg_name)
-    if traffic is not None and batched:
-        traffic = None      # the capture is of the per-frame launch
+    traffic, traffic_src = ncu_traffic_bytes(cfg_name + ("_batched" if batched and cfg_name != "cfg5" else ""))
 
+    config = cfg_config_block(cfg_name, cfg, frames)
     line = {
         "metric": "output Mpix/s", "value": round(value, 2), "unit": "Mpix/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5),
+        "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms_per_step, 5),
         "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": desc, "config": cfg_name, "frames_per_step_per_gpu": frames,
-                   "types": "%s->%s" % (TYPE_NAMES[ti], TYPE_NAMES[to]), "srgb": srgb,
-                   "l2": "inputs larger than L2: %d distinct frames = %.0f MB in + %.0f MB out per step"
-                         % (frames, frames * in_bytes / 1e6, frames * out_bytes / 1e6),
-                   "launch": "cuda graph replay" if graph is not None else "direct stream-ordered launches",
-                   "kernel": plan["kernel_name"], "parallelism": ("output row bands of every frame sharded across %d GPU(s), no collective" if strong
-                                   else "frames sharded across %d GPU(s), no collective") % world},
+        "config": config,
+        "run": {"passes_per_step": passes, "frames_per_step_per_gpu": frames * passes,
+                "timed_region_s": round(elapsed_ms / 1e3, 4),
+                "launch": "cuda graph of %d launches, replayed %d times per step" % (launches_per_pass, passes)
+                          if graph is not None else "direct stream-ordered launches",
+                "kernel": plan["kernel_name"],
+                "parallelism": ("output row bands of every frame sharded across %d GPU(s), no collective" if strong
+                                else "frames sharded across %d GPU(s), no collective") % world},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src,
@@ -481,14 +758,18 @@ def main():
         "clocks": clocks,
         "parity_spot_check": check,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            line["cpu_baseline"] = cpu_baseline_sample(cfg)
-        except Exception as e:
-            line["cpu_baseline"] = {"value": None, "unit": "Mpix/s", "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+    if multi is not None:
+        line["multi_gpu"] = multi
+    if world == 1:
+        if not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline_sample(cfg, h_src)
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "Mpix/s", "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+        if not args.quick:
+            line["direct_launch"] = direct_launch_from_c()
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 if __name__ == "__main__":

@@ -897,6 +897,112 @@ smol_half_kernel (const HalfParams P)
     }
 }
 
+/* 2:1 on both axes (BASELINE cfg 1, 2) with 32-byte-aligned source rows: the same arithmetic as
+ * smol_half_kernel<0, 0, PACK> on 256-bit loads.  A thread's four output pixels are eight source
+ * pixels = ONE 32-byte sector per source row, so a warp instruction reads 1 KB of contiguous
+ * bytes with every sector requested exactly once (the 128-bit form touches each sector from two
+ * instructions, and with L1 allocation off both go to L2).  A thread walks ROWS output rows with
+ * all its loads issued up front (ROWS x 64 bytes in flight); the per-CTA set-up -- staging the
+ * inverse-division table with a few vector loads, the PDL prologue -- is spread over ROWS times
+ * as much output.  Fewer, wider instructions per byte also matter for the sustained rate: under
+ * a long run the board is power-limited and SM clocks drop with issue activity. */
+__device__ __forceinline__ void ldg_nc_v8 (const void *p, uint4 &lo, uint4 &hi)
+{
+    asm volatile ("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                  : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
+}
+
+template <int PACK, int ROWS>
+__global__ void __launch_bounds__ (256)
+smol_half2v_kernel (const HalfParams P)
+{
+    __shared__ __align__ (16) uint32_t sm_inv[256];
+
+    pdl_launch_dependents ();
+    const uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x;                  /* group of 4 output pixels */
+    const uint32_t yl0 = (blockIdx.y * blockDim.y + threadIdx.y) * ROWS;        /* first of this thread's output rows */
+    const bool full = xi * 4 + 4 <= P.w_out;
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride
+                         + (size_t) (2 * (P.first_row + yl0)) * P.src_pitch + (size_t) xi * 32;
+
+    if (P.prefetch && xi * 4 < P.w_out && (threadIdx.x & 3) == 0 && in_first_wave (P.prefetch))
+    {
+        /* L2 prefetch ahead of the dependency wait (see prefetch_l2), one lane per 128-byte line */
+#pragma unroll
+        for (int r = 0; r < 2 * ROWS; r++)
+            if (yl0 + r / 2 < P.n_rows)
+                prefetch_l2 (src + (size_t) r * P.src_pitch);
+    }
+    if constexpr (PACK != 0)
+    {
+        /* library-owned constant data: safe to read before the dependency wait */
+        const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
+        if (t < 64)
+        {
+            uint4 v = __ldg (reinterpret_cast<const uint4 *> (P.inv_div_p8) + t);
+            v.x <<= 3; v.y <<= 3; v.z <<= 3; v.w <<= 3;
+            reinterpret_cast<uint4 *> (sm_inv)[t] = v;
+        }
+        __syncthreads ();
+    }
+    pdl_wait ();
+    if (xi * 4 >= P.w_out || yl0 >= P.n_rows)
+        return;
+
+    uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl0 * P.dst_pitch + (size_t) xi * 16;
+
+    if (full)
+    {
+        uint4 a_lo[ROWS], a_hi[ROWS], b_lo[ROWS], b_hi[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; r++)
+            if (yl0 + r < P.n_rows)
+            {
+                ldg_nc_v8 (src + (size_t) (2 * r) * P.src_pitch, a_lo[r], a_hi[r]);
+                ldg_nc_v8 (src + (size_t) (2 * r + 1) * P.src_pitch, b_lo[r], b_hi[r]);
+            }
+#pragma unroll
+        for (int r = 0; r < ROWS; r++)
+            if (yl0 + r < P.n_rows)
+            {
+                uint32_t out[4];
+                out[0] = byte_avg_floor (byte_avg_floor (a_lo[r].x, a_lo[r].y), byte_avg_floor (b_lo[r].x, b_lo[r].y));
+                out[1] = byte_avg_floor (byte_avg_floor (a_lo[r].z, a_lo[r].w), byte_avg_floor (b_lo[r].z, b_lo[r].w));
+                out[2] = byte_avg_floor (byte_avg_floor (a_hi[r].x, a_hi[r].y), byte_avg_floor (b_hi[r].x, b_hi[r].y));
+                out[3] = byte_avg_floor (byte_avg_floor (a_hi[r].z, a_hi[r].w), byte_avg_floor (b_hi[r].z, b_hi[r].w));
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+                {
+                    uint32_t v = out[o];
+                    if constexpr (PACK == 1)
+                        v = half_unpremul<false> (v, sm_inv);
+                    else if constexpr (PACK == 2)
+                        v = half_unpremul<true> (v, sm_inv);
+                    out[o] = __byte_perm (v, 0, P.prmt_sel);
+                }
+                *reinterpret_cast<uint4 *> (dst + (size_t) r * P.dst_pitch) = make_uint4 (out[0], out[1], out[2], out[3]);
+            }
+    }
+    else
+    {
+        /* ragged end of a row: one pixel at a time, same arithmetic */
+        const uint32_t n_px = P.w_out - xi * 4;
+        for (int r = 0; r < ROWS && yl0 + r < P.n_rows; r++)
+            for (uint32_t o = 0; o < n_px; o++)
+            {
+                const uint32_t *row0 = reinterpret_cast<const uint32_t *> (src + (size_t) (2 * r) * P.src_pitch) + 2 * o;
+                const uint32_t *row1 = reinterpret_cast<const uint32_t *> (src + (size_t) (2 * r + 1) * P.src_pitch) + 2 * o;
+                uint32_t v = byte_avg_floor (byte_avg_floor (__ldg (row0), __ldg (row0 + 1)),
+                                             byte_avg_floor (__ldg (row1), __ldg (row1 + 1)));
+                if constexpr (PACK == 1)
+                    v = half_unpremul<false> (v, sm_inv);
+                else if constexpr (PACK == 2)
+                    v = half_unpremul<true> (v, sm_inv);
+                reinterpret_cast<uint32_t *> (dst + (size_t) r * P.dst_pitch)[o] = __byte_perm (v, 0, P.prmt_sel);
+            }
+    }
+}
+
 /* Variant for 4:1 and 8:1 horizontal reductions (HH = 1, 2).  Here one output pixel spans 16 or
  * 32 source bytes per row, so the thread <-> data mapping is chosen for the loads: lane L of a
  * warp reads the L-th 16-byte chunk of the row segment (perfectly coalesced 512 bytes per
@@ -3525,6 +3631,20 @@ launch_half_hv (const HalfParams &P, int pack, dim3 grid, dim3 block, cudaStream
     }
 }
 
+/* rows per thread of the 256-bit 2:1 kernel (SMOL_HALF2V_ROWS: 0 = use the 128-bit kernel) */
+static int
+half2v_rows ()
+{
+    static int rows = -1;
+    if (rows < 0)
+    {
+        const char *e = getenv ("SMOL_HALF2V_ROWS");
+        const int r = e ? atoi (e) : 1;
+        rows = r <= 0 ? 0 : r == 1 ? 1 : r < 4 ? 2 : 4;
+    }
+    return rows;
+}
+
 static cudaError_t
 launch_half (const SmolLaunch &L, cudaStream_t stream)
 {
@@ -3582,6 +3702,41 @@ launch_half (const SmolLaunch &L, cudaStream_t stream)
     P.prefetch = pdl_first_wave (bx * by, pack ? 1024 : 0);
     if (pack && P.prefetch)
         P.prefetch = 0xffffffffu;
+
+    if (d.h_halvings == 0 && d.v_halvings == 0 && half2v_rows () > 0
+        && (reinterpret_cast<uintptr_t> (L.src) & 31) == 0 && (L.src_pitch & 31) == 0 && (L.src_image_stride & 31) == 0)
+    {
+        /* 256-bit loads, several rows per thread (see smol_half2v_kernel) */
+        const uint32_t rows = (uint32_t) half2v_rows ();
+        const uint32_t n_y = (L.n_rows + rows - 1) / rows;
+        static int tune_threads = -1, tune_pf = -1;
+        if (tune_threads < 0)
+        {
+            const char *e = getenv ("SMOL_HALF2V_THREADS"), *f = getenv ("SMOL_HALF2V_PF");
+            tune_pf = f ? atoi (f) : 1;
+            tune_threads = e ? atoi (e) : 256;
+        }
+        uint32_t vbx = 32, vwaste = 0xffffffffu;
+        for (uint32_t cand = (uint32_t) tune_threads; cand >= 32; cand -= 32)
+        {
+            const uint32_t waste = (n_x + cand - 1) / cand * cand - n_x;
+            if (waste < vwaste)
+            {
+                vwaste = waste;
+                vbx = cand;
+            }
+        }
+        uint32_t vy = (uint32_t) tune_threads / vbx;
+        if (vy > n_y)
+            vy = n_y;
+        dim3 vblock (vbx, vy), vgrid ((n_x + vbx - 1) / vbx, (n_y + vy - 1) / vy, L.n_images);
+        P.prefetch = tune_pf == 0 ? 0 : tune_pf == 2 ? 0xffffffffu : pdl_first_wave (vbx * vy, pack ? 1024 : 0);
+#define HALF2V(PK) (rows == 1 ? launch_pdl (smol_half2v_kernel<PK, 1>, P, vgrid, vblock, 0, stream) \
+                    : rows == 2 ? launch_pdl (smol_half2v_kernel<PK, 2>, P, vgrid, vblock, 0, stream) \
+                    : launch_pdl (smol_half2v_kernel<PK, 4>, P, vgrid, vblock, 0, stream))
+        return pack == 1 ? HALF2V (1) : pack == 2 ? HALF2V (2) : HALF2V (0);
+#undef HALF2V
+    }
 
     switch (d.h_halvings * 3 + d.v_halvings)
     {

@@ -1163,13 +1163,41 @@ row_copy_task (void *arg)
             memcpy (c->dst + r * c->dpitch, c->src + r * c->spitch, c->width_bytes);
 }
 
-/* Host-to-host row copy spread over the pool (about 1 MB per task). */
+static long
+env_long (const char *name, long dflt)
+{
+    const char *e = getenv (name);
+
+    return e && *e ? atol (e) : dflt;
+}
+
+/* Tunables of the pageable-memory path (environment, read once): SMOL_CUDA_BOUNCE=0 hands
+ * pageable pointers straight to cudaMemcpyAsync (the driver's own staging) instead of the pinned
+ * bounce buffers; _BAND_KB / _TASK_KB set the pipeline's band size and the host-copy task size. */
+static int g_bounce = -1;
+static size_t g_bounce_band, g_bounce_task;
+
+static void
+bounce_config (void)
+{
+    if (__atomic_load_n (&g_bounce, __ATOMIC_ACQUIRE) >= 0)
+        return;
+    g_bounce_band = (size_t) env_long ("SMOL_CUDA_BOUNCE_BAND_KB", 4096) << 10;
+    g_bounce_task = (size_t) env_long ("SMOL_CUDA_BOUNCE_TASK_KB", 512) << 10;
+    if (g_bounce_band < 65536)
+        g_bounce_band = 65536;
+    if (g_bounce_task < 16384)
+        g_bounce_task = 16384;
+    __atomic_store_n (&g_bounce, env_long ("SMOL_CUDA_BOUNCE", 1) != 0, __ATOMIC_RELEASE);
+}
+
+/* Host-to-host row copy spread over the pool. */
 static void
 copy_rows_host (void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t n_rows)
 {
     RowCopy parts[SMOL_POOL_MAX];
     size_t total = width_bytes * n_rows, per, r;
-    int n = (int) (total >> 20), i;
+    int n = (int) (total / g_bounce_task), i;
 
     if (n_rows == 0 || width_bytes == 0)
         return;
@@ -1227,8 +1255,8 @@ render_staged (SmolScaleCtx *ctx, int dev, void *outrows_dest, uint32_t first_ro
     const size_t in_row_bytes = (size_t) d->w_in * d->bpp_in;
     const size_t out_row_bytes = (size_t) d->w_out * d->bpp_out;
     const size_t in_pitch = align16 (in_row_bytes), out_pitch = align16 (out_row_bytes);
-    const int bounce_in = !pc_in.is_device && pc_in.mem == SMOL_MEM_PAGEABLE;
-    const int bounce_out = !pc_out.is_device && pc_out.mem == SMOL_MEM_PAGEABLE;
+    const int bounce_in = (bounce_config (), g_bounce) && !pc_in.is_device && pc_in.mem == SMOL_MEM_PAGEABLE;
+    const int bounce_out = g_bounce && !pc_out.is_device && pc_out.mem == SMOL_MEM_PAGEABLE;
     SmolLaunch L;
     Lane *lane;
     cudaStream_t s;
@@ -1291,7 +1319,7 @@ render_staged (SmolScaleCtx *ctx, int dev, void *outrows_dest, uint32_t first_ro
      * copies overlap the transfers too. */
     if (staged_bytes >= ((size_t) 4 << 20) && n_rows >= 2 * SMOL_MAX_BANDS)
     {
-        n_bands = (uint32_t) (staged_bytes >> ((bounce_in || bounce_out) ? 21 : 22));
+        n_bands = (uint32_t) ((bounce_in || bounce_out) ? staged_bytes / g_bounce_band : staged_bytes >> 22);
         if (n_bands > ((bounce_in || bounce_out) ? SMOL_MAX_BANDS : SMOL_MAX_BANDS / 2))
             n_bands = (bounce_in || bounce_out) ? SMOL_MAX_BANDS : SMOL_MAX_BANDS / 2;
         if (n_bands < 2)

@@ -114,7 +114,16 @@ static void timeit (const char *name, double bytes, int reps, F f, bool last = f
     }
     CK (cudaGetLastError ());
     std::sort (ms.begin (), ms.end ());
-    printf ("  \"%s\": {\"best_gbs\": %.1f, \"median_gbs\": %.1f}%s\n", name, bytes / ms[0] / 1e6, bytes / ms[ms.size () / 2] / 1e6, last ? "" : ",");
+    /* sustained: back to back for about half a second (power / clock limits show up here, not in a burst) */
+    int n = (int) (500.0f / ms[ms.size () / 2]) + 1;
+    float t;
+    CK (cudaEventRecord (e0));
+    for (int r = 0; r < n; r++)
+        f ();
+    CK (cudaEventRecord (e1)); CK (cudaEventSynchronize (e1));
+    CK (cudaEventElapsedTime (&t, e0, e1));
+    printf ("  \"%s\": {\"best_gbs\": %.1f, \"median_gbs\": %.1f, \"sustained_gbs\": %.1f, \"sustained_ms\": %.0f}%s\n", name,
+            bytes / ms[0] / 1e6, bytes / ms[ms.size () / 2] / 1e6, bytes * n / t / 1e6, t, last ? "" : ",");
     fflush (stdout);
 }
 
