@@ -725,10 +725,49 @@ __device__ __forceinline__ uint32_t half_hreduce (const uint32_t *px)
     }
 }
 
+/* AL: what the buffers are aligned to -- 16 bytes (the fast case), 8 (a tightly packed 32bpp image
+ * with an odd number of output columns) or 4 (views into larger images): 16-byte accesses become
+ * two 64-bit or four 32-bit ones.  The narrow loads allocate in L1 -- a warp still covers a
+ * contiguous run of the row, each sector is fetched from L2 once and its other words hit L1. */
+template <int AL>
+__device__ __forceinline__ uint4 half_load16 (const uint8_t *p)
+{
+    if constexpr (AL == 4)
+    {
+        const uint32_t *w = reinterpret_cast<const uint32_t *> (p);
+        return make_uint4 (__ldg (w), __ldg (w + 1), __ldg (w + 2), __ldg (w + 3));
+    }
+    else if constexpr (AL == 8)
+    {
+        const uint2 *w = reinterpret_cast<const uint2 *> (p);
+        const uint2 a = __ldg (w), b = __ldg (w + 1);
+        return make_uint4 (a.x, a.y, b.x, b.y);
+    }
+    else
+        return ldg_nc_v4 (p);
+}
+
+template <int AL>
+__device__ __forceinline__ void half_store16 (uint8_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    if constexpr (AL == 4)
+    {
+        uint32_t *w = reinterpret_cast<uint32_t *> (p);
+        w[0] = a; w[1] = b; w[2] = c; w[3] = d;
+    }
+    else if constexpr (AL == 8)
+    {
+        uint2 *w = reinterpret_cast<uint2 *> (p);
+        w[0] = make_uint2 (a, b); w[1] = make_uint2 (c, d);
+    }
+    else
+        *reinterpret_cast<uint4 *> (p) = make_uint4 (a, b, c, d);
+}
+
 /* PACK: 0 = byte permutation only, 1 = unpremultiply with alpha in byte 3, 2 = ... in byte 0.
  * Block = (bx, by) threads; thread (tx, ty) of CTA (cx, cy, image) produces output pixels
  * 4 * (cx * bx + tx) .. + 3 of output row first_row + cy * by + ty. */
-template <int HH, int VH, int PACK>
+template <int HH, int VH, int PACK, int AL>
 __global__ void __launch_bounds__ (256)
 smol_half_kernel (const HalfParams P)
 {
@@ -787,8 +826,8 @@ smol_half_kernel (const HalfParams P)
             if constexpr (HH == 0)
             {
                 /* 4 output pixels = 8 source pixels = two 128-bit loads per row */
-                const uint4 a0 = ldg_nc_v4 (row0), a1 = ldg_nc_v4 (row0 + 16);
-                const uint4 b0 = ldg_nc_v4 (row1), b1 = ldg_nc_v4 (row1 + 16);
+                const uint4 a0 = half_load16<AL> (row0), a1 = half_load16<AL> (row0 + 16);
+                const uint4 b0 = half_load16<AL> (row1), b1 = half_load16<AL> (row1 + 16);
                 h0[0] = byte_avg_floor (a0.x, a0.y); h0[1] = byte_avg_floor (a0.z, a0.w);
                 h0[2] = byte_avg_floor (a1.x, a1.y); h0[3] = byte_avg_floor (a1.z, a1.w);
                 h1[0] = byte_avg_floor (b0.x, b0.y); h1[1] = byte_avg_floor (b0.z, b0.w);
@@ -803,8 +842,8 @@ smol_half_kernel (const HalfParams P)
 #pragma unroll
                     for (int v = 0; v < VEC_PER_OUT; v++)
                     {
-                        const uint4 a = __ldg (reinterpret_cast<const uint4 *> (row0) + o * VEC_PER_OUT + v);
-                        const uint4 b = __ldg (reinterpret_cast<const uint4 *> (row1) + o * VEC_PER_OUT + v);
+                        const uint4 a = half_load16<AL> (row0 + 16 * (o * VEC_PER_OUT + v));
+                        const uint4 b = half_load16<AL> (row1 + 16 * (o * VEC_PER_OUT + v));
                         pa[4 * v] = a.x; pa[4 * v + 1] = a.y; pa[4 * v + 2] = a.z; pa[4 * v + 3] = a.w;
                         pb[4 * v] = b.x; pb[4 * v + 1] = b.y; pb[4 * v + 2] = b.z; pb[4 * v + 3] = b.w;
                     }
@@ -887,7 +926,7 @@ smol_half_kernel (const HalfParams P)
         out[o] = __byte_perm (v, 0, P.prmt_sel);
     }
     if (n_px == 4)
-        *reinterpret_cast<uint4 *> (dst) = make_uint4 (out[0], out[1], out[2], out[3]);
+        half_store16<AL> (dst, out[0], out[1], out[2], out[3]);
     else
     {
 #pragma unroll
@@ -1009,7 +1048,7 @@ smol_half2v_kernel (const HalfParams P)
  * instruction, all 2 << VH source rows in flight at once).  With HH = 1 a chunk is exactly one
  * output pixel; with HH = 2 two neighbouring lanes hold the two halves of an output pixel and
  * add their partial sums with one shuffle per word. */
-template <int HH, int VH, int PACK>
+template <int HH, int VH, int PACK, int AL>
 __global__ void __launch_bounds__ (256)
 smol_half_wide_kernel (const HalfParams P)
 {
@@ -1046,7 +1085,7 @@ smol_half_wide_kernel (const HalfParams P)
     uint4 rows[N_ROWS];
 #pragma unroll
     for (int r = 0; r < N_ROWS; r++)
-        rows[r] = live ? ldg_nc_v4 (src + (size_t) r * P.src_pitch) : make_uint4 (0, 0, 0, 0);
+        rows[r] = live ? half_load16<AL> (src + (size_t) r * P.src_pitch) : make_uint4 (0, 0, 0, 0);
 
     uint32_t acc_lo = 0, acc_hi = 0, res = 0;
 #pragma unroll
@@ -1861,12 +1900,13 @@ smol_mag_kernel (const MagParams M)
 #ifndef SMOL_MAGB_MINBLOCKS
 #define SMOL_MAGB_MINBLOCKS 1
 #endif
+#define SMOL_MAGB_MAX_TILE_H 256        /* rows of a tile (one thread per row builds the per-row tables) */
 
 struct MagbParams
 {
     TapsParams t;
     uint32_t nb_row;                /* bytes per output row: w_out * bpp_out */
-    uint32_t tile_b, tile_h;        /* output tile: tile_b bytes (16 << chunks_log2), tile_h rows (<= 64) */
+    uint32_t tile_b, tile_h;        /* output tile: tile_b bytes (16 << chunks_log2), tile_h rows (<= SMOL_MAGB_MAX_TILE_H) */
     uint32_t chunks_log2;           /* log2 (tile_b / 16), at most 8 */
     uint32_t gcols_log2;            /* thread columns of stage 2: power of two >= pixel groups per tile, at most 8 */
     uint32_t u_pitch;               /* pixels per row of the unpacked source window */
@@ -1887,8 +1927,8 @@ smol_magb_kernel (const MagbParams M)
     static_assert (!OU || BO == 4, "unassociated output is 32bpp");
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
     __shared__ uint32_t sm_inv[OU ? 256 : 1];
-    __shared__ uint32_t sm_ty[64];
-    __shared__ uint4 sm_row[64];            /* per output row of the tile: { F, 256 - F, source row offset, end of its run } */
+    __shared__ uint32_t sm_ty[SMOL_MAGB_MAX_TILE_H];
+    __shared__ uint4 sm_row[SMOL_MAGB_MAX_TILE_H];  /* per output row of the tile: { F, 256 - F, source row offset, end of its run } */
     const TapsParams &P = M.t;
     const uint32_t tid = threadIdx.x;
     constexpr bool GROUPS = BI == 3 && SRC32;       /* stage 1 works on groups of four 24bpp pixels */
@@ -2485,10 +2525,16 @@ box3_accum (uint32_t raw, uint32_t w, uint32_t acc[4], const BoxParams &P, uint3
 /* LUTM = 1: one big CTA per SM (128 KB composite table + the warps' staging buffers);
  * LUTM = 2: 512-thread CTAs with lane-replicated LUTs; LUTM = 0: 256-thread CTAs, plain LUTs;
  * LUTM = 3: one big CTA per SM, byte-addressed lane-replicated LUTs (see box3_accum). */
-template <int MODE, int LUTM, int BI>
+/* RS ("row shift", LUTM = 3 only): source rows need not start on 16-byte boundaries (32bpp: any
+ * 4-byte-aligned base and pitch; 24bpp: any).  The copies stay 16-byte cp.async on chunks aligned
+ * in GLOBAL memory; what changes from row to row is where the row's first byte lands in the
+ * staging buffer, a per-row constant added to the lane's walk addresses.  Chunks that straddle the
+ * row's start or end are copied byte-exactly, so nothing outside the row is ever touched. */
+template <int MODE, int LUTM, int BI, bool RS = false>
 __global__ void __launch_bounds__ (LUTM == 3 ? SMOL_BOX3_MAX_WARPS * 32 : LUTM == 1 ? 1024 : LUTM == 2 ? 512 : 256, LUTM == 1 || LUTM == 3 ? 1 : LUTM == 2 ? 2 : 5)
 smol_box_kernel (const BoxParams P)
 {
+    static_assert (!RS || LUTM == 3, "row-shifted staging exists for the lean row loop only");
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
     __shared__ uint32_t sm_inv8_plain[LUTM == 0 ? 256 : 1];
     __shared__ uint32_t sm_from_plain[LUTM == 0 ? 256 : 1];
@@ -2713,22 +2759,66 @@ smol_box_kernel (const BoxParams P)
                 grow += P.src_pitch;
             };
 
-            prefetch3 (0);
+            /* RS: row-relative offset (may be negative) of the first staged byte of source row r,
+             * and the copy of that row's chunks */
+            const uint8_t *img_base = P.src + (size_t) img * P.src_image_stride;
+            const uint32_t sx_b = sx0 * BI, end_b = (sx1 + 1) * BI;
+            auto staged_from = [&] (uint32_t r) -> int32_t
+            {
+                const uint32_t A = (uint32_t) reinterpret_cast<uintptr_t> (img_base + (size_t) r * P.src_pitch) & 15u;
+                return (int32_t) ((A + sx_b) & ~15u) - (int32_t) A;
+            };
+            auto prefetch3s = [&] (uint32_t slot_ofs, uint32_t r)
+            {
+                const uint8_t *rowp = img_base + (size_t) r * P.src_pitch;
+                const int32_t w0 = staged_from (r);
+                const uint32_t nch = ((uint32_t) ((int32_t) end_b - w0) + 15u) >> 4;
+                for (uint32_t k = lane; k < nch; k += 32)
+                {
+                    const int32_t ofs = w0 + 16 * (int32_t) k;
+                    const uint32_t sa = bufs_addr + slot_ofs + 16 * k;
+                    if (ofs >= 0 && ofs + 16 <= (int32_t) row_bytes)
+                        cp_async_16_full (sa, rowp + ofs);
+                    else
+                    {
+                        const int32_t lo = ofs < 0 ? -ofs : 0, hi = min (16, (int32_t) row_bytes - ofs);
+                        for (int32_t b = lo; b < hi; b++)
+                        {
+                            const uint32_t v = __ldg (rowp + ofs + b);
+                            asm volatile ("st.shared.u8 [%0], %1;" :: "r"(sa + b), "r"(v) : "memory");
+                        }
+                    }
+                }
+                cp_async_commit ();
+            };
+
+            if constexpr (RS)
+                prefetch3s (0, T);
+            else
+                prefetch3 (0);
             for (uint32_t r = T; r <= r_end; r++)
             {
                 if (r < r_end)
                 {
-                    prefetch3 (P.seg_bytes - cur);
+                    if constexpr (RS)
+                        prefetch3s (P.seg_bytes - cur, r + 1);
+                    else
+                        prefetch3 (P.seg_bytes - cur);
                     cp_async_wait<1> ();
                 }
                 else
                     cp_async_wait<0> ();
                 __syncwarp ();
 
-                const uint32_t row = bufs_addr + cur;               /* window address of the staged segment */
+                /* window address of the byte staged for row-relative offset win0 */
+                uint32_t row = bufs_addr + cur;
+                if constexpr (RS)
+                    row += (uint32_t) ((int32_t) win0 - staged_from (r));
                 auto fetch3 = [&] (uint32_t j) -> uint32_t
                 {
-                    const uint32_t b = j * 3 - win0, a = row + (b & ~3u);
+                    /* RS: `row` is not word aligned for 24bpp rows; split address and shift from the true staging offset */
+                    const uint32_t b = RS ? j * 3 - win0 + (row - (bufs_addr + cur)) : j * 3 - win0;
+                    const uint32_t a = (RS ? bufs_addr + cur : row) + (b & ~3u);
                     return __funnelshift_r (lds_u32_ordered (a), lds_u32_ordered (a + 4), (b & 3) * 8) | 0xff000000u;
                 };
                 BoxPx<MODE> acc;
@@ -3334,17 +3424,24 @@ aligned16 (const void *p)
 }
 
 static bool
+aligned4 (const void *p)
+{
+    return (reinterpret_cast<uintptr_t> (p) & 3) == 0;
+}
+
+static bool
 half_eligible (const SmolLaunch &L)
 {
     const SmolJobDesc &d = L.d;
 
+    /* 4-byte-aligned pixels; 16- and 32-byte alignment select wider accesses (launch_half) */
     return d.h_kind == SMOL_AXIS_TAPS && d.v_kind == SMOL_AXIS_TAPS
            && d.all_half_x && d.all_half_y
            && d.mid == SMOL_MID_P8 && !d.storage128
            && d.bpp_in == 4 && d.bpp_out == 4 && !d.in_unassoc
-           && aligned16 (L.src) && aligned16 (L.dst)
-           && (L.src_pitch & 15) == 0 && (L.dst_pitch & 15) == 0
-           && (L.src_image_stride & 15) == 0 && (L.dst_image_stride & 15) == 0;
+           && aligned4 (L.src) && aligned4 (L.dst)
+           && (L.src_pitch & 3) == 0 && (L.dst_pitch & 3) == 0
+           && (L.src_image_stride & 3) == 0 && (L.dst_image_stride & 3) == 0;
 }
 
 static bool
@@ -3425,7 +3522,9 @@ box_eligible (const SmolLaunch &L)
         return false;                   /* a warp's row segment must fit its staging buffer */
     if ((uint64_t) d.w_out * L.n_rows * L.n_images >= 0x7fffffffull)
         return false;                   /* 32-bit work item index */
-    return aligned16 (L.src) && (L.src_pitch & 15) == 0 && (L.src_image_stride & 15) == 0;
+    /* 32bpp: whole pixels must be word loads from the staged rows; 24bpp: any alignment.  Rows off
+     * 16-byte boundaries take the row-shifted variant (launch_box). */
+    return d.bpp_in == 3 || (aligned4 (L.src) && (L.src_pitch & 3) == 0 && (L.src_image_stride & 3) == 0);
 }
 
 extern "C" int
@@ -3609,26 +3708,46 @@ launch_pdl_args (Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t
     return cudaLaunchKernelEx (&cfg, kernel, args...);
 }
 
-template <int HH, int VH>
+template <int HH, int VH, int AL>
 static cudaError_t
 launch_half_hv (const HalfParams &P, int pack, dim3 grid, dim3 block, cudaStream_t stream)
 {
     if constexpr (HH == 0)
     {
         if (pack == 1)
-            return launch_pdl (smol_half_kernel<HH, VH, 1>, P, grid, block, 0, stream);
+            return launch_pdl (smol_half_kernel<HH, VH, 1, AL>, P, grid, block, 0, stream);
         if (pack == 2)
-            return launch_pdl (smol_half_kernel<HH, VH, 2>, P, grid, block, 0, stream);
-        return launch_pdl (smol_half_kernel<HH, VH, 0>, P, grid, block, 0, stream);
+            return launch_pdl (smol_half_kernel<HH, VH, 2, AL>, P, grid, block, 0, stream);
+        return launch_pdl (smol_half_kernel<HH, VH, 0, AL>, P, grid, block, 0, stream);
     }
     else
     {
         if (pack == 1)
-            return launch_pdl (smol_half_wide_kernel<HH, VH, 1>, P, grid, block, 0, stream);
+            return launch_pdl (smol_half_wide_kernel<HH, VH, 1, AL>, P, grid, block, 0, stream);
         if (pack == 2)
-            return launch_pdl (smol_half_wide_kernel<HH, VH, 2>, P, grid, block, 0, stream);
-        return launch_pdl (smol_half_wide_kernel<HH, VH, 0>, P, grid, block, 0, stream);
+            return launch_pdl (smol_half_wide_kernel<HH, VH, 2, AL>, P, grid, block, 0, stream);
+        return launch_pdl (smol_half_wide_kernel<HH, VH, 0, AL>, P, grid, block, 0, stream);
     }
+}
+
+/* Same, for a kernel picked at run time as a function pointer (one by-value parameter struct). */
+static cudaError_t
+launch_pdl_ptr (const void *fn, const void *params, dim3 grid, dim3 block, size_t smem, cudaStream_t stream)
+{
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr;
+    void *args[1] = { const_cast<void *> (params) };
+
+    memset (&cfg, 0, sizeof (cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelExC (&cfg, fn, args);
 }
 
 /* rows per thread of the 256-bit 2:1 kernel (SMOL_HALF2V_ROWS: 0 = use the 128-bit kernel) */
@@ -3704,7 +3823,8 @@ launch_half (const SmolLaunch &L, cudaStream_t stream)
         P.prefetch = 0xffffffffu;
 
     if (d.h_halvings == 0 && d.v_halvings == 0 && half2v_rows () > 0
-        && (reinterpret_cast<uintptr_t> (L.src) & 31) == 0 && (L.src_pitch & 31) == 0 && (L.src_image_stride & 31) == 0)
+        && (reinterpret_cast<uintptr_t> (L.src) & 31) == 0 && (L.src_pitch & 31) == 0 && (L.src_image_stride & 31) == 0
+        && aligned16 (L.dst) && (L.dst_pitch & 15) == 0 && (L.dst_image_stride & 15) == 0)
     {
         /* 256-bit loads, several rows per thread (see smol_half2v_kernel) */
         const uint32_t rows = (uint32_t) half2v_rows ();
@@ -3738,18 +3858,25 @@ launch_half (const SmolLaunch &L, cudaStream_t stream)
 #undef HALF2V
     }
 
+    const uintptr_t bits = reinterpret_cast<uintptr_t> (L.src) | reinterpret_cast<uintptr_t> (L.dst) | L.src_pitch | L.dst_pitch
+                           | L.src_image_stride | L.dst_image_stride;
+    const int al = (bits & 15) == 0 ? 16 : (bits & 7) == 0 ? 8 : 4;
+#define HALF_HV(H, V) (al == 16 ? launch_half_hv<H, V, 16> (P, pack, grid, block, stream) \
+                       : al == 8 ? launch_half_hv<H, V, 8> (P, pack, grid, block, stream) \
+                       : launch_half_hv<H, V, 4> (P, pack, grid, block, stream))
     switch (d.h_halvings * 3 + d.v_halvings)
     {
-        case 0: return launch_half_hv<0, 0> (P, pack, grid, block, stream);
-        case 1: return launch_half_hv<0, 1> (P, pack, grid, block, stream);
-        case 2: return launch_half_hv<0, 2> (P, pack, grid, block, stream);
-        case 3: return launch_half_hv<1, 0> (P, pack, grid, block, stream);
-        case 4: return launch_half_hv<1, 1> (P, pack, grid, block, stream);
-        case 5: return launch_half_hv<1, 2> (P, pack, grid, block, stream);
-        case 6: return launch_half_hv<2, 0> (P, pack, grid, block, stream);
-        case 7: return launch_half_hv<2, 1> (P, pack, grid, block, stream);
-        default: return launch_half_hv<2, 2> (P, pack, grid, block, stream);
+        case 0: return HALF_HV (0, 0);
+        case 1: return HALF_HV (0, 1);
+        case 2: return HALF_HV (0, 2);
+        case 3: return HALF_HV (1, 0);
+        case 4: return HALF_HV (1, 1);
+        case 5: return HALF_HV (1, 2);
+        case 6: return HALF_HV (2, 0);
+        case 7: return HALF_HV (2, 1);
+        default: return HALF_HV (2, 2);
     }
+#undef HALF_HV
 }
 
 /* destination byte j takes source byte perm[j] (PRMT selector); 24bpp sources carry a forced
@@ -4144,11 +4271,14 @@ launch_magb (const SmolLaunch &L, cudaStream_t stream)
     MagbParams M;
 
     taps_params_init (M.t, L);
-    static int tune_tb = -1, tune_th = -1;
+    static int tune_tb = -1, tune_th = -1, tune_hmax = 64;
     static uint32_t magb_reg_ctas = 8;
     if (tune_tb < 0)
     {
         const char *a = getenv ("SMOL_MAGB_TB"), *b = getenv ("SMOL_MAGB_TH"), *c = getenv ("SMOL_MAGB_CTAS");
+        const char *hm = getenv ("SMOL_MAGB_HMAX");
+        if (hm && atoi (hm) >= 8 && atoi (hm) <= SMOL_MAGB_MAX_TILE_H)
+            tune_hmax = atoi (hm);
         tune_tb = a ? atoi (a) : 0;
         tune_th = b ? atoi (b) : 0;
         if (c && atoi (c) > 0)
@@ -4198,7 +4328,7 @@ launch_magb (const SmolLaunch &L, cudaStream_t stream)
             c_max++;
         for (uint32_t c = c_max >= 5 ? 5 : c_max; c <= c_max; c++)
         {
-            for (uint32_t h = 8; h <= 64; h *= 2)
+            for (uint32_t h = 8; h <= (uint32_t) tune_hmax; h *= 2)
             {
                 size_t sm;
                 if ((tune_tb >= 16 && (16u << c) != (uint32_t) tune_tb && c != c_max) || (tune_th > 0 && h != (uint32_t) tune_th))
@@ -4373,22 +4503,28 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     P.unroll2 = tune_unroll != 0;
     P.prefetch = pdl_first_wave (1024, 0) != 0;
     const bool bi3 = d.bpp_in == 3;     /* 24bpp sources are never unassociated: modes P8_P / P8L_P only */
-#define BOX_KERNEL_FOR(M) (lutm == 3 ? (const void *) smol_box_kernel<M, 3, 4> : lutm == 1 ? (const void *) smol_box_kernel<M, 1, 4> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 4> : (const void *) smol_box_kernel<M, 0, 4>)
-#define BOX_KERNEL_FOR3(M) (lutm == 3 ? (const void *) smol_box_kernel<M, 3, 3> : lutm == 1 ? (const void *) smol_box_kernel<M, 1, 3> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 3> : (const void *) smol_box_kernel<M, 0, 3>)
+    /* rows that do not start on 16-byte boundaries: the row-shifted variant of the lean row loop */
+    const bool rs = !(aligned16 (L.src) && (L.src_pitch & 15) == 0 && (L.src_image_stride & 15) == 0);
+    if (rs && lutm != 3)
+        return cudaErrorNotSupported;   /* the caller falls back to the general kernel */
+#define BOX_K3(M, B) (rs ? (const void *) smol_box_kernel<M, 3, B, true> : (const void *) smol_box_kernel<M, 3, B, false>)
+#define BOX_KERNEL_FOR(M) (lutm == 3 ? BOX_K3 (M, 4) : lutm == 1 ? (const void *) smol_box_kernel<M, 1, 4> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 4> : (const void *) smol_box_kernel<M, 0, 4>)
+#define BOX_KERNEL_FOR3(M) (lutm == 3 ? BOX_K3 (M, 3) : lutm == 1 ? (const void *) smol_box_kernel<M, 1, 3> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 3> : (const void *) smol_box_kernel<M, 0, 3>)
     const void *fn;
     switch (mode)
     {
-        case BM_P8_P:   fn = lutm == 3 ? (bi3 ? (const void *) smol_box_kernel<BM_P8_P, 3, 3> : (const void *) smol_box_kernel<BM_P8_P, 3, 4>)
+        case BM_P8_P:   fn = lutm == 3 ? (bi3 ? BOX_K3 (BM_P8_P, 3) : BOX_K3 (BM_P8_P, 4))
                                        : (bi3 ? (const void *) smol_box_kernel<BM_P8_P, 0, 3> : (const void *) smol_box_kernel<BM_P8_P, 0, 4>); break;
-        case BM_P8_U:   fn = lutm == 3 ? (const void *) smol_box_kernel<BM_P8_U, 3, 4> : (const void *) smol_box_kernel<BM_P8_U, 0, 4>; break;
+        case BM_P8_U:   fn = lutm == 3 ? BOX_K3 (BM_P8_U, 4) : (const void *) smol_box_kernel<BM_P8_U, 0, 4>; break;
         case BM_P8L_P:  fn = bi3 ? BOX_KERNEL_FOR3 (BM_P8L_P) : BOX_KERNEL_FOR (BM_P8L_P); break;
         case BM_P8L_U:  fn = BOX_KERNEL_FOR (BM_P8L_U); break;
-        case BM_P16_U:  fn = lutm == 3 ? (const void *) smol_box_kernel<BM_P16_U, 3, 4> : (const void *) smol_box_kernel<BM_P16_U, 0, 4>; break;
-        default:        fn = lutm == 3 ? (const void *) smol_box_kernel<BM_P16L_U, 3, 4>
+        case BM_P16_U:  fn = lutm == 3 ? BOX_K3 (BM_P16_U, 4) : (const void *) smol_box_kernel<BM_P16_U, 0, 4>; break;
+        default:        fn = lutm == 3 ? BOX_K3 (BM_P16L_U, 4)
                              : lutm == 2 ? (const void *) smol_box_kernel<BM_P16L_U, 2, 4> : (const void *) smol_box_kernel<BM_P16L_U, 0, 4>; break;
     }
 #undef BOX_KERNEL_FOR
 #undef BOX_KERNEL_FOR3
+#undef BOX_K3
 
     /* Lanes per column (G).  Long spans want several lanes per column (8..16 source pixels per
      * lane per row).  Every extra lane repeats the per-row overhead (edge pixels, normalisation),
@@ -4480,20 +4616,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         blocks = (uint64_t) num_sms () * per_sm;
     dim3 grid ((unsigned) blocks), block (warps_per_cta * 32);
 
-#define BOX_LAUNCH(M, LM, B) launch_pdl (smol_box_kernel<M, LM, B>, P, grid, block, smem, stream)
-#define BOX_LAUNCH_LUT(M, B) (lutm == 3 ? BOX_LAUNCH (M, 3, B) : lutm == 1 ? BOX_LAUNCH (M, 1, B) : lutm == 2 ? BOX_LAUNCH (M, 2, B) : BOX_LAUNCH (M, 0, B))
-    switch (mode)
-    {
-        case BM_P8_P:   return lutm == 3 ? (bi3 ? BOX_LAUNCH (BM_P8_P, 3, 3) : BOX_LAUNCH (BM_P8_P, 3, 4))
-                                         : (bi3 ? BOX_LAUNCH (BM_P8_P, 0, 3) : BOX_LAUNCH (BM_P8_P, 0, 4));
-        case BM_P8_U:   return lutm == 3 ? BOX_LAUNCH (BM_P8_U, 3, 4) : BOX_LAUNCH (BM_P8_U, 0, 4);
-        case BM_P8L_P:  return bi3 ? BOX_LAUNCH_LUT (BM_P8L_P, 3) : BOX_LAUNCH_LUT (BM_P8L_P, 4);
-        case BM_P8L_U:  return BOX_LAUNCH_LUT (BM_P8L_U, 4);
-        case BM_P16_U:  return lutm == 3 ? BOX_LAUNCH (BM_P16_U, 3, 4) : BOX_LAUNCH (BM_P16_U, 0, 4);
-        default:        return lutm == 3 ? BOX_LAUNCH (BM_P16L_U, 3, 4) : lutm == 2 ? BOX_LAUNCH (BM_P16L_U, 2, 4) : BOX_LAUNCH (BM_P16L_U, 0, 4);
-    }
-#undef BOX_LAUNCH_LUT
-#undef BOX_LAUNCH
+    return launch_pdl_ptr (fn, &P, grid, block, smem, stream);
 }
 
 static void box_params_init (BoxParams &P, const SmolLaunch &L);
@@ -4698,7 +4821,11 @@ smol_cuda_launch (const SmolLaunch *launch, int kernel_id, void *stream_p, const
     if (kernel_id == SMOL_KERNEL_HALF2X && half_eligible (L))
         return (int) launch_half (L, stream);
     if (kernel_id == SMOL_KERNEL_BOX && box_eligible (L))
-        return (int) launch_box (L, stream);
+    {
+        const cudaError_t e = launch_box (L, stream);
+        if (e != cudaErrorNotSupported)
+            return (int) e;
+    }
     if (kernel_id == SMOL_KERNEL_TAPS128 && taps128_eligible (L))
         return (int) launch_taps128 (L, stream);
     if (kernel_id == SMOL_KERNEL_TILE128 && tile128_eligible (L))

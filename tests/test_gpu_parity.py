@@ -412,3 +412,60 @@ def test_baseline_config_properties(sb, restatement):
         y0 = ho // 3
         win = restatement.scale_rows(src, ti, wi, hi, si, to, wo, ho, y0, 5, so, srgb)
         assert np.array_equal(win, whole[y0 * so: y0 * so + win.size]), name
+
+
+def test_scale_images_thumbnail_batch(sb, restatement):
+    """smol_cuda_scale_images on the BASELINE cfg 5 shape (2048x2048 ARGB8 -> 256x256, the 8:1 packed-byte
+    kernel the benchmark runs): 24 images in one launch; the first three are the images of the committed
+    reference digests, the rest are checked against the oracle."""
+    import torch
+    with open(GOLDEN) as f:
+        golden = json.load(f)["digests"]
+    ti, wi, hi, to, wo, ho = cases.ARGB8_P, 2048, 2048, cases.ARGB8_P, 256, 256
+    si, so = wi * 4, wo * 4
+    n = 24
+    imgs = [cases.make_image(ti, wi, hi, si, "premul" if i < 12 else "random", seed=i) for i in range(n)]
+    d_in = torch.from_numpy(np.stack(imgs)).cuda()
+    d_out = torch.zeros((n, so * ho), dtype=torch.uint8, device="cuda")
+    sb.reset_stats()
+    sb.set_stream(torch.cuda.current_stream().cuda_stream)
+    sb.scale_images(d_in, si * hi, ti, wi, hi, si, d_out, so * ho, to, wo, ho, so, 0, n)
+    torch.cuda.synchronize()
+    sb.set_stream(None)
+    assert sb.kernel_launches()["half2x"] == 1
+    got = d_out.cpu().numpy()
+    for s in range(3):
+        assert hashlib.sha256(got[s].tobytes()).hexdigest() == golden["cfg5_2048sq_to_256sq_argb_seed%d" % s]["sha256"], s
+    for i in range(3, n):
+        want = restatement.scale_simple(imgs[i], ti, wi, hi, si, to, wo, ho, so, 0)
+        assert np.array_equal(got[i], want), i
+
+
+def test_reference_verify_program(sb):
+    """The reference's own known-answer program (verify.c, unmodified, compiled from /root/reference by
+    oracle/Makefile and linked against libsmolscale_cuda.so instead of the reference objects): its first
+    three suites -- Saturation, Unassociated alpha, Ordering -- must print ok.  The fourth (Pre/unmul)
+    fails on the reference itself, so the run is cut there."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "_ref", "verify_cuda")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/verify_cuda not built (needs /root/reference at build time)")
+    p = subprocess.Popen([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    lines, oks = [], 0
+    try:
+        import threading
+        killer = threading.Timer(120, p.kill)
+        killer.start()
+        for line in p.stdout:
+            lines.append(line.rstrip())
+            if line.strip().endswith("ok"):
+                oks += 1
+            if oks >= 3 or len(lines) > 400:
+                break
+    finally:
+        killer.cancel()
+        p.kill()
+        p.wait()
+    assert oks >= 3, "\n".join(lines[-40:])
+    assert [ln.split(":")[0] for ln in lines if ln.strip().endswith("ok")][:3] == ["Ordering", "Unassociated alpha", "Saturation"]
+    assert not any("mismatch" in ln.lower() for ln in lines), "\n".join(lines[-40:])

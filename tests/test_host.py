@@ -172,3 +172,33 @@ def test_dispatch_table():
     for want, ti, wi, hi, to, wo, ho, srgb in expect:
         got = sb.plan_query(ti, wi, hi, to, wo, ho, srgb)["kernel_name"]
         assert got == want, ((ti, wi, hi, to, wo, ho, srgb), got, want)
+
+
+def _header_tables(path, prefix):
+    """{name: list of ints} for every `static const <type> <prefix><name>[N] = {...};` in a generated header."""
+    text = open(path).read()
+    out = {}
+    for m in re.finditer(r"static const \w+ %s(\w+)\[(\d+)\] = \{(.*?)\};" % re.escape(prefix), text, flags=re.S):
+        vals = [int(v, 16) for v in re.findall(r"0x[0-9a-fA-F]+", m.group(3))]
+        assert len(vals) == int(m.group(2)), m.group(1)
+        out[m.group(1)] = vals
+    return out
+
+
+def test_lut_headers_equal_reference_data(reference):
+    """The six data tables (reference smolscale.c:87-421) the product and the oracle are built with are,
+    entry for entry, the data symbols of the compiled reference; two of them have no
+    generator, so this equality is the only thing that pins them besides bit-exact output."""
+    symbols = {"from_srgb": ("_smol_from_srgb_lut", ctypes.c_uint16, 256), "to_srgb": ("_smol_to_srgb_lut", ctypes.c_uint8, 2048),
+               "inv_div_p8": ("_smol_inv_div_p8_lut", ctypes.c_uint32, 256), "inv_div_p8l": ("_smol_inv_div_p8l_lut", ctypes.c_uint32, 256),
+               "inv_div_p16": ("_smol_inv_div_p16_lut", ctypes.c_uint32, 256), "inv_div_p16l": ("_smol_inv_div_p16l_lut", ctypes.c_uint32, 256)}
+    product = _header_tables(os.path.join(ROOT, "smolscale_b200", "csrc", "smolscale-cuda-luts.h"), "smol_lut_")
+    checker = _header_tables(os.path.join(ROOT, "oracle", "smol_oracle_luts.h"), "oracle_lut_")
+    assert set(product) == set(symbols) == set(checker)
+    for name, (sym, ct, n) in symbols.items():
+        ref = list((ct * n).in_dll(reference.lib, sym))
+        assert product[name] == ref, name
+        assert checker[name] == ref, name
+    # the two closed forms the survey found (ceil (2^16 / a), ceil (2^19 / a)) as an independent cross-check
+    assert all(product["inv_div_p16"][a] == -(-(1 << 16) // a) for a in range(1, 256))
+    assert all(product["inv_div_p16l"][a] == -(-(1 << 19) // a) for a in range(1, 256))
