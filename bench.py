@@ -515,6 +515,8 @@ def main():
         run_reference_arm(args, cfg_name, cfg, rank, world)
         return
 
+    # the library's host-copy pool (pageable buffers) shares the box's cores with the other ranks
+    os.environ.setdefault("SMOL_CUDA_HOST_THREADS", str(max(2, (os.cpu_count() or 8) // max(world, 1) // 2)))
     import torch
     import smolscale_b200 as sb
 
