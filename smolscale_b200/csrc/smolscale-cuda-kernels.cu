@@ -2228,6 +2228,7 @@ struct BoxParams
     uint32_t first_row, n_rows, n_images;
     uint32_t lanes_per_col_log2;    /* G = 1 << this */
     uint32_t x_tiles;               /* items per output row */
+    uint32_t rows_per_item, n_strips;   /* an item = one column tile x a strip of consecutive output rows (lean row loop: > 1 row) */
     uint32_t seg_bytes;             /* bytes per staging buffer (multiple of 16) */
     uint32_t alpha_shift, col_shift;/* bit positions in the packed source pixel */
     uint32_t sel_alpha, sel_c0, sel_c1, sel_c2;     /* PRMT selectors: that byte -> bits 0..7, zeros above */
@@ -2241,6 +2242,7 @@ struct BoxParams
     uint32_t warps_lo;              /* warps whose staging buffers lie below the tables (window < 0x10000) */
     uint32_t unroll2;               /* walk the span two pixels per trip */
     uint32_t prefetch;              /* L2-prefetch the first window rows ahead of the dependency wait */
+    uint32_t use_tma;               /* stage full windows with cp.async.bulk instead of cp.async (measurements) */
 };
 
 /* One 16-byte chunk of a staged row, of which the first src_bytes (1..16) lie inside the source
@@ -2439,6 +2441,9 @@ template <int MODE> __device__ __forceinline__ BoxPx<MODE> box_scale (const BoxP
 #define SMOL_BOX3_MAX_WARPS 32
 #endif
 #define SMOL_BOX3_FROM_WIN 0x10000u
+/* highest window address the dynamic allocation may start at: 1 KB reserved by the system + the
+ * kernel's static shared memory (the warps' transfer barriers) */
+#define SMOL_BOX3_DYN_WIN_MAX 0x700u
 
 #define SMOL_BOX3_INV_WIN  0x20000u
 
@@ -2525,6 +2530,33 @@ box3_accum (uint32_t raw, uint32_t w, uint32_t acc[4], const BoxParams &P, uint3
 /* LUTM = 1: one big CTA per SM (128 KB composite table + the warps' staging buffers);
  * LUTM = 2: 512-thread CTAs with lane-replicated LUTs; LUTM = 0: 256-thread CTAs, plain LUTs;
  * LUTM = 3: one big CTA per SM, byte-addressed lane-replicated LUTs (see box3_accum). */
+/* Bulk asynchronous copy (the TMA unit, `cp.async.bulk`) of a contiguous, 16-byte-aligned run of
+ * bytes into shared memory, completion signalled on an mbarrier by byte count.  One elected lane
+ * issues it; the warp waits on the barrier's phase parity. */
+__device__ __forceinline__ void mbar_init (uint32_t mbar, uint32_t arrivals)
+{
+    asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(arrivals) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_bytes (uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+    asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                  :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait (uint32_t mbar, uint32_t parity)
+{
+    asm volatile ("{\n"
+                  ".reg .pred p;\n"
+                  "SMOL_MBAR_WAIT:\n"
+                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                  "@p bra SMOL_MBAR_DONE;\n"
+                  "bra SMOL_MBAR_WAIT;\n"
+                  "SMOL_MBAR_DONE:\n"
+                  "}" :: "r"(mbar), "r"(parity) : "memory");
+}
+
 /* RS ("row shift", LUTM = 3 only): source rows need not start on 16-byte boundaries (32bpp: any
  * 4-byte-aligned base and pitch; 24bpp: any).  The copies stay 16-byte cp.async on chunks aligned
  * in GLOBAL memory; what changes from row to row is where the row's first byte lands in the
@@ -2538,10 +2570,23 @@ smol_box_kernel (const BoxParams P)
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
     __shared__ uint32_t sm_inv8_plain[LUTM == 0 ? 256 : 1];
     __shared__ uint32_t sm_from_plain[LUTM == 0 ? 256 : 1];
+    __shared__ __align__ (8) uint64_t sm_mbar[LUTM == 3 && !RS ? 2 * SMOL_BOX3_MAX_WARPS : 1];   /* two per warp: one per staging slot */
+#ifdef SMOL_BOX_TMA
+    constexpr bool TMA = LUTM == 3 && !RS;
+#else
+    constexpr bool TMA = false;      /* see use_tma below: measured slower, and even unused its scaffolding costs 2 us */
+#endif
     constexpr bool S128 = MODE >= BM_P8L_P;
     constexpr bool TAB = LUTM == 1;
     constexpr bool OPAQUE = LUTM == 3 && BI == 3 && MODE == BM_P8L_P;   /* see box3_accum */
     constexpr bool NEED_INV = MODE == BM_P8L_P && !OPAQUE;
+    /* 32bpp premultiplied linear light: rows whose staged pixels all have alpha 255 (photographs in an
+     * RGBA container) take the one-table-read-per-channel walk of the 24bpp case; see the row loop */
+#ifdef SMOL_BOX_NO_SPEC
+    constexpr bool SPEC_OPAQUE = false;
+#else
+    constexpr bool SPEC_OPAQUE = LUTM == 3 && NEED_INV && BI == 4;
+#endif
     constexpr bool NEED_FROM = MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U;
     constexpr uint32_t REP_BYTES = LUTM == 2 ? ((NEED_INV ? 32768u : 0u) + (NEED_FROM ? 32768u : 0u)) : 0u;
     constexpr uint32_t TAB_BYTES = TAB ? 65536 * 2 : REP_BYTES;
@@ -2584,8 +2629,8 @@ smol_box_kernel (const BoxParams P)
     {
         /* layout: see box3_accum; window address -> offset inside the dynamic allocation */
         const uint32_t dyn_win = (uint32_t) __cvta_generic_to_shared (sm_dyn) & 0x00ffffffu;
-        if (dyn_win > 0x480u)
-            __trap ();                  /* the host sized the low staging region for a start at or below 0x480 */
+        if (dyn_win > SMOL_BOX3_DYN_WIN_MAX)
+            __trap ();                  /* the host sized the low staging region for a start at or below this */
         uint32_t *t_from = reinterpret_cast<uint32_t *> (sm_dyn + (SMOL_BOX3_FROM_WIN - dyn_win));
         uint2 *t_inv = reinterpret_cast<uint2 *> (sm_dyn + (SMOL_BOX3_INV_WIN - dyn_win));
         for (uint32_t i = threadIdx.x; i < 8192; i += blockDim.x)
@@ -2593,6 +2638,8 @@ smol_box_kernel (const BoxParams P)
             const uint32_t e = i >> 5, l = i & 31;
             const uint32_t lin = P.luts->from_srgb[e];
             t_from[e * 64 + l] = OPAQUE ? ((lin + 1) * 2041u - 1) >> 11 : lin + (MODE == BM_P16L_U ? 0u : 1u);
+            if constexpr (SPEC_OPAQUE)
+                t_from[e * 64 + 32 + l] = ((lin + 1) * 2041u - 1) >> 11;    /* the chain's result for alpha = 255 (see box3_accum, OPAQUE) */
             if constexpr (NEED_INV)
                 t_inv[e * 32 + l] = make_uint2 (P.luts->inv_div_p8[e] << 3, e * 8 + 1);
         }
@@ -2604,8 +2651,20 @@ smol_box_kernel (const BoxParams P)
         if constexpr (NEED_FROM)
             sm_from_plain[threadIdx.x] = P.luts->from_srgb[threadIdx.x];
     }
+    const uint32_t mbar0 = (uint32_t) __cvta_generic_to_shared (&sm_mbar[TMA ? 2 * (threadIdx.x >> 5) : 0]);
+    uint32_t tma_parity = 0;        /* bit s: phase parity the warp waits for next on slot s */
+    if constexpr (TMA)
+    {
+        if ((threadIdx.x & 31) == 0)
+        {
+            mbar_init (mbar0, 1);
+            mbar_init (mbar0 + 8, 1);
+            asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
     __syncthreads ();
     bool waited = false;            /* the dependency wait happens at the warp's first item, after an L2 prefetch */
+    uint32_t opaque_backoff = 0;    /* rows to go before the warp tries the opaque walk again */
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t G = 1u << P.lanes_per_col_log2, g = lane & (G - 1);
@@ -2621,7 +2680,7 @@ smol_box_kernel (const BoxParams P)
     const uint32_t bufs_addr = (uint32_t) __cvta_generic_to_shared (bufs);
     const uint32_t row_bytes = d.w_in * BI;
 
-    const uint32_t items_per_image = P.x_tiles * P.n_rows;
+    const uint32_t items_per_image = P.x_tiles * P.n_strips;
     const uint32_t n_items = items_per_image * P.n_images;
     const uint32_t warp_stride = gridDim.x * (blockDim.x >> 5);
 
@@ -2629,7 +2688,8 @@ smol_box_kernel (const BoxParams P)
     {
         const uint32_t img = item / items_per_image;
         const uint32_t rem = item - img * items_per_image;
-        const uint32_t yl = rem / P.x_tiles, xt = rem - yl * P.x_tiles;
+        const uint32_t strip = rem / P.x_tiles, xt = rem - strip * P.x_tiles;
+        const uint32_t yl = strip * P.rows_per_item;        /* the item's first output row */
         const uint32_t y = P.first_row + yl;
         const uint32_t x_first = xt * cols_per_item;
         const uint32_t x_last = min (x_first + cols_per_item, d.w_out) - 1;
@@ -2725,9 +2785,24 @@ smol_box_kernel (const BoxParams P)
             const uint32_t o_left = hL * 4 - win0;
             uint32_t cur = 0;                                       /* byte offset of the slot in use: 0 or seg_bytes */
 
+            /* SMOL_BOX_TMA=1: windows that lie wholly inside the row travel as ONE bulk copy issued by
+             * lane 0 (TMA) -- no per-lane address arithmetic, no LSU work for the copy -- and the warp
+             * waits on the slot's barrier instead of its own cp.async group.  Measured on B200
+             * (8K -> 800x450): 59.0 us against 56.5 us with cp.async for the linear-light job, 35.5
+             * against 32.3 us without tables: a 1.2 KB copy per warp and row is too small for the
+             * bulk path's fixed latency, and the barrier polls cost issue slots the kernel is short
+             * of.  Compiled in with -DSMOL_BOX_TMA only (SMOL_NVCC_FLAGS); kept for measurements. */
+            const bool use_tma = TMA && win_full && P.use_tma;
             auto prefetch3 = [&] (uint32_t slot_ofs)
             {
                 const uint32_t sbase = sbuf + slot_ofs;
+                if (use_tma)
+                {
+                    if (lane == 0)
+                        tma_load_bytes (bufs_addr + slot_ofs, grow, 16 * n_chunks, mbar0 + (slot_ofs ? 8u : 0u));
+                    grow += P.src_pitch;
+                    return;
+                }
                 if (win_full)
                 {
                     if (cvalid[0])
@@ -2792,22 +2867,81 @@ smol_box_kernel (const BoxParams P)
                 cp_async_commit ();
             };
 
+            /* The item's output rows share their boundary source rows (row B of one output row is
+             * row T of the next, weighted F for the one and 255 - F for the other): the strip's
+             * source rows T .. r_last are walked ONCE, in one uninterrupted double-buffered stream,
+             * and a boundary row's horizontal result is handed on instead of being recomputed
+             * (the reference unpacks and filters that row twice, generic:2198-2260). */
+            const uint32_t yl_stop = min (yl + P.rows_per_item, P.n_rows);
+            uint32_t yl_cur = yl, B_cur = B, rend_cur = r_end, w1_cur = w1, w2_cur = w2, Fy_cur = Fy;
+            uint32_t r_last = r_end;
+            if (yl_stop - yl > 1)
+            {
+                const uint32_t ya = P.first_row + yl_stop - 1;
+                const uint32_t ea = __ldg (&P.tab_y[ya]), eb = __ldg (&P.tab_y[ya + 1]);
+                r_last = SMOL_TAB_F (ea) > 0 ? SMOL_TAB_OFS (eb) : SMOL_TAB_OFS (eb) - 1;
+            }
+            bool top_pending = true;        /* the current output row's first source row is still to come */
+
+            auto emit_row = [&] ()
+            {
+                BoxPx<MODE> fin;
+                if constexpr (S128)
+                {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        fin.v[i] = (uint32_t) (((uint64_t) vacc.v[i] * P.mul8_y + 0x80000000ull) >> 32) & 0xffffu;
+                }
+                else
+                    fin = box_scale<MODE> (vacc, d.span_mul_y, true);
+                if (store)
+                {
+                    uint32_t packed;
+                    if constexpr (S128)
+                    {
+                        Px<true> o;
+                        o.w[0] = (uint64_t) fin.v[0] | ((uint64_t) fin.v[1] << 32);
+                        o.w[1] = (uint64_t) fin.v[2] | ((uint64_t) fin.v[3] << 32);
+                        packed = pack_px<true> (o, d, P.luts);
+                    }
+                    else
+                    {
+                        const uint32_t bytes = fin.v[0] | (fin.v[1] << 8);
+                        const uint32_t alpha = (bytes >> P.alpha_shift) & 0xff;
+                        const uint32_t cols = bytes >> P.col_shift;
+                        Px<false> o;
+                        o.w[0] = (uint64_t) alpha | ((uint64_t) (cols & 0xff) << 16) | ((uint64_t) ((cols >> 8) & 0xff) << 32)
+                                 | ((uint64_t) ((cols >> 16) & 0xff) << 48);
+                        packed = pack_px<false> (o, d, P.luts);
+                    }
+                    uint8_t *o8 = P.dst + (size_t) img * P.dst_image_stride + (size_t) yl_cur * P.dst_pitch + (size_t) x * d.bpp_out;
+                    store_raw_px (o8, packed, d.bpp_out);
+                }
+            };
+
             if constexpr (RS)
                 prefetch3s (0, T);
             else
                 prefetch3 (0);
-            for (uint32_t r = T; r <= r_end; r++)
+            for (uint32_t r = T; r <= r_last; r++)
             {
-                if (r < r_end)
+                if (r < r_last)
                 {
                     if constexpr (RS)
                         prefetch3s (P.seg_bytes - cur, r + 1);
                     else
                         prefetch3 (P.seg_bytes - cur);
-                    cp_async_wait<1> ();
+                    if (!use_tma)
+                        cp_async_wait<1> ();
                 }
-                else
+                else if (!use_tma)
                     cp_async_wait<0> ();
+                if (use_tma)
+                {
+                    const uint32_t slot = cur ? 1u : 0u;
+                    mbar_wait (mbar0 + 8 * slot, (tma_parity >> slot) & 1u);
+                    tma_parity ^= 1u << slot;
+                }
                 __syncwarp ();
 
                 /* window address of the byte staged for row-relative offset win0 */
@@ -2826,22 +2960,33 @@ smol_box_kernel (const BoxParams P)
                 for (int i = 0; i < (S128 ? 4 : 2); i++) acc.v[i] = 0;
                 /* The row's pixel walk, instantiated per alpha position for the 32bpp table modes
                  * (immediate PRMT selectors; one uniform branch per row picks the instance). */
-                auto walk_row = [&] (auto ap_tag)
+                uint32_t alpha_and = 0xffffffffu;       /* AND of every pixel the opaque walk consumed */
+                auto walk_row = [&] (auto ap_tag, auto opaque_tag)
                 {
                 constexpr int AP = decltype (ap_tag)::value;
+                constexpr bool SPEC = decltype (opaque_tag)::value;
+                constexpr bool OPQ = OPAQUE || SPEC;
                 (void) AP;
+                const uint32_t tab_y = SPEC ? from_y + 128u : from_y;
                 /* unpack one pixel into the accumulators, table modes through box3_accum */
                 auto accum = [&] (uint32_t raw)
                 {
+                    if constexpr (SPEC)
+                        alpha_and &= raw;
                     if constexpr (NEED_FROM)
-                        box3_accum<MODE, false, OPAQUE, AP> (raw, 0, acc.v, P, from_y, inv_y);
+                        box3_accum<MODE, false, OPQ, AP> (raw, 0, acc.v, P, tab_y, inv_y);
                     else
                         box_add<MODE> (acc, box_unpack<MODE, 0> (raw, P, nullptr, nullptr, nullptr));
                 };
                 auto accum_w = [&] (uint32_t raw, uint32_t w)
                 {
+                    if constexpr (SPEC)
+                    {
+                        if (w > 0)
+                            alpha_and &= raw;
+                    }
                     if constexpr (NEED_FROM)
-                        box3_accum<MODE, true, OPAQUE, AP> (raw, w, acc.v, P, from_y, inv_y);
+                        box3_accum<MODE, true, OPQ, AP> (raw, w, acc.v, P, tab_y, inv_y);
                     else
                         box_add<MODE> (acc, box_weight<MODE> (box_unpack<MODE, 0> (raw, P, nullptr, nullptr, nullptr), w));
                 };
@@ -2894,15 +3039,45 @@ smol_box_kernel (const BoxParams P)
                         accum_w (fetch3 (hR), wr);
                 }
                 };
-                if constexpr (NEED_FROM && BI == 4)
+                bool row_done = false;
+                if constexpr (SPEC_OPAQUE)
                 {
-                    if (P.alpha_shift == 0)
-                        walk_row (std::integral_constant<int, 2> {});
+                    /* Speculate that the row's pixels are opaque: walk it with the alpha = 255 table while
+                     * ANDing the pixels together; if any lane met another alpha the row is redone the
+                     * general way and the warp does not try again for a while (random-alpha input pays
+                     * one wasted cheap walk per 64 rows, opaque input runs close to the 24bpp rate).
+                     * Measured (8K RGBA -> 800x450, linear light): opaque 56.5 -> 46.4 us per frame,
+                     * random alpha 56.5 -> 57.5 us (the second walk's code costs the first a little). */
+                    if (opaque_backoff == 0)
+                    {
+                        if (P.alpha_shift == 0)
+                            walk_row (std::integral_constant<int, 2> {}, std::true_type {});
+                        else
+                            walk_row (std::integral_constant<int, 1> {}, std::true_type {});
+                        const uint32_t amask = 0xffu << P.alpha_shift;
+                        row_done = __all_sync (0xffffffffu, (alpha_and & amask) == amask);
+                        if (!row_done)
+                        {
+                            opaque_backoff = 64;
+#pragma unroll
+                            for (int i = 0; i < 4; i++) acc.v[i] = 0;
+                        }
+                    }
                     else
-                        walk_row (std::integral_constant<int, 1> {});
+                        opaque_backoff--;
                 }
-                else
-                    walk_row (std::integral_constant<int, 0> {});
+                if (!row_done)
+                {
+                    if constexpr (NEED_FROM && BI == 4)
+                    {
+                        if (P.alpha_shift == 0)
+                            walk_row (std::integral_constant<int, 2> {}, std::false_type {});
+                        else
+                            walk_row (std::integral_constant<int, 1> {}, std::false_type {});
+                    }
+                    else
+                        walk_row (std::integral_constant<int, 0> {}, std::false_type {});
+                }
                 for (uint32_t m = G >> 1; m; m >>= 1)
                 {
 #pragma unroll
@@ -2925,13 +3100,41 @@ smol_box_kernel (const BoxParams P)
                 }
                 else
                     h = box_scale<MODE> (acc, d.span_mul_x, true);
-                if (r == T || r == B)
-                    box_add<MODE> (vacc, box_weight<MODE> (h, r == T ? w1 : w2));
+                if (top_pending)
+                {
+                    box_add<MODE> (vacc, box_weight<MODE> (h, w1_cur));
+                    top_pending = false;
+                }
+                else if (r == B_cur)
+                    box_add<MODE> (vacc, box_weight<MODE> (h, w2_cur));
                 else
                     box_add<MODE> (vacc, h);
+
+                if (r == rend_cur)
+                {
+                    emit_row ();
+                    if (++yl_cur < yl_stop)
+                    {
+                        const uint32_t yn = P.first_row + yl_cur;
+                        const uint32_t e0 = __ldg (&P.tab_y[yn]), e1 = __ldg (&P.tab_y[yn + 1]);
+                        const uint32_t F_new = SMOL_TAB_F (e0);
+                        w1_cur = 255u - Fy_cur;
+                        Fy_cur = F_new;
+                        const bool shared = r == B_cur;         /* this row also opens the next output row */
+                        B_cur = SMOL_TAB_OFS (e1);
+                        w2_cur = S128 ? F_new - 1 : F_new;
+                        rend_cur = F_new > 0 ? B_cur : B_cur - 1;
+#pragma unroll
+                        for (int i = 0; i < (S128 ? 4 : 2); i++) vacc.v[i] = 0;
+                        if (shared)
+                            box_add<MODE> (vacc, box_weight<MODE> (h, w1_cur));
+                        top_pending = !shared;
+                    }
+                }
                 cur = P.seg_bytes - cur;
                 __syncwarp ();      /* everyone is done with this slot before it is refilled */
             }
+            continue;               /* every row of the item has been stored */
         }
         else
         {
@@ -4433,8 +4636,19 @@ box_params_init (BoxParams &P, const SmolLaunch &L)
     P.sel_f1 = 0x7604u | ((d.in_col0 + 1u) << 4);
     P.sel_f2 = 0x7604u | ((d.in_col0 + 2u) << 4);
     P.warps_lo = 0;
+    P.rows_per_item = 1;
+    P.n_strips = L.n_rows;
     P.unroll2 = 1;
     P.prefetch = 0;
+    {
+        static int tma = -1;
+        if (tma < 0)
+        {
+            const char *e = getenv ("SMOL_BOX_TMA");
+            tma = e ? atoi (e) != 0 : 0;
+        }
+        P.use_tma = (uint32_t) tma;
+    }
     P.mul8_x = d.span_mul_x << 8;
     P.mul8_y = d.span_mul_y << 8;
     {
@@ -4496,7 +4710,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         const uint64_t seg_px0 = ((uint64_t) (32u >> glog0) * d.w_in + d.w_out - 1) / d.w_out + 3;
         const size_t per_warp0 = 2 * (size_t) ((seg_px0 * d.bpp_in + 32 + 15) & ~(uint64_t) 15);
         const size_t win_hi0 = mode == BM_P8L_P && d.bpp_in != 3 ? 0x30000 : 0x20000;    /* 24bpp: no inverse table (box3_accum) */
-        if ((0x10000 - 0x480) / per_warp0 + (225 * 1024 - 64 - (win_hi0 - 0x400)) / per_warp0 < 8)
+        if ((0x10000 - SMOL_BOX3_DYN_WIN_MAX) / per_warp0 + (225 * 1024 - 64 - (win_hi0 - 0x400)) / per_warp0 < 8)
             lutm = 2;
     }
 
@@ -4566,31 +4780,50 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
             const size_t win_hi = lut_bytes == 131072 ? 0x30000 : 0x20000;
             const size_t dyn_max = 225 * 1024 - 64;
             /* without tables the buffers are simply contiguous ("lo" = all of them) */
-            const size_t lo_room = has_lut ? 0x10000 - 0x480 : dyn_max, hi_room = has_lut ? dyn_max - (win_hi - 0x400) : 0;
+            const size_t lo_room = has_lut ? 0x10000 - SMOL_BOX3_DYN_WIN_MAX : dyn_max, hi_room = has_lut ? dyn_max - (win_hi - 0x400) : 0;
             uint32_t lo = (uint32_t) (lo_room / per_warp), hi = (uint32_t) (hi_room / per_warp);
             lo = lo > SMOL_BOX3_MAX_WARPS ? SMOL_BOX3_MAX_WARPS : lo;
             hi = hi > SMOL_BOX3_MAX_WARPS - lo ? SMOL_BOX3_MAX_WARPS - lo : hi;
-            /* Every work item costs the same and a warp takes ceil (items / warps) of them, so
-             * the kernel's length is quantised: among the warp counts that fit (down to 5/8 of
-             * the most) take the one that wastes the smallest share of its last round. */
+            /* An item is a column tile x a strip of K consecutive output rows; strips share their
+             * boundary source rows, so an item costs about K (R - 1) + 1 source rows (R = rows per
+             * output row).  A warp takes ceil (items / warps) items and the SM's issue slots are
+             * split between its warps, so the time goes like rounds x rows per item x warps:
+             * among the strip lengths and the warp counts that fit (down to 5/8 of the most) take
+             * the cheapest, preferring more warps when it is close (latency hiding). */
             {
                 const uint32_t w_max = lo + hi;
-                const uint64_t items = (uint64_t) ((d.w_out + cols - 1) / cols) * L.n_rows * L.n_images;
-                uint32_t best_w = w_max;
-                double best_eff = 0.0;
-                for (uint32_t w = w_max; w >= 8 && w * 8 >= w_max * 5; w--)
+                const uint32_t x_tiles = (d.w_out + cols - 1) / cols;
+                const double R = (double) d.h_in / d.h_out + 1.0;
+                static int tune_k = -1;
+                if (tune_k < 0)
                 {
-                    const uint64_t slots = (uint64_t) num_sms () * w;
-                    const uint64_t rounds = (items + slots - 1) / slots;
-                    const double eff = (double) items / (double) (rounds * slots);
-                    if (eff > best_eff + 0.02)
+                    const char *e = getenv ("SMOL_BOX_ROWS_PER_ITEM");
+                    tune_k = e ? atoi (e) : 0;
+                }
+                uint32_t best_w = w_max, best_k = 1;
+                double best_cost = 1e300;
+                for (uint32_t k = 1; k <= 8 && k <= L.n_rows; k++)
+                {
+                    if (tune_k > 0 && k != (uint32_t) tune_k && !(k == L.n_rows && (uint32_t) tune_k > L.n_rows))
+                        continue;
+                    const uint64_t items = (uint64_t) x_tiles * ((L.n_rows + k - 1) / k) * L.n_images;
+                    for (uint32_t w = w_max; w >= 8 && w * 8 >= w_max * 5; w--)
                     {
-                        best_eff = eff;
-                        best_w = w;
+                        const uint64_t slots = (uint64_t) num_sms () * w;
+                        const uint64_t rounds = (items + slots - 1) / slots;
+                        const double cost = (double) rounds * (k * (R - 1.0) + 1.0) * w * (1.0 + 0.15 * (w_max - w) / w_max);
+                        if (cost < best_cost * 0.99)
+                        {
+                            best_cost = cost;
+                            best_w = w;
+                            best_k = k;
+                        }
                     }
                 }
                 if (tune_wpc > 0 && (uint32_t) tune_wpc <= w_max)
                     best_w = (uint32_t) tune_wpc;
+                P.rows_per_item = best_k;
+                P.n_strips = (L.n_rows + best_k - 1) / best_k;
                 if (best_w < lo)
                     lo = best_w;
                 hi = best_w - lo;
@@ -4605,12 +4838,13 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, (int) warps_per_cta * 32, smem) != cudaSuccess || occ < 1)
             occ = 1;
         per_sm = (uint32_t) occ;
+        /* (column tiles x output rows: strips are chosen after G, they must not make it grow) */
         const double rounds = (double) P.x_tiles * L.n_rows * L.n_images / ((double) num_sms () * per_sm * warps_per_cta);
         if (tune_g != 99 || glog >= 5 || rounds >= 1.0)
             break;
     }
 
-    const uint64_t n_items = (uint64_t) P.x_tiles * L.n_rows * L.n_images;
+    const uint64_t n_items = (uint64_t) P.x_tiles * P.n_strips * L.n_images;
     uint64_t blocks = (n_items + warps_per_cta - 1) / warps_per_cta;
     if (blocks > (uint64_t) num_sms () * per_sm)
         blocks = (uint64_t) num_sms () * per_sm;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Time one job shape on the GPU: N distinct frames per step through smol_scale_simple with
 device-resident buffers, replayed as a CUDA graph (the bench.py protocol for an arbitrary job).
-Usage: time_job.py WI HI WO HO TYPE_IN TYPE_OUT SRGB [FRAMES] [--align]  (pitches padded to 16 bytes with --align;
+Usage: time_job.py WI HI WO HO TYPE_IN TYPE_OUT SRGB [FRAMES] [--align] [--opaque]  (pitches padded to 16 bytes with --align;
 SMOL_FORCE_KERNEL=<id> forces a kernel family)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,6 +17,9 @@ if align:
 if os.environ.get("SMOL_FORCE_KERNEL"):
     sb.force_kernel(int(os.environ["SMOL_FORCE_KERNEL"]))
 d_in = torch.randint(0, 256, (frames, hi * si), dtype=torch.uint8, device="cuda")
+if "--opaque" in sys.argv and bi == 4:
+    # every alpha byte 255 (a photograph in an RGBA container); needs pitch == width * 4
+    d_in.view(frames, -1, 4)[:, :, 3 if (ti & 3) < 2 else 0] = 255
 d_out = torch.zeros((frames, ho * so), dtype=torch.uint8, device="cuda")
 stream = torch.cuda.Stream()
 with torch.cuda.stream(stream):
