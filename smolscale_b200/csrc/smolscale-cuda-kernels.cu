@@ -1365,6 +1365,8 @@ struct Taps0Params
     uint32_t src_u32_ok;            /* 32bpp source rows are 4-byte aligned */
     uint32_t prefetch;              /* CTAs (in launch order) that L2-prefetch their first source rows on entry (see prefetch_l2) */
     uint32_t row_ahead;             /* taps0: L1-prefetch the source row this many rows below the one being fetched (0: off) */
+    const uint16_t *from_srgb;      /* taps0w, linear light */
+    const uint8_t *to_srgb;
 };
 
 template <int BI, bool IU, bool AF, bool U32OK>
@@ -3447,6 +3449,201 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
 }
 
 /* ------------------------------------------------------------------------------------------ *
+ * "taps0w" kernel: bilinear without halvings / copy / one on both axes for the unassociated ->    *
+ * unassociated pairs (reference smolscale.c:751-758: 16 bits per channel internally, P16 / P16L), *
+ * 32bpp on both sides, 4-byte-aligned rows.  The 128bpp counterpart of smol_taps0_kernel: a thread *
+ * owns two adjacent output columns and walks a strip of output rows with the last two             *
+ * horizontally filtered source rows ping-ponging between two register sets (the reference's      *
+ * two-row cache, generic:1648-1682), four 32-bit lanes per pixel.  P16 needs no tables on unpack  *
+ * (value x alpha, generic:616-660); the repack's inverse-division table (and, in linear light,   *
+ * the two sRGB tables) sit in shared memory.  Replaces one-thread-per-pixel taps128 / the tile    *
+ * kernel for these jobs (4K 1:1: 82 us -> see DESIGN.md).                                          *
+ * ------------------------------------------------------------------------------------------ */
+
+struct PxW { uint32_t v[4]; };      /* v[0]: alpha lane (alpha << 8 | 0x80), v[1..3]: colour x alpha, source byte order */
+
+template <bool LINEAR, bool AF>
+__device__ __forceinline__ PxW taps0w_fetch (const uint8_t *row, uint32_t x, const uint16_t *__restrict__ sm_from)
+{
+    const uint32_t raw = __ldg (reinterpret_cast<const uint32_t *> (row) + x);
+    const uint32_t alpha = AF ? raw & 0xffu : raw >> 24;
+    uint32_t c0 = __byte_perm (raw, 0, AF ? 0x4441 : 0x4440), c1 = __byte_perm (raw, 0, AF ? 0x4442 : 0x4441),
+             c2 = __byte_perm (raw, 0, AF ? 0x4443 : 0x4442);
+    if constexpr (LINEAR)
+    {
+        c0 = sm_from[c0]; c1 = sm_from[c1]; c2 = sm_from[c2];      /* generic:708-752 */
+    }
+    PxW r;
+    r.v[0] = (alpha << 8) | 0x80u;                                  /* generic:616-625 */
+    r.v[1] = c0 * alpha; r.v[2] = c1 * alpha; r.v[3] = c2 * alpha;
+    return r;
+}
+
+template <bool LINEAR, bool AF>
+__global__ void __launch_bounds__ (256)
+smol_taps0w_kernel (const Taps0Params T)
+{
+    constexpr int PX = 2;
+    __shared__ uint32_t sm_inv[256];
+    __shared__ uint16_t sm_from[LINEAR ? 256 : 2];
+    __shared__ uint8_t sm_to_srgb[LINEAR ? 2048 : 4];
+    const TapsParams &P = T.t;
+
+    pdl_launch_dependents ();
+    {
+        /* library-owned constant data: readable before the dependency wait.  P.inv_div_p8 carries
+         * the table this mode needs (inv_div_p16 or inv_div_p16l). */
+        const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+        for (uint32_t i = t; i < 256; i += nt)
+        {
+            sm_inv[i] = __ldg (&P.inv_div_p8[i]);
+            if constexpr (LINEAR)
+                sm_from[i] = __ldg (&T.from_srgb[i]);
+        }
+        if constexpr (LINEAR)
+            for (uint32_t i = t; i < 512; i += nt)
+                reinterpret_cast<uint32_t *> (sm_to_srgb)[i] = __ldg (reinterpret_cast<const uint32_t *> (T.to_srgb) + i);
+        __syncthreads ();
+    }
+
+    const uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
+    const uint32_t strip = blockIdx.y * blockDim.y + threadIdx.y;
+    const uint32_t yl0 = strip * P.rows_per_thread;
+    if (x >= P.w_out || yl0 >= P.n_rows)
+        return;
+    const uint32_t yl1 = min (yl0 + P.rows_per_thread, P.n_rows);
+    const uint32_t n_px = min ((uint32_t) PX, P.w_out - x);
+
+    uint32_t op[PX], oq[PX], Fx[PX];
+#pragma unroll
+    for (int o = 0; o < PX; o++)
+    {
+        const uint32_t e = __ldg (&P.tab_x[min (x + o, P.w_out - 1)]);
+        op[o] = SMOL_TAB_OFS (e);
+        oq[o] = min (op[o] + 1, P.w_in - 1);
+        Fx[o] = SMOL_TAB_F (e);
+    }
+
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
+    uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl0 * P.dst_pitch + (size_t) x * 4;
+    const bool store8 = n_px == PX && (reinterpret_cast<uintptr_t> (dst) & 7) == 0 && (P.dst_pitch & 7) == 0;
+
+    if (in_first_wave (T.prefetch))
+    {
+        const uint32_t r = SMOL_TAB_OFS (__ldg (&P.tab_y[P.first_row + yl0]));
+        const uint8_t *p = src + (size_t) r * P.src_pitch + (size_t) op[0] * 4;
+        prefetch_l2 (p);
+        prefetch_l2 (p + (size_t) (r + 1 < P.h_in ? P.src_pitch : 0));
+    }
+    pdl_wait ();
+
+    auto hrow = [&] (uint32_t r, PxW *out)
+    {
+        const uint8_t *row = src + (size_t) min (r, P.h_in - 1) * P.src_pitch;
+        if (T.row_ahead && r + T.row_ahead < P.h_in)
+            prefetch_l1 (row + (size_t) T.row_ahead * P.src_pitch + (size_t) op[0] * 4);
+#pragma unroll
+        for (int o = 0; o < PX; o++)
+        {
+            const PxW p = taps0w_fetch<LINEAR, AF> (row, op[o], sm_from);
+            const PxW q = taps0w_fetch<LINEAR, AF> (row, oq[o], sm_from);
+            const uint32_t F = Fx[o], G = 256u - F;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                out[o].v[i] = (p.v[i] * F + q.v[i] * G) >> 8;       /* lanes stay below 2^24: the reference's mask cannot bite */
+        }
+    };
+
+    auto emit = [&] (const PxW *top, const PxW *bot, uint32_t F)
+    {
+        const uint32_t G = 256u - F;
+        uint32_t out[PX];
+#pragma unroll
+        for (int o = 0; o < PX; o++)
+        {
+            uint32_t fin[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                fin[i] = (top[o].v[i] * F + bot[o].v[i] * G) >> 8;
+            /* repack (generic:1136-1164 via :290-318): every kept field lies in the low 32 bits of the products */
+            const uint32_t a = (fin[0] >> 8) & 0xffu;
+            const uint32_t inv = sm_inv[a];
+            uint32_t c[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+            {
+                if constexpr (LINEAR)
+                    c[i] = sm_to_srgb[((fin[i + 1] * inv) >> 19) & 0x7ffu];
+                else
+                    c[i] = __byte_perm (fin[i + 1] * inv, 0, 0x4442);
+            }
+            /* the pixel in source byte order, then the job's byte permutation */
+            const uint32_t cc = c[0] | (c[1] << 8) | (c[2] << 16);
+            const uint32_t v = AF ? (cc << 8) | a : cc | (a << 24);
+            out[o] = __byte_perm (v, 0, P.prmt_sel);
+        }
+        if (store8)
+            *reinterpret_cast<uint2 *> (dst) = make_uint2 (out[0], out[1]);
+        else
+        {
+            reinterpret_cast<uint32_t *> (dst)[0] = out[0];
+            if (n_px > 1)
+                reinterpret_cast<uint32_t *> (dst)[1] = out[1];
+        }
+        dst += P.dst_pitch;
+    };
+
+    const uint32_t *ty = P.tab_y + P.first_row;
+    uint32_t yl = yl0;
+    uint32_t e = __ldg (&ty[yl]);
+    uint32_t r = SMOL_TAB_OFS (e);
+    PxW A[PX], B[PX];
+    hrow (r, A);
+    hrow (r + 1, B);
+
+    for (;;)
+    {
+        /* phase A: top row in A, bottom row in B */
+        do
+        {
+            emit (A, B, SMOL_TAB_F (e));
+            if (++yl >= yl1)
+                return;
+            e = __ldg (&ty[yl]);
+        }
+        while (SMOL_TAB_OFS (e) == r);
+        if (SMOL_TAB_OFS (e) != r + 1)
+        {
+            r = SMOL_TAB_OFS (e);
+            hrow (r, A);
+            hrow (r + 1, B);
+            continue;
+        }
+        r++;
+        hrow (r + 1, A);
+
+        /* phase B: the other way round */
+        do
+        {
+            emit (B, A, SMOL_TAB_F (e));
+            if (++yl >= yl1)
+                return;
+            e = __ldg (&ty[yl]);
+        }
+        while (SMOL_TAB_OFS (e) == r);
+        if (SMOL_TAB_OFS (e) != r + 1)
+        {
+            r = SMOL_TAB_OFS (e);
+            hrow (r, A);
+            hrow (r + 1, B);
+            continue;
+        }
+        r++;
+        hrow (r + 1, B);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ *
  * "tile128" kernel: bilinear without halvings / copy / one on both axes (anything from 1:2 to     *
  * any magnification) with a 128bpp intermediate -- linear light and unassociated -> unassociated. *
  * Same two-phase shared-memory tile as the mag kernel, because here the unpack chain is the       *
@@ -4853,6 +5050,77 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     return launch_pdl_ptr (fn, &P, grid, block, smem, stream);
 }
 
+static void taps_params_init (TapsParams &P, const SmolLaunch &L);
+
+/* unassociated -> unassociated without halvings, 32bpp both sides, word-aligned rows: smol_taps0w_kernel */
+static bool
+taps0w_eligible (const SmolLaunch &L)
+{
+    const SmolJobDesc &d = L.d;
+    static int on = -1;
+    if (on < 0)
+    {
+        const char *e = getenv ("SMOL_TAPS0W");
+        on = e ? atoi (e) : 1;
+    }
+    return on && d.h_kind == SMOL_AXIS_TAPS && d.v_kind == SMOL_AXIS_TAPS && d.storage128
+           && (d.mid == SMOL_MID_P16 || d.mid == SMOL_MID_P16L) && d.h_halvings == 0 && d.v_halvings == 0
+           && d.bpp_in == 4 && d.bpp_out == 4
+           && aligned4 (L.src) && aligned4 (L.dst) && (L.src_pitch & 3) == 0 && (L.dst_pitch & 3) == 0
+           && (L.src_image_stride & 3) == 0 && (L.dst_image_stride & 3) == 0;
+}
+
+static cudaError_t
+launch_taps0w (const SmolLaunch &L, cudaStream_t stream)
+{
+    const SmolJobDesc &d = L.d;
+    Taps0Params T;
+
+    memset (&T, 0, sizeof (T));
+    taps_params_init (T.t, L);
+    const bool linear = d.mid == SMOL_MID_P16L;
+    T.t.inv_div_p8 = linear ? L.luts->inv_div_p16l : L.luts->inv_div_p16;      /* the repack table of this mode */
+    T.from_srgb = L.luts->from_srgb;
+    T.to_srgb = L.luts->to_srgb;
+
+    const uint64_t x_threads = (d.w_out + 1) / 2;
+    const uint64_t want_threads = (uint64_t) num_sms () * 1536;
+    uint32_t rpt = 16;
+    while (rpt > 1 && x_threads * ((L.n_rows + rpt - 1) / rpt) * L.n_images < want_threads)
+        rpt >>= 1;
+    if (d.h_in <= d.h_out && rpt < 4)
+        rpt = 4;                        /* magnification: row reuse matters more than thread count */
+    {
+        static int tune_rpt = -1;
+        if (tune_rpt < 0)
+        {
+            const char *e = getenv ("SMOL_TAPS0W_RPT");
+            tune_rpt = e ? atoi (e) : 0;
+        }
+        if (tune_rpt > 0)
+            rpt = (uint32_t) tune_rpt;
+    }
+    T.t.rows_per_thread = rpt;
+    uint32_t bx = 32;
+    while (bx < 128 && bx < x_threads)
+        bx *= 2;
+    const uint32_t strips = (L.n_rows + rpt - 1) / rpt;
+    uint32_t by = 256 / bx;
+    if (by > strips)
+        by = strips;
+    dim3 block (bx, by), grid ((unsigned) ((x_threads + bx - 1) / bx), (strips + by - 1) / by, L.n_images);
+    T.prefetch = pdl_first_wave (256, 4096);
+    if (T.prefetch)
+        T.prefetch = 0xffffffffu;       /* tables are staged first: see launch_half */
+    T.row_ahead = 2;
+    const bool af = d.in_alpha_idx == 0;
+    if (linear)
+        return af ? launch_pdl (smol_taps0w_kernel<true, true>, T, grid, block, 0, stream)
+                  : launch_pdl (smol_taps0w_kernel<true, false>, T, grid, block, 0, stream);
+    return af ? launch_pdl (smol_taps0w_kernel<false, true>, T, grid, block, 0, stream)
+              : launch_pdl (smol_taps0w_kernel<false, false>, T, grid, block, 0, stream);
+}
+
 static void box_params_init (BoxParams &P, const SmolLaunch &L);
 
 static cudaError_t
@@ -4860,6 +5128,9 @@ launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
 {
     const SmolJobDesc &d = L.d;
     BoxParams P;
+
+    if (taps0w_eligible (L))
+        return launch_taps0w (L, stream);
 
     box_params_init (P, L);
     const uint32_t src_u32_ok = d.bpp_in == 3 || ((reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
@@ -4940,6 +5211,9 @@ launch_tile128 (const SmolLaunch &L, cudaStream_t stream)
 {
     const SmolJobDesc &d = L.d;
     Tile128Params M;
+
+    if (taps0w_eligible (L))
+        return launch_taps0w (L, stream);
 
     box_params_init (M.b, L);
     M.src_u32_ok = d.bpp_in == 3 || ((reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0

@@ -12,7 +12,7 @@ last source pixel, and a solid colour with channel > alph
 every path.  Geometries that miss the bar are re-run on the CPU oracle: the GPU result must equal the
 oracle's bit for bit (that is the parity bar), and the deviation from the colour is recorded.
 
-Usage: check_sweep.py [--step N] [--colours N]     (--step 1 = exhaustive, about 262,000 geometries)
+Usage: check_sweep.py [--step N] [--step-v N] [--colours N]     (--step 1 = exhaustive, about 262,000 geometries)
 Output: one JSON object."""
 import argparse
 import json
@@ -28,7 +28,9 @@ import oracle
 import smolscale_b200 as sb
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--step", type=int, default=1)
+ap.add_argument("--step", type=int, default=1, help="stride of the horizontal sweeps")
+ap.add_argument("--step-v", type=int, default=0, help="stride of the vertical sweeps (0 = same as --step); a one-pixel-wide "
+                "65535-row image is one serial chain per colour, ~30 ms per geometry")
 ap.add_argument("--colours", type=int, default=64)
 ap.add_argument("--max", type=int, default=65535)
 args = ap.parse_args()
@@ -43,11 +45,11 @@ canvas = d_colours[:, None].expand(n_col, N).contiguous()          # [colour][pi
 out = torch.empty((n_col, N), dtype=torch.int32, device="cuda")
 sb.set_stream(torch.cuda.current_stream().cuda_stream)
 
-res = {"step": args.step, "colours": n_col, "sweeps": [], "what": "reference check mode (test.c:1128-1298) restated"}
+res = {"step_horizontal": args.step, "step_vertical": args.step_v or args.step, "colours": n_col, "sweeps": [], "what": "reference check mode (test.c:1128-1298) restated"}
 t_all = time.time()
 for name, vertical, fixed_in in (("width i -> 1", False, False), ("height i -> 1", True, False),
                                  ("width 65535 -> i", False, True), ("height 65535 -> i", True, True)):
-    sizes = list(range(1, N + 1, args.step))
+    sizes = list(range(1, N + 1, (args.step_v or args.step) if vertical else args.step))
     if sizes[-1] != N:
         sizes.append(N)
     exact = deviating = 0
