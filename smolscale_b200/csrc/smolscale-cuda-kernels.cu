@@ -326,6 +326,64 @@ __device__ __forceinline__ void store_px4_aligned (uint8_t *dst, const uint32_t 
     }
 }
 
+/* Four finished 24bpp pixels (12 bytes) of one thread to a destination row at ANY byte alignment
+ * (tightly packed RGB rows of odd width: 3 x width is rarely a multiple of four).  All threads of a
+ * warp sit in one output row, 12 bytes apart, so the row's misalignment `phi` is warp-uniform and
+ * the aligned words of the row interleave the threads' bytes: a thread writes the three aligned
+ * words that start inside its own 12 bytes, taking the first (4 - phi) bytes of the word that
+ * straddles into its right-hand neighbour from that neighbour by shuffle.  Only a warp's first
+ * and last lanes (and the row's ragged end) touch single bytes.  `mask`: the warp's live lanes
+ * (they never change inside the row walk); `has_next`: the lane to the right is live and owns at
+ * least one pixel; n_px: valid pixels of this thread (1..4). */
+__device__ __forceinline__ void
+store_px4_rgb_anywhere (uint8_t *dst, const uint32_t out[4], uint32_t n_px, unsigned mask, bool has_next)
+{
+    const uint32_t o0 = __byte_perm (out[0], out[1], 0x4210), o1 = __byte_perm (out[1], out[2], 0x5421),
+                   o2 = __byte_perm (out[2], out[3], 0x6542);
+    const uint32_t phi = (uint32_t) reinterpret_cast<uintptr_t> (dst) & 3u;
+    const uint32_t nxt = __shfl_down_sync (mask, o0, 1);
+    const bool has_prev = (threadIdx.x & 31) != 0;      /* the lane to the left writes this thread's first 4 - phi bytes */
+
+    if (phi == 0 && n_px == 4)
+    {
+        uint32_t *d32 = reinterpret_cast<uint32_t *> (dst);
+        d32[0] = o0; d32[1] = o1; d32[2] = o2;
+        return;
+    }
+    const uint32_t lead = phi ? 4u - phi : 0u;          /* bytes before this thread's first aligned word */
+    auto byte_at = [&] (uint32_t j) -> uint8_t
+    {
+        const uint32_t w = j < 4 ? o0 : j < 8 ? o1 : o2;
+        return (uint8_t) (w >> ((j & 3) * 8));
+    };
+    if (n_px == 4 && phi != 0)
+    {
+        const uint32_t sh = lead * 8;
+        uint32_t *d32 = reinterpret_cast<uint32_t *> (dst + lead);
+        d32[0] = __funnelshift_r (o0, o1, sh);
+        d32[1] = __funnelshift_r (o1, o2, sh);
+        if (has_next)
+            d32[2] = __funnelshift_r (o2, nxt, sh);
+        else
+        {
+#pragma unroll 1
+            for (uint32_t j = 8 + lead; j < 12; j++)
+                dst[j] = byte_at (j);
+        }
+        if (!has_prev)
+        {
+#pragma unroll 1
+            for (uint32_t j = 0; j < lead; j++)
+                dst[j] = byte_at (j);
+        }
+        return;
+    }
+    /* ragged end of the row (or an aligned row's short last thread): bytes, minus what the left lane wrote */
+#pragma unroll 1
+    for (uint32_t j = (has_prev && phi != 0) ? lead : 0u; j < 3 * n_px; j++)
+        dst[j] = byte_at (j);
+}
+
 __device__ __forceinline__ uint4 ldg_nc_v4 (const void *p)
 {
     uint4 r;
@@ -1365,8 +1423,6 @@ struct Taps0Params
     uint32_t src_u32_ok;            /* 32bpp source rows are 4-byte aligned */
     uint32_t prefetch;              /* CTAs (in launch order) that L2-prefetch their first source rows on entry (see prefetch_l2) */
     uint32_t row_ahead;             /* taps0: L1-prefetch the source row this many rows below the one being fetched (0: off) */
-    const uint16_t *from_srgb;      /* taps0w, linear light */
-    const uint8_t *to_srgb;
 };
 
 template <int BI, bool IU, bool AF, bool U32OK>
@@ -1432,6 +1488,11 @@ smol_taps0_kernel (const Taps0Params T)
         return;
     const uint32_t yl1 = min (yl0 + P.rows_per_thread, P.n_rows);
     const uint32_t n_px = min ((uint32_t) PX, P.w_out - x);
+    /* 24bpp stores cooperate across the warp's lanes (store_px4_rgb_anywhere): the lanes that got
+     * here all walk the same strip of the same row range, so the live set never changes */
+    const unsigned live_mask = __activemask ();
+    const bool has_next = (threadIdx.x & 31) != 31 && x + PX < P.w_out;
+    (void) live_mask; (void) has_next;
 
     /* this thread's four horizontal taps never change */
     uint32_t op[PX], oq[PX], Fx[PX];
@@ -1495,6 +1556,8 @@ smol_taps0_kernel (const Taps0Params T)
         }
         if constexpr (PX == 1)
             *reinterpret_cast<uint32_t *> (dst) = out[0];       /* PX == 1 implies BO == 4 and FASTIO */
+        else if constexpr (BO == 3)
+            store_px4_rgb_anywhere (dst, out, n_px, live_mask, has_next);
         else if (fast_store)
             store_px4_aligned<BO> (dst, out);
         else
@@ -3232,8 +3295,9 @@ smol_box_kernel (const BoxParams P)
 template <int MODE>
 __device__ __forceinline__ uint32_t
 pack128_fast (const uint32_t lane[4], const SmolJobDesc &d, const SmolDeviceLuts *__restrict__ lut,
-              const uint8_t *__restrict__ sm_to_srgb)
+              const uint8_t *__restrict__ sm_to_srgb, const uint32_t *__restrict__ sm_inv = nullptr)
 {
+    /* sm_inv: the mode's inverse-division table in shared memory, if the caller staged one */
     uint32_t a, c[3];
 
     if constexpr (MODE == BM_P16_U || MODE == BM_P16L_U)
@@ -3243,14 +3307,14 @@ pack128_fast (const uint32_t lane[4], const SmolJobDesc &d, const SmolDeviceLuts
 
     if constexpr (MODE == BM_P16_U)
     {
-        const uint32_t inv = __ldg (&lut->inv_div_p16[a]);
+        const uint32_t inv = sm_inv ? sm_inv[a] : __ldg (&lut->inv_div_p16[a]);
 #pragma unroll
         for (int i = 0; i < 3; i++)
             c[i] = __byte_perm (lane[i + 1] * inv, 0, 0x4442);           /* (v * inv) >> 16 & 0xff, generic:290-299 */
     }
     else if constexpr (MODE == BM_P16L_U)
     {
-        const uint32_t inv = __ldg (&lut->inv_div_p16l[a]);
+        const uint32_t inv = sm_inv ? sm_inv[a] : __ldg (&lut->inv_div_p16l[a]);
 #pragma unroll
         for (int i = 0; i < 3; i++)
             c[i] = sm_to_srgb[((lane[i + 1] * inv) >> 19) & 0x7ff];      /* generic:309-318 */
@@ -3258,7 +3322,7 @@ pack128_fast (const uint32_t lane[4], const SmolJobDesc &d, const SmolDeviceLuts
     else
     {
         /* P8L (generic:1096-1134, 24bpp :922-935 / :1010-1023) */
-        const uint32_t inv = __ldg (&lut->inv_div_p8l[a]);
+        const uint32_t inv = sm_inv ? sm_inv[a] : __ldg (&lut->inv_div_p8l[a]);
         const bool unpremul = !(d.bpp_out == 3 && d.pack24_direct);
         const bool repremul = d.bpp_out == 4 && !d.out_unassoc;
 #pragma unroll
@@ -3449,60 +3513,111 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
 }
 
 /* ------------------------------------------------------------------------------------------ *
- * "taps0w" kernel: bilinear without halvings / copy / one on both axes for the unassociated ->    *
- * unassociated pairs (reference smolscale.c:751-758: 16 bits per channel internally, P16 / P16L), *
- * 32bpp on both sides, 4-byte-aligned rows.  The 128bpp counterpart of smol_taps0_kernel: a thread *
- * owns two adjacent output columns and walks a strip of output rows with the last two             *
- * horizontally filtered source rows ping-ponging between two register sets (the reference's      *
- * two-row cache, generic:1648-1682), four 32-bit lanes per pixel.  P16 needs no tables on unpack  *
- * (value x alpha, generic:616-660); the repack's inverse-division table (and, in linear light,   *
- * the two sRGB tables) sit in shared memory.  Replaces one-thread-per-pixel taps128 / the tile    *
- * kernel for these jobs (4K 1:1: 82 us -> see DESIGN.md).                                          *
+ * "taps0w" kernel: bilinear without halvings / copy / one on both axes with a 128bpp             *
+ * intermediate -- linear light (P8L) and unassociated -> unassociated (P16 / P16L; reference      *
+ * smolscale.c:751-758) -- word-aligned 32bpp rows (24bpp: any).  The 128bpp counterpart of        *
+ * smol_taps0_kernel: a thread owns PX adjacent output columns and walks a strip of output rows    *
+ * with the last two horizontally filtered source rows ping-ponging between two register sets     *
+ * (the reference's two-row cache, generic:1648-1682), four 32-bit lanes per pixel.  The data      *
+ * tables are plain shared-memory copies (a strip kernel runs the unpack chain about once per      *
+ * output pixel, so a few bank conflicts cost less than 64 KB of lane-replicated tables per CTA).  *
+ * Replaces the one-thread-per-pixel taps128 / the tile kernel for these jobs: 4K 1:1              *
+ * unassociated 82 -> 29 us, 2x up 42 -> 21 us (B200).                                             *
  * ------------------------------------------------------------------------------------------ */
 
-struct PxW { uint32_t v[4]; };      /* v[0]: alpha lane (alpha << 8 | 0x80), v[1..3]: colour x alpha, source byte order */
+struct PxW { uint32_t v[4]; };      /* v[0]: alpha lane, v[1..3]: colour lanes in source colour order (box_unpack's layout) */
 
-template <bool LINEAR, bool AF>
-__device__ __forceinline__ PxW taps0w_fetch (const uint8_t *row, uint32_t x, const uint16_t *__restrict__ sm_from)
+struct Taps0wParams
 {
-    const uint32_t raw = __ldg (reinterpret_cast<const uint32_t *> (row) + x);
-    const uint32_t alpha = AF ? raw & 0xffu : raw >> 24;
-    uint32_t c0 = __byte_perm (raw, 0, AF ? 0x4441 : 0x4440), c1 = __byte_perm (raw, 0, AF ? 0x4442 : 0x4441),
-             c2 = __byte_perm (raw, 0, AF ? 0x4443 : 0x4442);
-    if constexpr (LINEAR)
+    TapsParams t;
+    SmolJobDesc d;
+    const SmolDeviceLuts *luts;
+    uint32_t prefetch, row_ahead;
+};
+
+/* sm_from: from_srgb + 1 (P8L), from_srgb (P16L), or for opaque 24bpp sources the whole chain's
+ * result ((from_srgb + 1) * 2041 - 1) >> 11 (see box3_accum) */
+template <int MODE, int BI, bool AF>
+__device__ __forceinline__ PxW
+taps0w_fetch (const uint8_t *row, uint32_t x, const uint32_t *__restrict__ sm_inv8, const uint16_t *__restrict__ sm_from)
+{
+    uint32_t raw;
+    if constexpr (BI == 4)
+        raw = __ldg (reinterpret_cast<const uint32_t *> (row) + x);
+    else
     {
-        c0 = sm_from[c0]; c1 = sm_from[c1]; c2 = sm_from[c2];      /* generic:708-752 */
+        const uint8_t *p = row + (size_t) x * 3;
+        raw = (uint32_t) __ldg (p) | ((uint32_t) __ldg (p + 1) << 8) | ((uint32_t) __ldg (p + 2) << 16) | 0xff000000u;
     }
+    constexpr bool af = BI == 4 && AF;
+    const uint32_t alpha = af ? raw & 0xffu : raw >> 24;
+    uint32_t c[3] = { __byte_perm (raw, 0, af ? 0x4441 : 0x4440), __byte_perm (raw, 0, af ? 0x4442 : 0x4441),
+                      __byte_perm (raw, 0, af ? 0x4443 : 0x4442) };
     PxW r;
-    r.v[0] = (alpha << 8) | 0x80u;                                  /* generic:616-625 */
-    r.v[1] = c0 * alpha; r.v[2] = c1 * alpha; r.v[3] = c2 * alpha;
+    if constexpr (MODE == BM_P16_U || MODE == BM_P16L_U)
+    {
+        r.v[0] = (alpha << 8) | 0x80u;                              /* generic:616-625 */
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            r.v[i + 1] = (MODE == BM_P16L_U ? (uint32_t) sm_from[c[i]] : c[i]) * alpha;     /* generic:616-660, :708-752 */
+    }
+    else if constexpr (BI == 3)
+    {
+        r.v[0] = 255u;                                              /* opaque: one table read per channel */
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            r.v[i + 1] = sm_from[c[i]];
+    }
+    else
+    {
+        const uint32_t m = alpha * 8 + 1;
+        if constexpr (MODE == BM_P8L_P)
+        {
+            const uint32_t inv8 = sm_inv8[alpha];                   /* unpremultiply, generic:227-236 */
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                c[i] = __byte_perm (c[i] * inv8, 0, 0x4442);
+        }
+        r.v[0] = alpha;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            r.v[i + 1] = ((uint32_t) sm_from[c[i]] * m - 1) >> 11;  /* ((lin + 1) * m - 1) >> 11, generic:261-269 */
+    }
     return r;
 }
 
-template <bool LINEAR, bool AF>
+template <int MODE, int BI, int BO, bool AF>
 __global__ void __launch_bounds__ (256)
-smol_taps0w_kernel (const Taps0Params T)
+smol_taps0w_kernel (const Taps0wParams T)
 {
-    constexpr int PX = 2;
-    __shared__ uint32_t sm_inv[256];
-    __shared__ uint16_t sm_from[LINEAR ? 256 : 2];
-    __shared__ uint8_t sm_to_srgb[LINEAR ? 2048 : 4];
+    constexpr int PX = BO == 3 ? 4 : 2;
+    constexpr bool NEED_INV8 = MODE == BM_P8L_P && BI == 4;
+    constexpr bool NEED_FROM = MODE != BM_P16_U;
+    __shared__ uint32_t sm_inv8[NEED_INV8 ? 256 : 1];
+    __shared__ uint32_t sm_invp[256];       /* the repack's inverse-division table */
+    __shared__ uint16_t sm_from[NEED_FROM ? 256 : 2];
+    __shared__ __align__ (4) uint8_t sm_to_srgb[NEED_FROM ? 2048 : 4];
     const TapsParams &P = T.t;
+    const SmolJobDesc &d = T.d;
 
     pdl_launch_dependents ();
     {
-        /* library-owned constant data: readable before the dependency wait.  P.inv_div_p8 carries
-         * the table this mode needs (inv_div_p16 or inv_div_p16l). */
+        /* library-owned constant data: readable before the dependency wait */
         const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
         for (uint32_t i = t; i < 256; i += nt)
         {
-            sm_inv[i] = __ldg (&P.inv_div_p8[i]);
-            if constexpr (LINEAR)
-                sm_from[i] = __ldg (&T.from_srgb[i]);
+            sm_invp[i] = MODE == BM_P16_U ? T.luts->inv_div_p16[i] : MODE == BM_P16L_U ? T.luts->inv_div_p16l[i] : T.luts->inv_div_p8l[i];
+            if constexpr (NEED_FROM)
+            {
+                const uint32_t lin = T.luts->from_srgb[i];
+                sm_from[i] = (uint16_t) (MODE == BM_P16L_U ? lin : BI == 3 ? ((lin + 1) * 2041u - 1) >> 11 : lin + 1);
+            }
+            if constexpr (NEED_INV8)
+                sm_inv8[i] = T.luts->inv_div_p8[i] << 3;
         }
-        if constexpr (LINEAR)
+        if constexpr (NEED_FROM)
             for (uint32_t i = t; i < 512; i += nt)
-                reinterpret_cast<uint32_t *> (sm_to_srgb)[i] = __ldg (reinterpret_cast<const uint32_t *> (T.to_srgb) + i);
+                reinterpret_cast<uint32_t *> (sm_to_srgb)[i] = reinterpret_cast<const uint32_t *> (T.luts->to_srgb)[i];
         __syncthreads ();
     }
 
@@ -3513,6 +3628,9 @@ smol_taps0w_kernel (const Taps0Params T)
         return;
     const uint32_t yl1 = min (yl0 + P.rows_per_thread, P.n_rows);
     const uint32_t n_px = min ((uint32_t) PX, P.w_out - x);
+    const unsigned live_mask = __activemask ();         /* see smol_taps0_kernel */
+    const bool has_next = (threadIdx.x & 31) != 31 && x + PX < P.w_out;
+    (void) live_mask; (void) has_next;
 
     uint32_t op[PX], oq[PX], Fx[PX];
 #pragma unroll
@@ -3525,13 +3643,14 @@ smol_taps0w_kernel (const Taps0Params T)
     }
 
     const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
-    uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl0 * P.dst_pitch + (size_t) x * 4;
-    const bool store8 = n_px == PX && (reinterpret_cast<uintptr_t> (dst) & 7) == 0 && (P.dst_pitch & 7) == 0;
+    uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl0 * P.dst_pitch + (size_t) x * BO;
+    /* full-width store of a 32bpp thread's two pixels: 8 bytes */
+    const bool fast_store = BO == 4 && n_px == PX && (reinterpret_cast<uintptr_t> (dst) & 7) == 0 && (P.dst_pitch & 7) == 0;
 
     if (in_first_wave (T.prefetch))
     {
         const uint32_t r = SMOL_TAB_OFS (__ldg (&P.tab_y[P.first_row + yl0]));
-        const uint8_t *p = src + (size_t) r * P.src_pitch + (size_t) op[0] * 4;
+        const uint8_t *p = src + (size_t) r * P.src_pitch + (size_t) op[0] * BI;
         prefetch_l2 (p);
         prefetch_l2 (p + (size_t) (r + 1 < P.h_in ? P.src_pitch : 0));
     }
@@ -3541,12 +3660,12 @@ smol_taps0w_kernel (const Taps0Params T)
     {
         const uint8_t *row = src + (size_t) min (r, P.h_in - 1) * P.src_pitch;
         if (T.row_ahead && r + T.row_ahead < P.h_in)
-            prefetch_l1 (row + (size_t) T.row_ahead * P.src_pitch + (size_t) op[0] * 4);
+            prefetch_l1 (row + (size_t) T.row_ahead * P.src_pitch + (size_t) op[0] * BI);
 #pragma unroll
         for (int o = 0; o < PX; o++)
         {
-            const PxW p = taps0w_fetch<LINEAR, AF> (row, op[o], sm_from);
-            const PxW q = taps0w_fetch<LINEAR, AF> (row, oq[o], sm_from);
+            const PxW p = taps0w_fetch<MODE, BI, AF> (row, op[o], sm_inv8, sm_from);
+            const PxW q = taps0w_fetch<MODE, BI, AF> (row, oq[o], sm_inv8, sm_from);
             const uint32_t F = Fx[o], G = 256u - F;
 #pragma unroll
             for (int i = 0; i < 4; i++)
@@ -3557,7 +3676,7 @@ smol_taps0w_kernel (const Taps0Params T)
     auto emit = [&] (const PxW *top, const PxW *bot, uint32_t F)
     {
         const uint32_t G = 256u - F;
-        uint32_t out[PX];
+        uint32_t out[4] = { 0, 0, 0, 0 };
 #pragma unroll
         for (int o = 0; o < PX; o++)
         {
@@ -3565,31 +3684,21 @@ smol_taps0w_kernel (const Taps0Params T)
 #pragma unroll
             for (int i = 0; i < 4; i++)
                 fin[i] = (top[o].v[i] * F + bot[o].v[i] * G) >> 8;
-            /* repack (generic:1136-1164 via :290-318): every kept field lies in the low 32 bits of the products */
-            const uint32_t a = (fin[0] >> 8) & 0xffu;
-            const uint32_t inv = sm_inv[a];
-            uint32_t c[3];
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-            {
-                if constexpr (LINEAR)
-                    c[i] = sm_to_srgb[((fin[i + 1] * inv) >> 19) & 0x7ffu];
-                else
-                    c[i] = __byte_perm (fin[i + 1] * inv, 0, 0x4442);
-            }
-            /* the pixel in source byte order, then the job's byte permutation */
-            const uint32_t cc = c[0] | (c[1] << 8) | (c[2] << 16);
-            const uint32_t v = AF ? (cc << 8) | a : cc | (a << 24);
-            out[o] = __byte_perm (v, 0, P.prmt_sel);
+            out[o] = pack128_fast<MODE> (fin, d, T.luts, sm_to_srgb, sm_invp);
         }
-        if (store8)
-            *reinterpret_cast<uint2 *> (dst) = make_uint2 (out[0], out[1]);
-        else
+        if constexpr (BO == 4)
         {
-            reinterpret_cast<uint32_t *> (dst)[0] = out[0];
-            if (n_px > 1)
-                reinterpret_cast<uint32_t *> (dst)[1] = out[1];
+            if (fast_store)
+                *reinterpret_cast<uint2 *> (dst) = make_uint2 (out[0], out[1]);
+            else
+            {
+                reinterpret_cast<uint32_t *> (dst)[0] = out[0];
+                if (n_px > 1)
+                    reinterpret_cast<uint32_t *> (dst)[1] = out[1];
+            }
         }
+        else
+            store_px4_rgb_anywhere (dst, out, n_px, live_mask, has_next);
         dst += P.dst_pitch;
     };
 
@@ -4390,8 +4499,9 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
             T.row_ahead = (uint32_t) tune_ahead;
         }
         const bool af = d.in_alpha_idx == 0;
-        const bool fastio = T.src_u32_ok && (reinterpret_cast<uintptr_t> (L.dst) & 3) == 0
-                            && (L.dst_pitch & 3) == 0 && (L.dst_image_stride & 3) == 0;
+        /* (24bpp destinations are stored cooperatively at any alignment: store_px4_rgb_anywhere) */
+        const bool fastio = T.src_u32_ok && (d.bpp_out == 3 || ((reinterpret_cast<uintptr_t> (L.dst) & 3) == 0
+                                                                && (L.dst_pitch & 3) == 0 && (L.dst_image_stride & 3) == 0));
         /* one pixel per thread (fully coalesced source reads) when the destination is 32bpp and
          * rows are aligned; otherwise four (vector / 24bpp stores) */
         static int tune_px = -1;
@@ -5052,7 +5162,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
 
 static void taps_params_init (TapsParams &P, const SmolLaunch &L);
 
-/* unassociated -> unassociated without halvings, 32bpp both sides, word-aligned rows: smol_taps0w_kernel */
+/* bilinear / copy / one without halvings on a 128bpp intermediate, word-aligned 32bpp rows: smol_taps0w_kernel */
 static bool
 taps0w_eligible (const SmolLaunch &L)
 {
@@ -5063,27 +5173,29 @@ taps0w_eligible (const SmolLaunch &L)
         const char *e = getenv ("SMOL_TAPS0W");
         on = e ? atoi (e) : 1;
     }
-    return on && d.h_kind == SMOL_AXIS_TAPS && d.v_kind == SMOL_AXIS_TAPS && d.storage128
-           && (d.mid == SMOL_MID_P16 || d.mid == SMOL_MID_P16L) && d.h_halvings == 0 && d.v_halvings == 0
-           && d.bpp_in == 4 && d.bpp_out == 4
-           && aligned4 (L.src) && aligned4 (L.dst) && (L.src_pitch & 3) == 0 && (L.dst_pitch & 3) == 0
-           && (L.src_image_stride & 3) == 0 && (L.dst_image_stride & 3) == 0;
+    if (!on || d.h_kind != SMOL_AXIS_TAPS || d.v_kind != SMOL_AXIS_TAPS || !d.storage128 || d.mid == SMOL_MID_P8
+        || d.h_halvings != 0 || d.v_halvings != 0)
+        return false;
+    if (d.bpp_in == 4 && !(aligned4 (L.src) && (L.src_pitch & 3) == 0 && (L.src_image_stride & 3) == 0))
+        return false;
+    if (d.bpp_out == 4 && !(aligned4 (L.dst) && (L.dst_pitch & 3) == 0 && (L.dst_image_stride & 3) == 0))
+        return false;
+    return true;
 }
 
 static cudaError_t
 launch_taps0w (const SmolLaunch &L, cudaStream_t stream)
 {
     const SmolJobDesc &d = L.d;
-    Taps0Params T;
+    Taps0wParams T;
 
     memset (&T, 0, sizeof (T));
     taps_params_init (T.t, L);
-    const bool linear = d.mid == SMOL_MID_P16L;
-    T.t.inv_div_p8 = linear ? L.luts->inv_div_p16l : L.luts->inv_div_p16;      /* the repack table of this mode */
-    T.from_srgb = L.luts->from_srgb;
-    T.to_srgb = L.luts->to_srgb;
+    T.d = d;
+    T.luts = L.luts;
 
-    const uint64_t x_threads = (d.w_out + 1) / 2;
+    const uint32_t px = d.bpp_out == 3 ? 4 : 2;
+    const uint64_t x_threads = (d.w_out + px - 1) / px;
     const uint64_t want_threads = (uint64_t) num_sms () * 1536;
     uint32_t rpt = 16;
     while (rpt > 1 && x_threads * ((L.n_rows + rpt - 1) / rpt) * L.n_images < want_threads)
@@ -5114,11 +5226,20 @@ launch_taps0w (const SmolLaunch &L, cudaStream_t stream)
         T.prefetch = 0xffffffffu;       /* tables are staged first: see launch_half */
     T.row_ahead = 2;
     const bool af = d.in_alpha_idx == 0;
-    if (linear)
-        return af ? launch_pdl (smol_taps0w_kernel<true, true>, T, grid, block, 0, stream)
-                  : launch_pdl (smol_taps0w_kernel<true, false>, T, grid, block, 0, stream);
-    return af ? launch_pdl (smol_taps0w_kernel<false, true>, T, grid, block, 0, stream)
-              : launch_pdl (smol_taps0w_kernel<false, false>, T, grid, block, 0, stream);
+
+#define TAPS0W(M, BI, BO, AF) launch_pdl (smol_taps0w_kernel<M, BI, BO, AF>, T, grid, block, 0, stream)
+#define TAPS0W_AF(M, BO) (af ? TAPS0W (M, 4, BO, true) : TAPS0W (M, 4, BO, false))
+    if (d.mid == SMOL_MID_P16)
+        return TAPS0W_AF (BM_P16_U, 4);
+    if (d.mid == SMOL_MID_P16L)
+        return TAPS0W_AF (BM_P16L_U, 4);
+    if (d.bpp_in == 3)
+        return d.bpp_out == 3 ? TAPS0W (BM_P8L_P, 3, 3, false) : TAPS0W (BM_P8L_P, 3, 4, false);
+    if (d.in_unassoc)
+        return d.bpp_out == 3 ? TAPS0W_AF (BM_P8L_U, 3) : TAPS0W_AF (BM_P8L_U, 4);
+    return d.bpp_out == 3 ? TAPS0W_AF (BM_P8L_P, 3) : TAPS0W_AF (BM_P8L_P, 4);
+#undef TAPS0W_AF
+#undef TAPS0W
 }
 
 static void box_params_init (BoxParams &P, const SmolLaunch &L);

@@ -503,3 +503,31 @@ def test_box_opaque_rows(sb, restatement):
             want = restatement.scale_simple(src, ti, wi, hi, wi * b, to, wo, ho, None, 1)
             got = cuda_scale(sb, src, ti, wi, hi, wi * b, to, wo, ho, None, 1)
             assert np.array_equal(got, want), (gi, variant, to, describe(got, want))
+
+
+def test_rgb_destination_at_any_alignment(sb, restatement):
+    """24bpp destinations at every byte alignment of base and pitch (tightly packed RGB rows of odd width):
+    the taps kernels store a warp's row segment as aligned words shared between neighbouring threads
+    (store_px4_rgb_anywhere).  Widths sit around the 4-pixel-per-thread and 32-lane boundaries; pitch
+    padding and the bytes either side of the image must stay untouched."""
+    import torch
+    rng = np.random.default_rng(5)
+    widths = [1, 2, 3, 4, 5, 7, 8, 9, 123, 124, 125, 127, 128, 129, 131, 132, 133, 255, 257, 515]
+    for ti, srgb in [(cases.RGBA8_P, 0), (cases.RGB8, 0), (cases.BGRA8_U, 0), (cases.RGBA8_P, 1), (cases.RGB8, 1), (cases.ARGB8_U, 1)]:
+        for wo in widths:
+            wi = int(max(1, round(wo * rng.choice([1.0, 0.77, 1.6, 2.0]))))
+            hi, ho = 23, int(rng.integers(9, 40))
+            to = int(rng.choice([cases.RGB8, cases.BGR8]))
+            si = wi * cases.bpp(ti) + int(rng.integers(0, 4)) * (cases.bpp(ti) == 3)
+            so = wo * 3 + int(rng.integers(0, 9))
+            off = int(rng.integers(0, 4))
+            src = cases.make_image(ti, wi, hi, si, "random", seed=wo)
+            want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
+            d_in = torch.from_numpy(src).cuda()
+            d_out = torch.full((want.size + 16,), 0xCD, dtype=torch.uint8, device="cuda")
+            sb.scale_simple(d_in, ti, wi, hi, si, d_out.data_ptr() + off, to, wo, ho, so, srgb)
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy()
+            body = got[off:off + want.size]
+            assert np.array_equal(body, want), ((ti, wi, hi, si, to, wo, ho, so, srgb, off), describe(body, want))
+            assert (got[:off] == 0xCD).all() and (got[off + want.size:] == 0xCD).all(), (ti, wo, so, off)
