@@ -1,5 +1,5 @@
 /* TEST INFRASTRUCTURE ONLY -- see smol_oracle.h.  Parity status: PINNED against the compiled
- * reference (tests/test_oracle_vs_ref.py) and the golden digests in tests/golden/.
+ * reference (tests/test_oracle.py) and the golden digests in tests/golden/.
  *
  * A plain scalar restatement of the smolscale pipeline.  Where the reference packs four 16-bit
  * or two 32-bit channel lanes into uint64_t words and filters whole words at a time

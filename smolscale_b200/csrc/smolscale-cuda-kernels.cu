@@ -1033,8 +1033,8 @@ smol_half2v_kernel (const HalfParams P)
     if constexpr (PACK != 0)
     {
         /* library-owned constant data: safe to read before the dependency wait */
-        const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
-        if (t < 64)
+        /* (a block can be as small as one warp: a one-row job) */
+        for (uint32_t t = threadIdx.y * blockDim.x + threadIdx.x; t < 64; t += blockDim.x * blockDim.y)
         {
             uint4 v = __ldg (reinterpret_cast<const uint4 *> (P.inv_div_p8) + t);
             v.x <<= 3; v.y <<= 3; v.z <<= 3; v.w <<= 3;
@@ -3910,12 +3910,285 @@ smol_tile128_kernel (const Tile128Params M)
 }
 
 /* ------------------------------------------------------------------------------------------ *
+ * "rows" kernel: ANY filter pair, any format, any alignment -- the fast backstop.  It takes what  *
+ * the specialised kernels leave: box on one axis and bilinear on the other (8000 x 1000 -> 800 x   *
+ * 500), ratios beyond 255:1 without linear light, box jobs on byte-misaligned 32bpp rows.          *
+ *                                                                                              *
+ * The frame is the box kernel's: the unit of work is one WARP producing 32 / G adjacent output     *
+ * columns of a strip of consecutive output rows (no block barriers, load balance at warp           *
+ * granularity); the strip's source rows are walked ONCE, in order, each staged into the warp's     *
+ * own double-buffered shared-memory window with 16-byte cp.async on chunks aligned in global       *
+ * memory (straddling chunks byte-exactly), so the copy of row r + 1 overlaps the arithmetic on     *
+ * row r.  Per row a lane computes its column's horizontally filtered pixel -- a box span walk or   *
+ * 2^h bilinear taps -- and feeds it to the vertical stage: box accumulation with the boundary      *
+ * rows shared between neighbouring output rows, or a two-row cache from which every vertical       *
+ * sample whose lower row has just arrived is taken.  The arithmetic is the general kernel's        *
+ * (64-bit words of four 16-bit or two 32-bit lanes, runtime formats through unpack_px / pack_px),  *
+ * with the six data tables copied to shared memory once per CTA.                                   *
+ * ------------------------------------------------------------------------------------------ */
+
+struct RowsParams
+{
+    SmolLaunch L;
+    uint32_t lanes_per_col_log2;    /* box spans: lanes sharing a column */
+    uint32_t x_tiles;               /* items per strip of rows */
+    uint32_t rows_per_item, n_strips;
+    uint32_t seg_bytes;             /* bytes per staging buffer (multiple of 16) */
+};
+
+template <bool S128, bool HBOX, bool VBOX>
+__global__ void __launch_bounds__ (256)
+smol_rows_kernel (const RowsParams P)
+{
+    extern __shared__ __align__ (16) uint8_t sm_dyn[];
+    __shared__ SmolDeviceLuts sm_luts;
+    const SmolLaunch &L = P.L;
+    const SmolJobDesc &d = L.d;
+    const uint32_t bpp = d.bpp_in;
+
+    pdl_launch_dependents ();
+    {
+        /* library-owned constant data: readable before the dependency wait */
+        const uint32_t *g = reinterpret_cast<const uint32_t *> (L.luts);
+        uint32_t *s = reinterpret_cast<uint32_t *> (&sm_luts);
+        for (uint32_t i = threadIdx.x; i < sizeof (SmolDeviceLuts) / 4; i += blockDim.x)
+            s[i] = __ldg (g + i);
+    }
+    __syncthreads ();
+    pdl_wait ();
+    const SmolDeviceLuts *luts = &sm_luts;
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t G = 1u << P.lanes_per_col_log2, g = lane & (G - 1);
+    const uint32_t cols_per_item = 32u >> P.lanes_per_col_log2;
+    uint8_t *bufs = sm_dyn + (size_t) warp * 2 * P.seg_bytes;
+    const uint32_t bufs_addr = (uint32_t) __cvta_generic_to_shared (bufs);
+    const uint32_t row_bytes = d.w_in * bpp;
+    const uint32_t hh = d.h_halvings, vh = d.v_halvings;
+
+    const uint32_t items_per_image = P.x_tiles * P.n_strips;
+    const uint32_t n_items = items_per_image * L.n_images;
+    const uint32_t warp_stride = gridDim.x * (blockDim.x >> 5);
+
+    for (uint32_t item = blockIdx.x * (blockDim.x >> 5) + warp; item < n_items; item += warp_stride)
+    {
+        const uint32_t img = item / items_per_image;
+        const uint32_t rem = item - img * items_per_image;
+        const uint32_t strip = rem / P.x_tiles, xt = rem - strip * P.x_tiles;
+        const uint32_t yl0 = strip * P.rows_per_item, yl1 = min (yl0 + P.rows_per_item, L.n_rows);
+        const uint32_t x_first = xt * cols_per_item;
+        const uint32_t x_last = min (x_first + cols_per_item, d.w_out) - 1;
+        uint32_t x = x_first + (lane >> P.lanes_per_col_log2);
+        const bool store = x <= x_last && g == 0;
+        x = min (x, x_last);
+
+        /* horizontal plan of this lane's column, and the window of source pixels the item reads */
+        uint32_t hL = 0, hR = 0, wl = 0, wr = 0, sx0, sx1;
+        if constexpr (HBOX)
+        {
+            const uint32_t e0 = __ldg (&L.tab_x[x]), e1 = __ldg (&L.tab_x[x + 1]);
+            hL = SMOL_TAB_OFS (e0); hR = SMOL_TAB_OFS (e1); wr = SMOL_TAB_F (e0);
+            wl = x == 0 ? 256u : 255u - SMOL_TAB_F (__ldg (&L.tab_x[x - 1]));
+            sx0 = SMOL_TAB_OFS (__ldg (&L.tab_x[x_first]));
+            sx1 = SMOL_TAB_OFS (__ldg (&L.tab_x[x_last + 1]));
+        }
+        else
+        {
+            sx0 = SMOL_TAB_OFS (__ldg (&L.tab_x[x_first << hh]));
+            sx1 = min (SMOL_TAB_OFS (__ldg (&L.tab_x[((x_last + 1) << hh) - 1])) + 1, d.w_in - 1);
+        }
+        const uint32_t sx_b = sx0 * bpp, end_b = (sx1 + 1) * bpp;
+
+        /* vertical plan: the strip's source rows r_first .. r_last are consecutive */
+        const uint32_t y0 = L.first_row + yl0;
+        uint32_t r_first, r_last;
+        uint32_t B_cur = 0, rend_cur = 0, w1_cur = 0, w2_cur = 0, Fy_cur = 0;     /* box */
+        uint32_t k_cur = 0, k_stop = 0;                                            /* taps: sample indices into tab_y */
+        if constexpr (VBOX)
+        {
+            const uint32_t e0 = __ldg (&L.tab_y[y0]), e1 = __ldg (&L.tab_y[y0 + 1]);
+            r_first = SMOL_TAB_OFS (e0);
+            B_cur = SMOL_TAB_OFS (e1);
+            Fy_cur = SMOL_TAB_F (e0);
+            w1_cur = y0 == 0 ? 256u : 255u - SMOL_TAB_F (__ldg (&L.tab_y[y0 - 1]));
+            w2_cur = S128 ? Fy_cur - 1 : Fy_cur;        /* 128bpp weighs the trailing row by F - 1 (generic:2247-2249) */
+            rend_cur = Fy_cur > 0 ? B_cur : B_cur - 1;
+            const uint32_t ya = L.first_row + yl1 - 1;
+            const uint32_t ea = __ldg (&L.tab_y[ya]), eb = __ldg (&L.tab_y[ya + 1]);
+            r_last = SMOL_TAB_F (ea) > 0 ? SMOL_TAB_OFS (eb) : SMOL_TAB_OFS (eb) - 1;
+        }
+        else
+        {
+            k_cur = y0 << vh;
+            k_stop = (L.first_row + yl1) << vh;
+            r_first = SMOL_TAB_OFS (__ldg (&L.tab_y[k_cur]));
+            r_last = min (SMOL_TAB_OFS (__ldg (&L.tab_y[k_stop - 1])) + 1, d.h_in - 1);
+        }
+
+        const uint8_t *img_base = L.src + (size_t) img * L.src_image_stride;
+        uint8_t *dst_img = L.dst + (size_t) img * L.dst_image_stride;
+
+        /* row-relative offset (may be negative) of the first staged byte of source row r */
+        auto staged_from = [&] (uint32_t r) -> int32_t
+        {
+            const uint32_t A = (uint32_t) reinterpret_cast<uintptr_t> (img_base + (size_t) r * L.src_pitch) & 15u;
+            return (int32_t) ((A + sx_b) & ~15u) - (int32_t) A;
+        };
+        auto stage = [&] (uint32_t slot_ofs, uint32_t r)
+        {
+            const uint8_t *rowp = img_base + (size_t) r * L.src_pitch;
+            const int32_t w0 = staged_from (r);
+            const uint32_t nch = ((uint32_t) ((int32_t) end_b - w0) + 15u) >> 4;
+            for (uint32_t k = lane; k < nch; k += 32)
+            {
+                const int32_t ofs = w0 + 16 * (int32_t) k;
+                const uint32_t sa = bufs_addr + slot_ofs + 16 * k;
+                if (ofs >= 0 && ofs + 16 <= (int32_t) row_bytes)
+                    cp_async_16_full (sa, rowp + ofs);
+                else
+                {
+                    const int32_t lo = ofs < 0 ? -ofs : 0, hi = min (16, (int32_t) row_bytes - ofs);
+                    for (int32_t b = lo; b < hi; b++)
+                    {
+                        const uint32_t v = __ldg (rowp + ofs + b);
+                        asm volatile ("st.shared.u8 [%0], %1;" :: "r"(sa + b), "r"(v) : "memory");
+                    }
+                }
+            }
+            cp_async_commit ();
+        };
+
+        Px<S128> vacc = px_zero<S128> ();       /* box: the output row's accumulator; taps: the sum of its samples */
+        Px<S128> h_prev = px_zero<S128> ();     /* taps: the row above */
+        bool top_pending = true;                /* box: the current output row's first source row is still to come */
+        uint32_t yl_cur = yl0;
+        uint32_t cur = 0;
+
+        auto emit_row = [&] (const Px<S128> &out)
+        {
+            if (store)
+            {
+                uint8_t *o = dst_img + (size_t) yl_cur * L.dst_pitch + (size_t) x * d.bpp_out;
+                store_raw_px (o, pack_px<S128> (out, d, luts), d.bpp_out);
+            }
+            yl_cur++;
+        };
+
+        stage (0, r_first);
+        for (uint32_t r = r_first; r <= r_last; r++)
+        {
+            if (r < r_last)
+            {
+                stage (P.seg_bytes - cur, r + 1);
+                cp_async_wait<1> ();
+            }
+            else
+                cp_async_wait<0> ();
+            __syncwarp ();
+
+            /* pixel j of the row starts at sm[j * bpp - w0] */
+            const uint8_t *sm = bufs + cur - staged_from (r);
+            auto px_at = [&] (uint32_t j) -> Px<S128>
+            {
+                return unpack_px<S128> (load_raw_px (sm + (size_t) j * bpp, bpp), d, luts);
+            };
+
+            Px<S128> h;
+            if constexpr (HBOX)
+            {
+                /* generic:1427-1556 in absolute offsets */
+                Px<S128> acc = px_zero<S128> ();
+                for (uint32_t j = hL + 1 + g; j < hR; j += G)
+                    px_add<S128> (acc, px_at (j));
+                if (g == 0)
+                    px_add<S128> (acc, px_weight<S128> (px_at (hL), wl));
+                if (g == G - 1 && wr > 0)
+                    px_add<S128> (acc, px_weight<S128> (px_at (hR), wr));
+                for (uint32_t m = G >> 1; m; m >>= 1)
+                    acc = px_shfl_xor_add<S128> (acc, m);
+                h = px_box_scale<S128> (acc, d.span_mul_x);
+            }
+            else
+            {
+                /* generic:1290-1425 */
+                Px<S128> acc = px_zero<S128> ();
+                const uint32_t *tx = L.tab_x + (x << hh);
+                for (uint32_t k = 0; k < (1u << hh); k++)
+                {
+                    const uint32_t e = __ldg (&tx[k]);
+                    const uint32_t ofs = SMOL_TAB_OFS (e);
+                    px_add<S128> (acc, px_lerp<S128> (px_at (ofs), px_at (min (ofs + 1, d.w_in - 1)), SMOL_TAB_F (e)));
+                }
+                h = px_halve<S128> (acc, hh);
+            }
+
+            if constexpr (VBOX)
+            {
+                /* generic:2112-2161 (64bpp) / :2198-2260 (128bpp); boundary rows are filtered once and
+                 * handed on to the next output row (see the box kernel) */
+                if (top_pending)
+                {
+                    px_add<S128> (vacc, px_weight<S128> (h, w1_cur));
+                    top_pending = false;
+                }
+                else if (r == B_cur)
+                    px_add<S128> (vacc, px_weight<S128> (h, w2_cur));
+                else
+                    px_add<S128> (vacc, h);
+                if (r == rend_cur)
+                {
+                    emit_row (px_box_scale<S128> (vacc, d.span_mul_y));
+                    if (yl_cur < yl1)
+                    {
+                        const uint32_t yn = L.first_row + yl_cur;
+                        const uint32_t e0 = __ldg (&L.tab_y[yn]), e1 = __ldg (&L.tab_y[yn + 1]);
+                        const uint32_t F_new = SMOL_TAB_F (e0);
+                        const bool shared = r == B_cur;
+                        w1_cur = 255u - Fy_cur;
+                        Fy_cur = F_new;
+                        B_cur = SMOL_TAB_OFS (e1);
+                        w2_cur = S128 ? F_new - 1 : F_new;
+                        rend_cur = F_new > 0 ? B_cur : B_cur - 1;
+                        vacc = px_zero<S128> ();
+                        if (shared)
+                            px_add<S128> (vacc, px_weight<S128> (h, w1_cur));
+                        top_pending = !shared;
+                    }
+                }
+            }
+            else
+            {
+                /* generic:1684-2007: every sample whose lower row is this one (its upper row is the
+                 * one before, or this one again where the table clamps at the image's last row) */
+                while (k_cur < k_stop)
+                {
+                    const uint32_t e = __ldg (&L.tab_y[k_cur]);
+                    const uint32_t r0 = SMOL_TAB_OFS (e), r1 = min (r0 + 1, d.h_in - 1);
+                    if (r1 > r)
+                        break;
+                    px_add<S128> (vacc, px_lerp<S128> (r0 == r ? h : h_prev, h, SMOL_TAB_F (e)));
+                    k_cur++;
+                    if ((k_cur & ((1u << vh) - 1)) == 0)
+                    {
+                        emit_row (px_halve<S128> (vacc, vh));
+                        vacc = px_zero<S128> ();
+                    }
+                }
+                h_prev = h;
+            }
+            cur = P.seg_bytes - cur;
+            __syncwarp ();      /* everyone is done with this slot before it is refilled */
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ *
  * Host-side dispatch                                                                         *
  * ------------------------------------------------------------------------------------------ */
 
 static const char *const kernel_names[SMOL_KERNEL_MAX] =
 {
-    "auto", "general", "taps_direct", "half2x", "box", "mag", "taps128", "tile128", "magb"
+    "auto", "general", "taps_direct", "half2x", "box", "mag", "taps128", "tile128", "magb", "rows"
 };
 
 extern "C" const char *
@@ -4036,6 +4309,41 @@ box_eligible (const SmolLaunch &L)
     return d.bpp_in == 3 || (aligned4 (L.src) && (L.src_pitch & 3) == 0 && (L.src_image_stride & 3) == 0);
 }
 
+/* The warp-per-tile backstop: anything whose per-warp source window fits its staging buffers. */
+static uint32_t
+rows_seg_bytes (const SmolLaunch &L, uint32_t *glog_out)
+{
+    const SmolJobDesc &d = L.d;
+    uint32_t glog = 0;
+    if (d.h_kind == SMOL_AXIS_BOX)
+    {
+        const uint32_t ratio = d.w_in / d.w_out;
+        while (glog < 5 && ratio >= (16u << glog))
+            glog++;
+    }
+    const uint32_t cols = 32u >> glog;
+    /* widest window an item can need: its columns' share of the row, the taps' extra pixel, rounding slack */
+    const uint64_t seg_px = ((uint64_t) cols * d.w_in + d.w_out - 1) / d.w_out + 4;
+    if (glog_out)
+        *glog_out = glog;
+    const uint64_t bytes = (seg_px * d.bpp_in + 32 + 15) & ~(uint64_t) 15;
+    return bytes > 0x7fffffffu ? 0x7fffffffu : (uint32_t) bytes;
+}
+
+static bool
+rows_eligible (const SmolLaunch &L)
+{
+    static int on = -1;
+    if (on < 0)
+    {
+        const char *e = getenv ("SMOL_ROWS_KERNEL");
+        on = e ? atoi (e) : 1;
+    }
+    if (!on || rows_seg_bytes (L, nullptr) > 12 * 1024)
+        return false;
+    return (uint64_t) L.d.w_out * L.n_rows * L.n_images < 0x7fffffffull;
+}
+
 extern "C" int
 smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
 {
@@ -4058,6 +4366,8 @@ smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
 
     if (forced == SMOL_KERNEL_GENERAL)
         return SMOL_KERNEL_GENERAL;
+    if (forced == SMOL_KERNEL_ROWS)
+        return rows_eligible (*launch) ? SMOL_KERNEL_ROWS : SMOL_KERNEL_GENERAL;
     if (forced == SMOL_KERNEL_HALF2X)
         return half_ok ? SMOL_KERNEL_HALF2X : SMOL_KERNEL_GENERAL;
     if (forced == SMOL_KERNEL_TAPS_DIRECT)
@@ -4082,6 +4392,9 @@ smol_cuda_pick_kernel (const SmolLaunch *launch, int forced)
         return SMOL_KERNEL_MAGB;
     if (taps_ok)
         return SMOL_KERNEL_TAPS_DIRECT;
+    /* box on one axis only, > 255:1 without linear light, byte-misaligned 32bpp box rows */
+    if (rows_eligible (*launch))
+        return SMOL_KERNEL_ROWS;
     return SMOL_KERNEL_GENERAL;
 }
 
@@ -4147,6 +4460,28 @@ smem_optin (const void *fn, int bytes)
         return err;
     }
     return cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+/* cudaOccupancyMaxActiveBlocksPerMultiprocessor costs ~20 us of host time: a C caller looping over
+ * small box jobs would be bound by it.  Answers are remembered per (device, kernel, block size, shared
+ * memory) in a small direct-mapped table (racing writers store the same value). */
+static int
+cached_occupancy (const void *fn, int threads, size_t smem)
+{
+    struct Entry { const void *fn; int threads, dev, occ; size_t smem; };
+    static Entry table[256];
+    const int dev = current_device ();
+    const uint32_t h = (uint32_t) ((reinterpret_cast<uintptr_t> (fn) >> 4) * 2654435761u + (uint32_t) threads * 40503u
+                                   + (uint32_t) smem * 2246822519u + (uint32_t) dev) & 255u;
+    Entry e = table[h];
+    if (e.fn == fn && e.threads == threads && e.smem == smem && e.dev == dev && e.occ > 0)
+        return e.occ;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, threads, smem) != cudaSuccess || occ < 1)
+        occ = 1;
+    e.fn = fn; e.threads = threads; e.smem = smem; e.dev = dev; e.occ = occ;
+    table[h] = e;
+    return occ;
 }
 
 /* See prefetch_l2 / in_first_wave: the number of CTAs of a launch that can be resident at once
@@ -5141,10 +5476,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         }
         if (smem > 32 * 1024)        /* static shared memory counts against the 48 KB default too */
             smem_optin (fn, 225 * 1024);
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, (int) warps_per_cta * 32, smem) != cudaSuccess || occ < 1)
-            occ = 1;
-        per_sm = (uint32_t) occ;
+        per_sm = (uint32_t) cached_occupancy (fn, (int) warps_per_cta * 32, smem);
         /* (column tiles x output rows: strips are chosen after G, they must not make it grow) */
         const double rounds = (double) P.x_tiles * L.n_rows * L.n_images / ((double) num_sms () * per_sm * warps_per_cta);
         if (tune_g != 99 || glog >= 5 || rounds >= 1.0)
@@ -5387,6 +5719,81 @@ launch_tile128 (const SmolLaunch &L, cudaStream_t stream)
 
 template <bool S128, bool HBOX, bool VBOX>
 static cudaError_t
+launch_rows_k (const RowsParams &P, dim3 grid, size_t smem, cudaStream_t stream)
+{
+    if (smem > 40 * 1024)
+        smem_optin ((const void *) smol_rows_kernel<S128, HBOX, VBOX>, 200 * 1024);
+    return launch_pdl (smol_rows_kernel<S128, HBOX, VBOX>, P, grid, dim3 (256), smem, stream);
+}
+
+static cudaError_t
+launch_rows (const SmolLaunch &L, cudaStream_t stream)
+{
+    const SmolJobDesc &d = L.d;
+    RowsParams P;
+    uint32_t glog = 0;
+
+    P.L = L;
+    P.seg_bytes = rows_seg_bytes (L, &glog);
+    /* few work items (small outputs): more lanes per box column make more of them */
+    const uint32_t warps_resident = (uint32_t) num_sms () * 8 * 4;
+    while (d.h_kind == SMOL_AXIS_BOX && glog < 5
+           && (uint64_t) ((d.w_out + (32u >> glog) - 1) / (32u >> glog)) * L.n_rows * L.n_images < warps_resident
+           && d.w_in / d.w_out >= (4u << glog))
+        glog++;
+    P.lanes_per_col_log2 = glog;
+    const uint32_t cols = 32u >> glog;
+    P.x_tiles = (d.w_out + cols - 1) / cols;
+    {
+        const uint64_t seg_px = ((uint64_t) cols * d.w_in + d.w_out - 1) / d.w_out + 4;
+        P.seg_bytes = (uint32_t) ((seg_px * d.bpp_in + 32 + 15) & ~(uint64_t) 15);
+    }
+    /* Strip length: long strips share boundary rows (box) and reuse row pairs (bilinear
+     * magnification), short ones make more items; aim at a few items per resident warp. */
+    uint64_t k = (uint64_t) P.x_tiles * L.n_rows * L.n_images / ((uint64_t) warps_resident * 2);
+    k = k < 1 ? 1 : k > 16 ? 16 : k;
+    if (d.v_kind == SMOL_AXIS_TAPS && d.h_out > d.h_in && k < 4)
+        k = 4;
+    {
+        static int tune_k = -1;
+        if (tune_k < 0)
+        {
+            const char *e = getenv ("SMOL_ROWS_PER_ITEM");
+            tune_k = e ? atoi (e) : 0;
+        }
+        if (tune_k > 0)
+            k = (uint64_t) tune_k;
+    }
+    if (k > L.n_rows)
+        k = L.n_rows;
+    P.rows_per_item = (uint32_t) k;
+    P.n_strips = (L.n_rows + P.rows_per_item - 1) / P.rows_per_item;
+
+    const size_t smem = (size_t) 8 * 2 * P.seg_bytes;
+    const uint64_t n_items = (uint64_t) P.x_tiles * P.n_strips * L.n_images;
+    uint32_t per_sm = (uint32_t) ((200 * 1024) / (smem + sizeof (SmolDeviceLuts) + 1024));
+    per_sm = per_sm > 8 ? 8 : per_sm < 1 ? 1 : per_sm;
+    uint64_t blocks = (n_items + 7) / 8;
+    if (blocks > (uint64_t) num_sms () * per_sm)
+        blocks = (uint64_t) num_sms () * per_sm;
+    dim3 grid ((unsigned) blocks);
+    const bool hb = d.h_kind == SMOL_AXIS_BOX, vb = d.v_kind == SMOL_AXIS_BOX;
+
+    if (d.storage128)
+    {
+        if (hb && vb)   return launch_rows_k<true, true, true> (P, grid, smem, stream);
+        if (hb)         return launch_rows_k<true, true, false> (P, grid, smem, stream);
+        if (vb)         return launch_rows_k<true, false, true> (P, grid, smem, stream);
+        return launch_rows_k<true, false, false> (P, grid, smem, stream);
+    }
+    if (hb && vb)       return launch_rows_k<false, true, true> (P, grid, smem, stream);
+    if (hb)             return launch_rows_k<false, true, false> (P, grid, smem, stream);
+    if (vb)             return launch_rows_k<false, false, true> (P, grid, smem, stream);
+    return launch_rows_k<false, false, false> (P, grid, smem, stream);
+}
+
+template <bool S128, bool HBOX, bool VBOX>
+static cudaError_t
 launch_general (const SmolLaunch &L, cudaStream_t stream)
 {
     const uint32_t TW = SMOL_BLOCK / L.lanes_per_col;
@@ -5465,6 +5872,13 @@ smol_cuda_launch (const SmolLaunch *launch, int kernel_id, void *stream_p, const
         return (int) launch_mag (L, stream);
     if (kernel_id == SMOL_KERNEL_TAPS_DIRECT && taps_eligible (L))
         return (int) launch_taps (L, stream);
+    /* the box kernel's own fallback (rows off 16-byte boundaries with an older table placement) lands here too */
+    if ((kernel_id == SMOL_KERNEL_ROWS || kernel_id == SMOL_KERNEL_BOX) && rows_eligible (L))
+    {
+        if (name_out)
+            *name_out = kernel_names[SMOL_KERNEL_ROWS];
+        return (int) launch_rows (L, stream);
+    }
     if (name_out)
         *name_out = kernel_names[SMOL_KERNEL_GENERAL];
 

@@ -32,6 +32,7 @@ enum
     SMOL_KERNEL_TAPS128 = 6,     /* bilinear with halvings, 128bpp intermediate (linear light, P16) */
     SMOL_KERNEL_TILE128 = 7,     /* bilinear without halvings / copy / one, 128bpp intermediate */
     SMOL_KERNEL_MAGB = 8,        /* vertical magnification, byte-granular vertical stage (no alpha work on output) */
+    SMOL_KERNEL_ROWS = 9,        /* any filter pair, any format: one warp per tile of columns, source rows streamed through shared memory */
     SMOL_KERNEL_MAX
 };
 

@@ -43,10 +43,11 @@ def test_golden_digests(sb):
     assert not bad, "CUDA output differs from the reference digests: %s" % bad[:10]
 
 
-@pytest.mark.parametrize("forced", [0, 1, 2, 4, 5, 6, 7, 8],
-                         ids=["auto", "general", "taps", "box", "mag", "taps128", "tile128", "magb"])
+@pytest.mark.parametrize("forced", [0, 1, 2, 4, 5, 6, 7, 8, 9],
+                         ids=["auto", "general", "taps", "box", "mag", "taps128", "tile128", "magb", "rows"])
 def test_random_matrix_vs_oracle(sb, restatement, forced):
-    """forced = 0: the dispatcher's choice; 1: everything through the general kernel;
+    """forced = 0: the dispatcher's choice; 1: everything through the general kernel; 9: everything
+    through the warp-per-tile "rows" kernel (any filter pair, any format);
     2 / 5 / 8: the direct taps / magnification kernels wherever eligible (general elsewhere)."""
     sb.force_kernel(forced)
     try:
@@ -63,6 +64,10 @@ def test_random_matrix_vs_oracle(sb, restatement, forced):
 REGRESSION_JOBS = [
     # found by tools/soak.py: dynamic + static shared memory just above the 48 KB default limit
     (cases.BGR8, 77, 37, 240, cases.RGBA8_U, 154, 41, 624, 0, "saturated"),
+    # found by tools/soak.py (round 2): a one-row 2:1 job runs the 256-bit kernel with a single warp per block,
+    # which staged only half of the inverse-division table
+    (cases.ABGR8_P, 62, 2, 256, cases.ARGB8_U, 31, 1, 128, 0, "saturated"),
+    (cases.RGBA8_P, 16, 2, 64, cases.BGRA8_U, 8, 1, 32, 0, "alpha_edges"),
 ]
 
 

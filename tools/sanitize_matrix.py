@@ -17,6 +17,18 @@ for (wi, hi, wo, ho) in [(64, 48, 256, 192), (100, 7, 349, 65), (33, 30, 130, 61
 for (wi, hi, wo, ho) in [(200, 90, 15, 9), (255, 100, 16, 7), (1500, 120, 100, 11), (1021, 50, 64, 5), (4000, 40, 15, 3)]:
     for ti, srgb in [(cases.RGBA8_P, 1), (cases.ARGB8_U, 1), (cases.RGB8, 0), (cases.BGRA8_U, 0), (cases.RGB8, 1)]:
         jobs.append((ti, wi, hi, (wi * cases.bpp(ti) + 15) // 16 * 16, cases.RGBA8_P, wo, ho, wo * 4, srgb, "random"))
+# round 2 kernels: 2:1 on 32- / 16- / 8- / 4-byte-aligned rows (256-bit loads and the narrow variants), box rows off
+# 16-byte boundaries (row-shifted staging, 24bpp tight pitches), the 128bpp strip kernel, 24bpp stores at any alignment
+for (wi, hi, wo, ho) in [(256, 64, 128, 32), (250, 62, 125, 31), (64, 64, 8, 8), (72, 40, 18, 10)]:
+    for extra in (0, 4, 8, 12, 16):
+        jobs.append((cases.BGRA8_P, wi, hi, wi * 4 + extra, cases.BGRA8_U, wo, ho, wo * 4 + extra, 0, "premul"))
+for (wi, hi, wo, ho) in [(1500, 120, 100, 11), (1021, 50, 64, 5), (777, 95, 33, 7)]:
+    for ti, extra, srgb in [(cases.RGBA8_P, 4, 1), (cases.ARGB8_U, 8, 1), (cases.RGB8, 1, 0), (cases.RGB8, 3, 1), (cases.BGRA8_U, 12, 0)]:
+        jobs.append((ti, wi, hi, wi * cases.bpp(ti) + extra, cases.RGBA8_P, wo, ho, wo * 4, srgb, "random"))
+for (wi, hi, wo, ho) in [(129, 33, 131, 35), (64, 48, 127, 96), (200, 100, 133, 67), (37, 21, 41, 37)]:
+    for ti, to, srgb in [(cases.RGBA8_U, cases.ARGB8_U, 0), (cases.BGRA8_U, cases.BGRA8_U, 1), (cases.RGBA8_P, cases.RGB8, 1),
+                         (cases.RGB8, cases.BGR8, 1), (cases.RGBA8_P, cases.RGB8, 0), (cases.RGB8, cases.RGB8, 0)]:
+        jobs.append((ti, wi, hi, wi * cases.bpp(ti), to, wo, ho, wo * cases.bpp(to) + (1 if cases.bpp(to) == 3 else 0), srgb, "random"))
 for idx, job in enumerate(jobs):
     ti, wi, hi, si, to, wo, ho, so, srgb, mode = job
     src = cases.make_image(ti, wi, hi, si, mode, seed=idx)
@@ -35,4 +47,17 @@ for idx, job in enumerate(jobs):
     sb.scale_simple(src, ti, wi, hi, si, got, to, wo, ho, so, srgb)
     if not np.array_equal(got, want):
         bad += 1; print("MISMATCH host", job)
+# row batches of height-preserving jobs on host buffers (the staged band must hold the row below its last one)
+import threading
+for ti, wi, hi, to, wo, ho in [(cases.BGRA8_P, 640, 360, cases.BGRA8_P, 320, 360), (cases.RGBA8_U, 200, 120, cases.ABGR8_P, 200, 120)]:
+    si, so = wi * cases.bpp(ti), wo * cases.bpp(to)
+    src = cases.make_image(ti, wi, hi, si, "random", seed=7)
+    want = chk.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, 0)
+    out = np.zeros_like(want)
+    ctx = sb.ScaleCtx(src, ti, wi, hi, si, out, to, wo, ho, so, 0)
+    for y in range(0, ho, 50):
+        ctx.batch(y, min(50, ho - y))
+    ctx.destroy()
+    if not np.array_equal(out, want):
+        bad += 1; print("MISMATCH bands", (ti, wi, hi, to, wo, ho))
 print("jobs", len(jobs), "bad", bad)
