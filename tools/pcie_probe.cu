@@ -92,7 +92,7 @@ static long set_mempolicy_node (int node)
 
 typedef struct
 {
-    int dev, numa, bind, mode;      /* mode 0: h2d, 1: d2h, 2: both, 3: pageable h2d */
+    int dev, numa, bind, mode;      /* mode 0: h2d, 1: d2h, 2: both, 3: pageable h2d, 4: 4 bytes up per byte down (BASELINE cfg 2's mix) */
     size_t bytes;
     int reps;
     pthread_barrier_t *bar;
@@ -150,6 +150,11 @@ static void *worker (void *arg)
             CK (cudaMemcpyAsync (h_down, d_b, j->bytes, cudaMemcpyDeviceToHost, s1));
         if (j->mode == 3)
             CK (cudaMemcpyAsync (d_a, pg, j->bytes, cudaMemcpyHostToDevice, s0));
+        if (j->mode == 4)
+        {
+            CK (cudaMemcpyAsync (d_a, h_up, j->bytes, cudaMemcpyHostToDevice, s0));
+            CK (cudaMemcpyAsync (h_down, d_b, j->bytes / 4, cudaMemcpyDeviceToHost, s1));
+        }
     }
     CK (cudaStreamSynchronize (s0));
     CK (cudaStreamSynchronize (s1));
@@ -167,7 +172,7 @@ int main (int argc, char **argv)
     int n_dev = 0;
     const size_t bytes = (size_t) (argc > 1 ? atoi (argv[1]) : 256) << 20;
     const int reps = argc > 2 ? atoi (argv[2]) : 8;
-    static const char *mode_name[] = { "h2d", "d2h", "both", "pageable_h2d" };
+    static const char *mode_name[] = { "h2d", "d2h", "both", "pageable_h2d", "mix_4up_1down" };
 
     CK (cudaGetDeviceCount (&n_dev));
     printf ("{\"gpus_visible\": %d, \"host_cpus\": %ld, \"buffer_mb\": %zu, \"reps\": %d, \"gpu_numa\": [",
@@ -182,7 +187,7 @@ int main (int argc, char **argv)
     int first = 1;
     for (int n = 1; n <= n_dev; n *= 2)
         for (int bind = 0; bind <= 1; bind++)
-            for (int mode = 0; mode < 4; mode++)
+            for (int mode = 0; mode < 5; mode++)
             {
                 if (mode == 3 && bind)
                     continue;
@@ -204,7 +209,7 @@ int main (int argc, char **argv)
                         worst = jobs[i].seconds;
                 }
                 pthread_barrier_destroy (&bar);
-                const double dirs = mode == 2 ? 2.0 : 1.0;
+                const double dirs = mode == 2 ? 2.0 : mode == 4 ? 1.25 : 1.0;
                 printf ("%s\n  {\"gpus\": %d, \"placement\": \"%s\", \"mode\": \"%s\", \"aggregate_gbs\": %.1f, \"per_gpu_gbs\": %.1f, "
                         "\"bound_cpus\": %d, \"mempolicy_rc\": %ld}",
                         first ? "" : ",", n, bind ? "numa" : "plain", mode_name[mode],
