@@ -787,11 +787,26 @@ __device__ __forceinline__ uint32_t half_hreduce (const uint32_t *px)
  * with an odd number of output columns) or 4 (views into larger images): 16-byte accesses become
  * two 64-bit or four 32-bit ones.  The narrow loads allocate in L1 -- a warp still covers a
  * contiguous run of the row, each sector is fetched from L2 once and its other words hit L1. */
+/* `interior`: the four bytes before p and the four after p + 16 belong to the same source row (any
+ * chunk but a row's first and last), so a chunk that is only 4-byte aligned may be assembled from
+ * the three aligned 64-bit words around it instead of four 32-bit ones. */
 template <int AL>
-__device__ __forceinline__ uint4 half_load16 (const uint8_t *p)
+__device__ __forceinline__ uint4 half_load16 (const uint8_t *p, bool interior = false)
 {
     if constexpr (AL == 4)
     {
+        if ((reinterpret_cast<uintptr_t> (p) & 7) == 0)
+        {
+            const uint2 *w = reinterpret_cast<const uint2 *> (p);
+            const uint2 a = __ldg (w), b = __ldg (w + 1);
+            return make_uint4 (a.x, a.y, b.x, b.y);
+        }
+        if (interior)
+        {
+            const uint2 *w = reinterpret_cast<const uint2 *> (p - 4);
+            const uint2 a = __ldg (w), b = __ldg (w + 1), c = __ldg (w + 2);
+            return make_uint4 (a.y, b.x, b.y, c.x);
+        }
         const uint32_t *w = reinterpret_cast<const uint32_t *> (p);
         return make_uint4 (__ldg (w), __ldg (w + 1), __ldg (w + 2), __ldg (w + 3));
     }
@@ -884,8 +899,10 @@ smol_half_kernel (const HalfParams P)
             if constexpr (HH == 0)
             {
                 /* 4 output pixels = 8 source pixels = two 128-bit loads per row */
-                const uint4 a0 = half_load16<AL> (row0), a1 = half_load16<AL> (row0 + 16);
-                const uint4 b0 = half_load16<AL> (row1), b1 = half_load16<AL> (row1 + 16);
+                /* (x is a multiple of 4: this thread's 32 source bytes start the row iff x == 0 and end it iff x + 4 == w_out) */
+                const bool in0 = x > 0, in1 = x + 4 < P.w_out;
+                const uint4 a0 = half_load16<AL> (row0, in0), a1 = half_load16<AL> (row0 + 16, in1);
+                const uint4 b0 = half_load16<AL> (row1, in0), b1 = half_load16<AL> (row1 + 16, in1);
                 h0[0] = byte_avg_floor (a0.x, a0.y); h0[1] = byte_avg_floor (a0.z, a0.w);
                 h0[2] = byte_avg_floor (a1.x, a1.y); h0[3] = byte_avg_floor (a1.z, a1.w);
                 h1[0] = byte_avg_floor (b0.x, b0.y); h1[1] = byte_avg_floor (b0.z, b0.w);
@@ -1143,7 +1160,7 @@ smol_half_wide_kernel (const HalfParams P)
     uint4 rows[N_ROWS];
 #pragma unroll
     for (int r = 0; r < N_ROWS; r++)
-        rows[r] = live ? half_load16<AL> (src + (size_t) r * P.src_pitch) : make_uint4 (0, 0, 0, 0);
+        rows[r] = live ? half_load16<AL> (src + (size_t) r * P.src_pitch, cx > 0 && cx + 1 < n_chunks) : make_uint4 (0, 0, 0, 0);
 
     uint32_t acc_lo = 0, acc_hi = 0, res = 0;
 #pragma unroll
