@@ -166,8 +166,10 @@ def test_dispatch_table():
         ("taps128", c.RGBA8_U, 3840, 2160, c.RGBA8_U, 3839, 2159, 0),       # unassociated -> unassociated, ~1:1
         ("tile128", c.RGBA8_U, 1920, 1080, c.RGBA8_U, 3840, 2160, 0),       # ... upscale
         ("box", c.RGB8, 7680, 4320, c.RGB8, 800, 450, 0),                   # box without linear light
-        ("general", c.RGBA8_P, 3000, 7, c.RGBA8_P, 11, 7, 0),               # box on one axis only
-        ("general", c.RGBA8_P, 9000, 1, c.RGBA8_P, 1, 1, 0),                # > 255:1 without linear light
+        ("rows", c.RGBA8_P, 3000, 7, c.RGBA8_P, 11, 7, 0),                  # box on one axis only
+        ("rows", c.RGBA8_P, 7680, 1080, c.RGBA8_P, 800, 540, 1),            # ... in linear light
+        ("rows", c.RGBA8_P, 7680, 4320, c.RGBA8_P, 20, 12, 0),              # > 255:1 without linear light
+        ("general", c.RGBA8_P, 9000, 1, c.RGBA8_P, 1, 1, 0),                # ... a 36 KB window per warp: the CTA-wide backstop
     ]
     for want, ti, wi, hi, to, wo, ho, srgb in expect:
         got = sb.plan_query(ti, wi, hi, to, wo, ho, srgb)["kernel_name"]
