@@ -73,11 +73,30 @@ def alpha_index(t):
     return 3 if (t & 3) < 2 else 0
 
 
-def ncu_traffic_bytes(cfg_name):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this config's kernel, from the
-    committed `ncu --set full` capture summary (profiles/rNN_ncu_full_<cfg>.txt; newest round wins)."""
+def ncu_traffic_bytes(cfg_name, launches_per_graph=16):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of this config's kernel.  Preferred source: a
+    graph-level capture of one whole replayed step (profiles/rNN_ncu_graph_<cfg>.csv, `ncu --graph-profiling
+    graph`: the launches overlap as in the bench and the written output is charged too), divided by the
+    launches in the graph; else the committed `ncu --set full` summary of one isolated launch
+    (profiles/rNN_ncu_full_<cfg>.txt; newest round wins)."""
+    import csv
     import glob
     import re
+    graphs = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_graph_%s.csv" % cfg_name)))
+    if graphs:
+        try:
+            rows = list(csv.reader(open(graphs[-1])))
+            hdr = [r for r in rows if r and r[0] == "ID"][0]
+            per_id = {}
+            for r in rows:
+                if len(r) == len(hdr) and r[0] != "ID":
+                    d = dict(zip(hdr, r))
+                    if d["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                        per_id[d["ID"]] = per_id.get(d["ID"], 0.0) + float(d["Metric Value"])
+            if per_id:
+                return int(sum(per_id.values()) / len(per_id) / launches_per_graph), os.path.relpath(graphs[-1], ROOT)
+        except Exception:
+            pass
     best = None
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_%s.txt" % cfg_name))):
         best = path

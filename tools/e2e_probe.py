@@ -19,7 +19,7 @@ pin_in = torch.from_numpy(src.copy()).pin_memory(); pin_out = torch.zeros(frames
 pg_in = src.reshape(-1).copy(); pg_out = np.zeros(frames * out_bytes, np.uint8)
 res = {"config": cfg_name, "env": {k: v for k, v in os.environ.items() if k.startswith("SMOL_")}, "runs": []}
 for kind, a, b in (("pinned", pin_in.data_ptr(), pin_out.data_ptr()), ("pageable", pg_in.ctypes.data, pg_out.ctypes.data)):
-    for threads in (1, 3):
+    for threads in [int(t) for t in os.environ.get("E2E_THREADS", "1,3").split(",")]:
         pool = concurrent.futures.ThreadPoolExecutor(max_workers=threads)
         def one(f):
             sb.scale_simple(a + f * in_bytes, ti, wi, hi, si, b + f * out_bytes, to, wo, ho, so, srgb)
