@@ -5268,6 +5268,21 @@ launch_magb (const SmolLaunch &L, cudaStream_t stream)
     return launch_magb_fmt<4, 4, false, false, false> (M, src32, grid, smem, stream);
 }
 
+/* work items per SM below which the box launcher trades lanes per column for more items (SMOL_BOX_MIN_WARPS) */
+static double
+box_min_warps ()
+{
+    static double v = -1.0;
+    if (v < 0)
+    {
+        const char *e = getenv ("SMOL_BOX_MIN_WARPS");
+        /* measured on B200 (us per frame at 26 = every resident warp / 16 / 12 / 8): a 57-row band of cfg 3
+         * 25.7 / 16.6 / 16.6 / 19.5, 2048^2 -> 128^2 15.3 / 15.3 / 12.9 / 12.9, 4000x3000 -> 200x150 51.4 / 30.8 / 33.6 / 33.6 */
+        v = e && atof (e) > 0 ? atof (e) : 12.0;
+    }
+    return v;
+}
+
 static void
 box_params_init (BoxParams &P, const SmolLaunch &L)
 {
@@ -5494,9 +5509,12 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         if (smem > 32 * 1024)        /* static shared memory counts against the 48 KB default too */
             smem_optin (fn, 225 * 1024);
         per_sm = (uint32_t) cached_occupancy (fn, (int) warps_per_cta * 32, smem);
-        /* (column tiles x output rows: strips are chosen after G, they must not make it grow) */
-        const double rounds = (double) P.x_tiles * L.n_rows * L.n_images / ((double) num_sms () * per_sm * warps_per_cta);
-        if (tune_g != 99 || glog >= 5 || rounds >= 1.0)
+        /* More lanes per column only while the job is too small to keep ~8 warps per SM busy (column
+         * tiles x output rows; strips are chosen after G and must not make it grow): every extra lane
+         * repeats the per-row overhead, so an under-filled GPU at G = 1 still beats a full one at G = 4
+         * (a 57-row band of cfg 3, one GPU of eight: 25.7 -> 16.6 us). */
+        const double busy = (double) P.x_tiles * L.n_rows * L.n_images / ((double) num_sms () * per_sm * box_min_warps ());
+        if (tune_g != 99 || glog >= 5 || busy >= 1.0)
             break;
     }
 

@@ -24,9 +24,16 @@ d_out = torch.zeros((frames, ho * so), dtype=torch.uint8, device="cuda")
 stream = torch.cuda.Stream()
 with torch.cuda.stream(stream):
     sb.set_stream(stream.cuda_stream)
+    band = [a for a in sys.argv if a.startswith("--rows=")]     # --rows=FIRST:COUNT : one output row band per frame (smol_scale_batch_full)
     def step():
         for f in range(frames):
-            sb.scale_simple(d_in[f].data_ptr(), ti, wi, hi, si, d_out[f].data_ptr(), to, wo, ho, so, srgb)
+            if band:
+                first, count = [int(v) for v in band[0][7:].split(":")]
+                ctx = sb.ScaleCtx(d_in[f].data_ptr(), ti, wi, hi, si, None, to, wo, ho, so, srgb)
+                ctx.batch_full(d_out[f].data_ptr(), first, count)
+                ctx.destroy()
+            else:
+                sb.scale_simple(d_in[f].data_ptr(), ti, wi, hi, si, d_out[f].data_ptr(), to, wo, ho, so, srgb)
     sb.reset_stats(); step(); stream.synchronize()
     fam = {k: v for k, v in sb.kernel_launches().items() if v}
     g = torch.cuda.CUDAGraph()
