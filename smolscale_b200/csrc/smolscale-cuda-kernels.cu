@@ -3947,18 +3947,130 @@ smol_tile128_kernel (const Tile128Params M)
 struct RowsParams
 {
     SmolLaunch L;
+    BoxParams b;                    /* the lane-arithmetic variants' selectors (box_params_init) */
     uint32_t lanes_per_col_log2;    /* box spans: lanes sharing a column */
     uint32_t x_tiles;               /* items per strip of rows */
     uint32_t rows_per_item, n_strips;
     uint32_t seg_bytes;             /* bytes per staging buffer (multiple of 16) */
 };
 
-template <bool S128, bool HBOX, bool VBOX>
+/* Pixel arithmetic of the rows kernel, two interchangeable sets:
+ *   RowsSwar<S128>      the general kernel's: 64-bit words of 16- or 32-bit lanes, formats decoded at
+ *                       run time (unpack_px / pack_px) -- every format, every storage, any alignment;
+ *   RowsLanes<MODE, BI> the box kernel's: 32-bit registers, the intermediate encoding and the source
+ *                       pixel size fixed at compile time (box_unpack) -- word-aligned 32bpp rows or
+ *                       24bpp rows; about four times fewer instructions per source pixel. */
+struct RowsTables
+{
+    const SmolDeviceLuts *luts;     /* shared-memory copy */
+    const uint32_t *inv8, *from;    /* inv_div_p8 << 3 and from_srgb as 32-bit words, shared memory */
+};
+
+template <bool S128>
+struct RowsSwar
+{
+    typedef Px<S128> P;
+    static constexpr bool WIDE = S128;
+    static __device__ __forceinline__ P zero () { return px_zero<S128> (); }
+    static __device__ __forceinline__ void add (P &a, const P &b) { px_add<S128> (a, b); }
+    static __device__ __forceinline__ P weight (const P &p, uint32_t w) { return px_weight<S128> (p, w); }
+    static __device__ __forceinline__ P lerp (const P &p, const P &q, uint32_t F) { return px_lerp<S128> (p, q, F); }
+    static __device__ __forceinline__ P halve (const P &p, uint32_t n) { return px_halve<S128> (p, n); }
+    static __device__ __forceinline__ P scale (const P &p, uint32_t mul, const RowsParams &) { return px_box_scale<S128> (p, mul); }
+    static __device__ __forceinline__ P shfl_add (const P &p, uint32_t m) { return px_shfl_xor_add<S128> (p, m); }
+    static __device__ __forceinline__ P fetch (const uint8_t *sm, uint32_t j, const RowsParams &R, const RowsTables &T)
+    {
+        return unpack_px<S128> (load_raw_px (sm + (size_t) j * R.L.d.bpp_in, R.L.d.bpp_in), R.L.d, T.luts);
+    }
+    static __device__ __forceinline__ uint32_t pack (const P &p, const RowsParams &R, const RowsTables &T)
+    {
+        return pack_px<S128> (p, R.L.d, T.luts);
+    }
+};
+
+template <int MODE, int BI>
+struct RowsLanes
+{
+    typedef BoxPx<MODE> P;
+    static constexpr bool WIDE = MODE >= BM_P8L_P;
+    static constexpr int N = WIDE ? 4 : 2;
+    static constexpr uint32_t MASK = WIDE ? 0x00ffffffu : 0x00ff00ffu;
+    static __device__ __forceinline__ P zero ()
+    {
+        P r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = 0;
+        return r;
+    }
+    static __device__ __forceinline__ void add (P &a, const P &b) { box_add<MODE> (a, b); }
+    static __device__ __forceinline__ P weight (const P &p, uint32_t w) { return box_weight<MODE> (p, w); }
+    static __device__ __forceinline__ P lerp (const P &p, const P &q, uint32_t F)
+    {
+        P r;
+        const uint32_t G = 256u - F;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = ((p.v[i] * F + q.v[i] * G) >> 8) & MASK;
+        return r;
+    }
+    static __device__ __forceinline__ P halve (const P &p, uint32_t n)
+    {
+        P r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = (p.v[i] >> n) & MASK;
+        return r;
+    }
+    static __device__ __forceinline__ P scale (const P &p, uint32_t mul, const RowsParams &R) { return box_scale<MODE> (p, mul, R.b.acc_fits_24 != 0); }
+    static __device__ __forceinline__ P shfl_add (P p, uint32_t m)
+    {
+#pragma unroll
+        for (int i = 0; i < N; i++) p.v[i] += __shfl_xor_sync (0xffffffffu, p.v[i], m);
+        return p;
+    }
+    static __device__ __forceinline__ P fetch (const uint8_t *sm, uint32_t j, const RowsParams &R, const RowsTables &T)
+    {
+        uint32_t raw;
+        if constexpr (BI == 4)
+            raw = *reinterpret_cast<const uint32_t *> (sm + (size_t) j * 4);       /* rows are word aligned, so is the staging offset */
+        else
+        {
+            const uintptr_t a = reinterpret_cast<uintptr_t> (sm + (size_t) j * 3);
+            const uint32_t *w = reinterpret_cast<const uint32_t *> (a & ~(uintptr_t) 3);
+            raw = __funnelshift_r (w[0], w[1], (uint32_t) (a & 3) * 8) | 0xff000000u;
+        }
+        return box_unpack<MODE, 0> (raw, R.b, T.inv8, T.from, nullptr);
+    }
+    static __device__ __forceinline__ uint32_t pack (const P &p, const RowsParams &R, const RowsTables &T)
+    {
+        if constexpr (WIDE)
+        {
+            Px<true> o;
+            o.w[0] = (uint64_t) p.v[0] | ((uint64_t) p.v[1] << 32);
+            o.w[1] = (uint64_t) p.v[2] | ((uint64_t) p.v[3] << 32);
+            return pack_px<true> (o, R.L.d, T.luts);
+        }
+        else
+        {
+            /* the pixel's four bytes in source order (see the box kernel) */
+            const uint32_t bytes = p.v[0] | (p.v[1] << 8);
+            const uint32_t alpha = (bytes >> R.b.alpha_shift) & 0xff;
+            const uint32_t cols = bytes >> R.b.col_shift;
+            Px<false> o;
+            o.w[0] = (uint64_t) alpha | ((uint64_t) (cols & 0xff) << 16) | ((uint64_t) ((cols >> 8) & 0xff) << 32)
+                     | ((uint64_t) ((cols >> 16) & 0xff) << 48);
+            return pack_px<false> (o, R.L.d, T.luts);
+        }
+    }
+};
+
+template <class OPS, bool HBOX, bool VBOX>
 __global__ void __launch_bounds__ (256)
 smol_rows_kernel (const RowsParams P)
 {
+    typedef typename OPS::P PxT;
+    constexpr bool S128 = OPS::WIDE;
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
     __shared__ SmolDeviceLuts sm_luts;
+    __shared__ uint32_t sm_inv8[256], sm_from[256];
     const SmolLaunch &L = P.L;
     const SmolJobDesc &d = L.d;
     const uint32_t bpp = d.bpp_in;
@@ -3970,10 +4082,15 @@ smol_rows_kernel (const RowsParams P)
         uint32_t *s = reinterpret_cast<uint32_t *> (&sm_luts);
         for (uint32_t i = threadIdx.x; i < sizeof (SmolDeviceLuts) / 4; i += blockDim.x)
             s[i] = __ldg (g + i);
+        sm_inv8[threadIdx.x] = __ldg (&L.luts->inv_div_p8[threadIdx.x]) << 3;
+        sm_from[threadIdx.x] = L.luts->from_srgb[threadIdx.x];
     }
     __syncthreads ();
     pdl_wait ();
-    const SmolDeviceLuts *luts = &sm_luts;
+    RowsTables tabs;
+    tabs.luts = &sm_luts;
+    tabs.inv8 = sm_inv8;
+    tabs.from = sm_from;
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t G = 1u << P.lanes_per_col_log2, g = lane & (G - 1);
@@ -4075,18 +4192,18 @@ smol_rows_kernel (const RowsParams P)
             cp_async_commit ();
         };
 
-        Px<S128> vacc = px_zero<S128> ();       /* box: the output row's accumulator; taps: the sum of its samples */
-        Px<S128> h_prev = px_zero<S128> ();     /* taps: the row above */
+        PxT vacc = OPS::zero ();       /* box: the output row's accumulator; taps: the sum of its samples */
+        PxT h_prev = OPS::zero ();     /* taps: the row above */
         bool top_pending = true;                /* box: the current output row's first source row is still to come */
         uint32_t yl_cur = yl0;
         uint32_t cur = 0;
 
-        auto emit_row = [&] (const Px<S128> &out)
+        auto emit_row = [&] (const PxT &out)
         {
             if (store)
             {
                 uint8_t *o = dst_img + (size_t) yl_cur * L.dst_pitch + (size_t) x * d.bpp_out;
-                store_raw_px (o, pack_px<S128> (out, d, luts), d.bpp_out);
+                store_raw_px (o, OPS::pack (out, P, tabs), d.bpp_out);
             }
             yl_cur++;
         };
@@ -4105,38 +4222,38 @@ smol_rows_kernel (const RowsParams P)
 
             /* pixel j of the row starts at sm[j * bpp - w0] */
             const uint8_t *sm = bufs + cur - staged_from (r);
-            auto px_at = [&] (uint32_t j) -> Px<S128>
+            auto px_at = [&] (uint32_t j) -> PxT
             {
-                return unpack_px<S128> (load_raw_px (sm + (size_t) j * bpp, bpp), d, luts);
+                return OPS::fetch (sm, j, P, tabs);
             };
 
-            Px<S128> h;
+            PxT h;
             if constexpr (HBOX)
             {
                 /* generic:1427-1556 in absolute offsets */
-                Px<S128> acc = px_zero<S128> ();
+                PxT acc = OPS::zero ();
                 for (uint32_t j = hL + 1 + g; j < hR; j += G)
-                    px_add<S128> (acc, px_at (j));
+                    OPS::add (acc, px_at (j));
                 if (g == 0)
-                    px_add<S128> (acc, px_weight<S128> (px_at (hL), wl));
+                    OPS::add (acc, OPS::weight (px_at (hL), wl));
                 if (g == G - 1 && wr > 0)
-                    px_add<S128> (acc, px_weight<S128> (px_at (hR), wr));
+                    OPS::add (acc, OPS::weight (px_at (hR), wr));
                 for (uint32_t m = G >> 1; m; m >>= 1)
-                    acc = px_shfl_xor_add<S128> (acc, m);
-                h = px_box_scale<S128> (acc, d.span_mul_x);
+                    acc = OPS::shfl_add (acc, m);
+                h = OPS::scale (acc, d.span_mul_x, P);
             }
             else
             {
                 /* generic:1290-1425 */
-                Px<S128> acc = px_zero<S128> ();
+                PxT acc = OPS::zero ();
                 const uint32_t *tx = L.tab_x + (x << hh);
                 for (uint32_t k = 0; k < (1u << hh); k++)
                 {
                     const uint32_t e = __ldg (&tx[k]);
                     const uint32_t ofs = SMOL_TAB_OFS (e);
-                    px_add<S128> (acc, px_lerp<S128> (px_at (ofs), px_at (min (ofs + 1, d.w_in - 1)), SMOL_TAB_F (e)));
+                    OPS::add (acc, OPS::lerp (px_at (ofs), px_at (min (ofs + 1, d.w_in - 1)), SMOL_TAB_F (e)));
                 }
-                h = px_halve<S128> (acc, hh);
+                h = OPS::halve (acc, hh);
             }
 
             if constexpr (VBOX)
@@ -4145,16 +4262,16 @@ smol_rows_kernel (const RowsParams P)
                  * handed on to the next output row (see the box kernel) */
                 if (top_pending)
                 {
-                    px_add<S128> (vacc, px_weight<S128> (h, w1_cur));
+                    OPS::add (vacc, OPS::weight (h, w1_cur));
                     top_pending = false;
                 }
                 else if (r == B_cur)
-                    px_add<S128> (vacc, px_weight<S128> (h, w2_cur));
+                    OPS::add (vacc, OPS::weight (h, w2_cur));
                 else
-                    px_add<S128> (vacc, h);
+                    OPS::add (vacc, h);
                 if (r == rend_cur)
                 {
-                    emit_row (px_box_scale<S128> (vacc, d.span_mul_y));
+                    emit_row (OPS::scale (vacc, d.span_mul_y, P));
                     if (yl_cur < yl1)
                     {
                         const uint32_t yn = L.first_row + yl_cur;
@@ -4166,9 +4283,9 @@ smol_rows_kernel (const RowsParams P)
                         B_cur = SMOL_TAB_OFS (e1);
                         w2_cur = S128 ? F_new - 1 : F_new;
                         rend_cur = F_new > 0 ? B_cur : B_cur - 1;
-                        vacc = px_zero<S128> ();
+                        vacc = OPS::zero ();
                         if (shared)
-                            px_add<S128> (vacc, px_weight<S128> (h, w1_cur));
+                            OPS::add (vacc, OPS::weight (h, w1_cur));
                         top_pending = !shared;
                     }
                 }
@@ -4183,12 +4300,12 @@ smol_rows_kernel (const RowsParams P)
                     const uint32_t r0 = SMOL_TAB_OFS (e), r1 = min (r0 + 1, d.h_in - 1);
                     if (r1 > r)
                         break;
-                    px_add<S128> (vacc, px_lerp<S128> (r0 == r ? h : h_prev, h, SMOL_TAB_F (e)));
+                    OPS::add (vacc, OPS::lerp (r0 == r ? h : h_prev, h, SMOL_TAB_F (e)));
                     k_cur++;
                     if ((k_cur & ((1u << vh) - 1)) == 0)
                     {
-                        emit_row (px_halve<S128> (vacc, vh));
-                        vacc = px_zero<S128> ();
+                        emit_row (OPS::halve (vacc, vh));
+                        vacc = OPS::zero ();
                     }
                 }
                 h_prev = h;
@@ -5752,13 +5869,22 @@ launch_tile128 (const SmolLaunch &L, cudaStream_t stream)
 #undef TILE128_BO
 }
 
-template <bool S128, bool HBOX, bool VBOX>
+template <class OPS, bool HBOX, bool VBOX>
 static cudaError_t
 launch_rows_k (const RowsParams &P, dim3 grid, size_t smem, cudaStream_t stream)
 {
-    if (smem > 40 * 1024)
-        smem_optin ((const void *) smol_rows_kernel<S128, HBOX, VBOX>, 200 * 1024);
-    return launch_pdl (smol_rows_kernel<S128, HBOX, VBOX>, P, grid, dim3 (256), smem, stream);
+    if (smem > 32 * 1024)
+        smem_optin ((const void *) smol_rows_kernel<OPS, HBOX, VBOX>, 200 * 1024);
+    return launch_pdl (smol_rows_kernel<OPS, HBOX, VBOX>, P, grid, dim3 (256), smem, stream);
+}
+
+/* one of the two mixed filter pairs with compile-time lane arithmetic */
+template <int MODE, int BI>
+static cudaError_t
+launch_rows_lanes (const RowsParams &P, bool hbox, dim3 grid, size_t smem, cudaStream_t stream)
+{
+    return hbox ? launch_rows_k<RowsLanes<MODE, BI>, true, false> (P, grid, smem, stream)
+                : launch_rows_k<RowsLanes<MODE, BI>, false, true> (P, grid, smem, stream);
 }
 
 static cudaError_t
@@ -5768,6 +5894,7 @@ launch_rows (const SmolLaunch &L, cudaStream_t stream)
     RowsParams P;
     uint32_t glog = 0;
 
+    memset (&P, 0, sizeof (P));
     P.L = L;
     P.seg_bytes = rows_seg_bytes (L, &glog);
     /* few work items (small outputs): more lanes per box column make more of them */
@@ -5814,17 +5941,46 @@ launch_rows (const SmolLaunch &L, cudaStream_t stream)
     dim3 grid ((unsigned) blocks);
     const bool hb = d.h_kind == SMOL_AXIS_BOX, vb = d.v_kind == SMOL_AXIS_BOX;
 
+    /* Box on one axis and bilinear on the other, an intermediate the lane arithmetic knows (not
+     * 8-bit values in 128bpp storage, i.e. > 255:1 without linear light), word-aligned 32bpp rows:
+     * compile-time formats. */
+    static int lanes_on = -1;
+    if (lanes_on < 0)
+    {
+        const char *e = getenv ("SMOL_ROWS_LANES");
+        lanes_on = e ? atoi (e) : 1;
+    }
+    const bool src_ok = d.bpp_in == 3 || (aligned4 (L.src) && (L.src_pitch & 3) == 0 && (L.src_image_stride & 3) == 0);
+    if (lanes_on && hb != vb && src_ok && !(d.mid == SMOL_MID_P8 && d.storage128))
+    {
+        box_params_init (P.b, L);
+        const bool bi3 = d.bpp_in == 3;
+        if (d.mid == SMOL_MID_P8)
+        {
+            if (d.in_unassoc)   return launch_rows_lanes<BM_P8_U, 4> (P, hb, grid, smem, stream);
+            return bi3 ? launch_rows_lanes<BM_P8_P, 3> (P, hb, grid, smem, stream) : launch_rows_lanes<BM_P8_P, 4> (P, hb, grid, smem, stream);
+        }
+        if (d.mid == SMOL_MID_P8L)
+        {
+            if (d.in_unassoc)   return launch_rows_lanes<BM_P8L_U, 4> (P, hb, grid, smem, stream);
+            return bi3 ? launch_rows_lanes<BM_P8L_P, 3> (P, hb, grid, smem, stream) : launch_rows_lanes<BM_P8L_P, 4> (P, hb, grid, smem, stream);
+        }
+        if (d.mid == SMOL_MID_P16)
+            return launch_rows_lanes<BM_P16_U, 4> (P, hb, grid, smem, stream);
+        return launch_rows_lanes<BM_P16L_U, 4> (P, hb, grid, smem, stream);
+    }
+
     if (d.storage128)
     {
-        if (hb && vb)   return launch_rows_k<true, true, true> (P, grid, smem, stream);
-        if (hb)         return launch_rows_k<true, true, false> (P, grid, smem, stream);
-        if (vb)         return launch_rows_k<true, false, true> (P, grid, smem, stream);
-        return launch_rows_k<true, false, false> (P, grid, smem, stream);
+        if (hb && vb)   return launch_rows_k<RowsSwar<true>, true, true> (P, grid, smem, stream);
+        if (hb)         return launch_rows_k<RowsSwar<true>, true, false> (P, grid, smem, stream);
+        if (vb)         return launch_rows_k<RowsSwar<true>, false, true> (P, grid, smem, stream);
+        return launch_rows_k<RowsSwar<true>, false, false> (P, grid, smem, stream);
     }
-    if (hb && vb)       return launch_rows_k<false, true, true> (P, grid, smem, stream);
-    if (hb)             return launch_rows_k<false, true, false> (P, grid, smem, stream);
-    if (vb)             return launch_rows_k<false, false, true> (P, grid, smem, stream);
-    return launch_rows_k<false, false, false> (P, grid, smem, stream);
+    if (hb && vb)       return launch_rows_k<RowsSwar<false>, true, true> (P, grid, smem, stream);
+    if (hb)             return launch_rows_k<RowsSwar<false>, true, false> (P, grid, smem, stream);
+    if (vb)             return launch_rows_k<RowsSwar<false>, false, true> (P, grid, smem, stream);
+    return launch_rows_k<RowsSwar<false>, false, false> (P, grid, smem, stream);
 }
 
 template <bool S128, bool HBOX, bool VBOX>
