@@ -2644,11 +2644,15 @@ __device__ __forceinline__ void mbar_wait (uint32_t mbar, uint32_t parity)
  * in GLOBAL memory; what changes from row to row is where the row's first byte lands in the
  * staging buffer, a per-row constant added to the lane's walk addresses.  Chunks that straddle the
  * row's start or end are copied byte-exactly, so nothing outside the row is ever touched. */
-template <int MODE, int LUTM, int BI, bool RS = false>
+/* G1: one lane per column (spans of up to 16 pixels: cfg 3 and most thumbnails), known at compile
+ * time: constant loop strides, no lane-group bookkeeping for the compiler to keep alive or rebuild in
+ * the row loop (the kernel runs at its 64-register cap). */
+template <int MODE, int LUTM, int BI, bool RS = false, bool G1 = false>
 __global__ void __launch_bounds__ (LUTM == 3 ? SMOL_BOX3_MAX_WARPS * 32 : LUTM == 1 ? 1024 : LUTM == 2 ? 512 : 256, LUTM == 1 || LUTM == 3 ? 1 : LUTM == 2 ? 2 : 5)
 smol_box_kernel (const BoxParams P)
 {
     static_assert (!RS || LUTM == 3, "row-shifted staging exists for the lean row loop only");
+    static_assert (!G1 || (LUTM == 3 && !RS), "the one-lane-per-column instance exists for the aligned lean row loop only");
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
     __shared__ uint32_t sm_inv8_plain[LUTM == 0 ? 256 : 1];
     __shared__ uint32_t sm_from_plain[LUTM == 0 ? 256 : 1];
@@ -2749,8 +2753,8 @@ smol_box_kernel (const BoxParams P)
     uint32_t opaque_backoff = 0;    /* rows to go before the warp tries the opaque walk again */
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t G = 1u << P.lanes_per_col_log2, g = lane & (G - 1);
-    const uint32_t cols_per_item = 32u >> P.lanes_per_col_log2;
+    const uint32_t G = G1 ? 1u : 1u << P.lanes_per_col_log2, g = G1 ? 0u : lane & (G - 1);
+    const uint32_t cols_per_item = G1 ? 32u : 32u >> P.lanes_per_col_log2;
     uint8_t *bufs = sm_dyn + TAB_BYTES + (size_t) warp * 2 * P.seg_bytes;
     if constexpr (LUTM == 3 && NEED_FROM)
     {
@@ -2775,7 +2779,7 @@ smol_box_kernel (const BoxParams P)
         const uint32_t y = P.first_row + yl;
         const uint32_t x_first = xt * cols_per_item;
         const uint32_t x_last = min (x_first + cols_per_item, d.w_out) - 1;
-        uint32_t x = x_first + (lane >> P.lanes_per_col_log2);
+        uint32_t x = x_first + (G1 ? lane : lane >> P.lanes_per_col_log2);
         const bool store = x <= x_last && g == 0;
         x = min (x, x_last);
 
@@ -5512,10 +5516,14 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
     const bool rs = !(aligned16 (L.src) && (L.src_pitch & 15) == 0 && (L.src_image_stride & 15) == 0);
     if (rs && lutm != 3)
         return cudaErrorNotSupported;   /* the caller falls back to the general kernel */
-#define BOX_K3(M, B) (rs ? (const void *) smol_box_kernel<M, 3, B, true> : (const void *) smol_box_kernel<M, 3, B, false>)
+#define BOX_K3(M, B) (rs ? (const void *) smol_box_kernel<M, 3, B, true, false> : g1 ? (const void *) smol_box_kernel<M, 3, B, false, true> \
+                         : (const void *) smol_box_kernel<M, 3, B, false, false>)
 #define BOX_KERNEL_FOR(M) (lutm == 3 ? BOX_K3 (M, 4) : lutm == 1 ? (const void *) smol_box_kernel<M, 1, 4> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 4> : (const void *) smol_box_kernel<M, 0, 4>)
 #define BOX_KERNEL_FOR3(M) (lutm == 3 ? BOX_K3 (M, 3) : lutm == 1 ? (const void *) smol_box_kernel<M, 1, 3> : lutm == 2 ? (const void *) smol_box_kernel<M, 2, 3> : (const void *) smol_box_kernel<M, 0, 3>)
-    const void *fn;
+    /* (picked again once the lanes per column are known: one lane per column has its own instance) */
+    const void *fn = nullptr;
+    auto pick_fn = [&] (bool g1)
+    {
     switch (mode)
     {
         case BM_P8_P:   fn = lutm == 3 ? (bi3 ? BOX_K3 (BM_P8_P, 3) : BOX_K3 (BM_P8_P, 4))
@@ -5527,9 +5535,11 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
         default:        fn = lutm == 3 ? BOX_K3 (BM_P16L_U, 4)
                              : lutm == 2 ? (const void *) smol_box_kernel<BM_P16L_U, 2, 4> : (const void *) smol_box_kernel<BM_P16L_U, 0, 4>; break;
     }
+    };
 #undef BOX_KERNEL_FOR
 #undef BOX_KERNEL_FOR3
 #undef BOX_K3
+    pick_fn (false);
 
     /* Lanes per column (G).  Long spans want several lanes per column (8..16 source pixels per
      * lane per row).  Every extra lane repeats the per-row overhead (edge pixels, normalisation),
@@ -5550,6 +5560,7 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
             glog = (uint32_t) tune_g;
         const uint32_t cols = 32u >> glog;
         P.lanes_per_col_log2 = glog;
+        pick_fn (glog == 0 && lutm == 3 && !rs);
         P.x_tiles = (d.w_out + cols - 1) / cols;
         /* staging buffer: the widest segment an item can need, + alignment slack */
         const uint64_t seg_px = ((uint64_t) cols * d.w_in + d.w_out - 1) / d.w_out + 3;
