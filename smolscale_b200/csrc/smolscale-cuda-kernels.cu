@@ -5254,14 +5254,17 @@ launch_magb (const SmolLaunch &L, cudaStream_t stream)
     MagbParams M;
 
     taps_params_init (M.t, L);
-    static int tune_tb = -1, tune_th = -1, tune_hmax = 64;
-    static uint32_t magb_reg_ctas = 8;
+    static int tune_tb = -1, tune_th = -1, tune_hmax = 64, tune_waves = 1;
+    static uint32_t magb_reg_ctas = 5;      /* resident CTAs per SM by registers (48 x 256 threads) */
     if (tune_tb < 0)
     {
         const char *a = getenv ("SMOL_MAGB_TB"), *b = getenv ("SMOL_MAGB_TH"), *c = getenv ("SMOL_MAGB_CTAS");
-        const char *hm = getenv ("SMOL_MAGB_HMAX");
+        const char *hm = getenv ("SMOL_MAGB_HMAX"), *wv = getenv ("SMOL_MAGB_WAVES");
         if (hm && atoi (hm) >= 8 && atoi (hm) <= SMOL_MAGB_MAX_TILE_H)
             tune_hmax = atoi (hm);
+        if (wv)
+            tune_waves = atoi (wv) != 0;
+        (void) tune_hmax;
         tune_tb = a ? atoi (a) : 0;
         tune_th = b ? atoi (b) : 0;
         if (c && atoi (c) > 0)
@@ -5311,8 +5314,32 @@ launch_magb (const SmolLaunch &L, cudaStream_t stream)
             c_max++;
         for (uint32_t c = c_max >= 5 ? 5 : c_max; c <= c_max; c++)
         {
-            for (uint32_t h = 8; h <= (uint32_t) tune_hmax; h *= 2)
+            /* Candidate tile heights: powers of two, and the heights at which the grid fills exactly
+             * 1, 2 or 3 waves of resident CTAs -- a 1.56-wave grid leaves the SMs half empty for its
+             * last third and the next frame's CTAs idle at the dependency wait meanwhile (cfg 4: 64-row
+             * tiles, 1152 CTAs, 11.5 us; 104-row tiles, 720 CTAs = one wave of 5 per SM, 10.0 us). */
+            uint32_t heights[24], n_heights = 0;
+            for (uint32_t h = 8; h <= 64; h *= 2)
+                heights[n_heights++] = h;
+            if (tune_th > 0 && tune_th <= SMOL_MAGB_MAX_TILE_H)
+                heights[n_heights++] = (uint32_t) tune_th;
+            if (tune_waves)
             {
+                const uint64_t tiles_x = (uint64_t) ((M.nb_row + (16u << c) - 1) / (16u << c)) * L.n_images;
+                for (uint32_t per = 2; per <= magb_reg_ctas; per++)
+                    for (uint32_t w = 1; w <= 3; w++)
+                    {
+                        const uint64_t tiles_y = (uint64_t) num_sms () * per * w / tiles_x;
+                        if (tiles_y < 1)
+                            continue;
+                        const uint64_t h = (L.n_rows + tiles_y - 1) / tiles_y;
+                        if (h >= 8 && h <= SMOL_MAGB_MAX_TILE_H && n_heights < 24)
+                            heights[n_heights++] = (uint32_t) h;
+                    }
+            }
+            for (uint32_t hi = 0; hi < n_heights; hi++)
+            {
+                const uint32_t h = heights[hi];
                 size_t sm;
                 if ((tune_tb >= 16 && (16u << c) != (uint32_t) tune_tb && c != c_max) || (tune_th > 0 && h != (uint32_t) tune_th))
                     continue;
