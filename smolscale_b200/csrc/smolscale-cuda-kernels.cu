@@ -4898,6 +4898,42 @@ launch_taps_h (const TapsParams &P, uint32_t vh, dim3 grid, dim3 block, cudaStre
     return launch_pdl (smol_taps_kernel<HH, 2>, P, grid, block, 0, stream);
 }
 
+/* Rows per thread of the strip kernels (taps0, taps0w).  Long strips reuse the two-row cache better
+ * (a strip of n output rows filters n * h_in / h_out + 1 source rows), but what decides among the
+ * reasonable lengths is how the resulting grid fills the GPU: CTAs / (SMs x resident CTAs) should be
+ * just under a whole number -- 1.46 waves run as long as 2, 0.73 leave a quarter of the SMs idle
+ * (4K 1:1, us per frame at 16 / 8 / 12 rows: 24.9 / 21.9 / 19.9). */
+static uint32_t
+pick_rows_per_thread (uint64_t x_threads, uint32_t bx, uint32_t n_rows, uint32_t n_images, double v, uint32_t per_sm)
+{
+    static const uint32_t cand[] = { 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 32 };
+    uint32_t best = 8;
+    double best_eff = -1.0;
+    const double slots = (double) num_sms () * (per_sm ? per_sm : 1);
+
+    for (uint32_t rpt : cand)
+    {
+        if (rpt > n_rows && rpt != cand[0])
+            break;
+        const uint32_t strips = (n_rows + rpt - 1) / rpt;
+        uint32_t by = 256 / bx;
+        if (by > strips)
+            by = strips;
+        const double ctas = (double) ((x_threads + bx - 1) / bx) * ((strips + by - 1) / by) * n_images;
+        const double waves = ctas / slots;
+        const double weff = waves <= 1.0 ? waves : waves / (double) (uint64_t) (waves + 0.999999);
+        /* emit one output row = 1, horizontally filter one source row = 1.5 */
+        const double work_eff = rpt * (1.0 + v * 1.5) / (rpt + (rpt * v + 1.0) * 1.5);
+        const double eff = weff * work_eff;
+        if (eff > best_eff * 1.01)
+        {
+            best_eff = eff;
+            best = rpt;
+        }
+    }
+    return best;
+}
+
 static cudaError_t
 launch_taps (const SmolLaunch &L, cudaStream_t stream)
 {
@@ -4919,12 +4955,20 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
     /* strip height: long strips amortise the two-row cache (essential on upscales) but leave
      * fewer threads; keep at least ~2 resident waves of threads on the GPU */
     const uint64_t x_threads = (d.w_out + 3) / 4;
-    const uint64_t want_threads = (uint64_t) num_sms () * 1536;
-    uint32_t rpt = 16;
-    while (rpt > 1 && x_threads * ((L.n_rows + rpt - 1) / rpt) * L.n_images < want_threads)
-        rpt >>= 1;
-    if (d.h_in <= d.h_out && rpt < 4)
-        rpt = 4;                        /* magnification: row reuse matters more than thread count */
+    uint32_t bx = 32;
+    while (bx < 128 && bx < x_threads)
+        bx *= 2;
+    uint32_t rpt;
+    if (d.h_halvings == 0 && d.v_halvings == 0)
+        rpt = pick_rows_per_thread (x_threads, bx, L.n_rows, L.n_images, (double) d.h_in / d.h_out, SMOL_TAPS0_MINBLOCKS);
+    else
+    {
+        /* (the runtime-format kernel with halvings: strips while they leave ~2 resident waves of threads) */
+        const uint64_t want_threads = (uint64_t) num_sms () * 1536;
+        rpt = 16;
+        while (rpt > 1 && x_threads * ((L.n_rows + rpt - 1) / rpt) * L.n_images < want_threads)
+            rpt >>= 1;
+    }
     {
         static int tune_rpt = -1;
         if (tune_rpt < 0)
@@ -4937,9 +4981,6 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
     }
     P.rows_per_thread = rpt;
 
-    uint32_t bx = 32;
-    while (bx < 128 && bx < x_threads)
-        bx *= 2;
     const uint32_t strips = (L.n_rows + rpt - 1) / rpt;
     uint32_t by = 256 / bx;
     if (by > strips)
@@ -5716,8 +5757,28 @@ launch_taps0w (const SmolLaunch &L, cudaStream_t stream)
     T.d = d;
     T.luts = L.luts;
 
+    const bool af = d.in_alpha_idx == 0;
+    const void *fn;
+#define TAPS0W(M, BI, BO, AF) ((const void *) smol_taps0w_kernel<M, BI, BO, AF>)
+#define TAPS0W_AF(M, BO) (af ? TAPS0W (M, 4, BO, true) : TAPS0W (M, 4, BO, false))
+    if (d.mid == SMOL_MID_P16)
+        fn = TAPS0W_AF (BM_P16_U, 4);
+    else if (d.mid == SMOL_MID_P16L)
+        fn = TAPS0W_AF (BM_P16L_U, 4);
+    else if (d.bpp_in == 3)
+        fn = d.bpp_out == 3 ? TAPS0W (BM_P8L_P, 3, 3, false) : TAPS0W (BM_P8L_P, 3, 4, false);
+    else if (d.in_unassoc)
+        fn = d.bpp_out == 3 ? TAPS0W_AF (BM_P8L_U, 3) : TAPS0W_AF (BM_P8L_U, 4);
+    else
+        fn = d.bpp_out == 3 ? TAPS0W_AF (BM_P8L_P, 3) : TAPS0W_AF (BM_P8L_P, 4);
+
     const uint32_t px = d.bpp_out == 3 ? 4 : 2;
     const uint64_t x_threads = (d.w_out + px - 1) / px;
+    uint32_t bx = 32;
+    while (bx < 128 && bx < x_threads)
+        bx *= 2;
+    /* strips while they leave ~2 resident waves of threads (the wave-fitting choice of the 64bpp strip
+     * kernel, pick_rows_per_thread, was measured here too: 4K 1:1 unassociated 31.8 -> 34.7 us) */
     const uint64_t want_threads = (uint64_t) num_sms () * 1536;
     uint32_t rpt = 16;
     while (rpt > 1 && x_threads * ((L.n_rows + rpt - 1) / rpt) * L.n_images < want_threads)
@@ -5735,9 +5796,6 @@ launch_taps0w (const SmolLaunch &L, cudaStream_t stream)
             rpt = (uint32_t) tune_rpt;
     }
     T.t.rows_per_thread = rpt;
-    uint32_t bx = 32;
-    while (bx < 128 && bx < x_threads)
-        bx *= 2;
     const uint32_t strips = (L.n_rows + rpt - 1) / rpt;
     uint32_t by = 256 / bx;
     if (by > strips)
@@ -5747,19 +5805,7 @@ launch_taps0w (const SmolLaunch &L, cudaStream_t stream)
     if (T.prefetch)
         T.prefetch = 0xffffffffu;       /* tables are staged first: see launch_half */
     T.row_ahead = 2;
-    const bool af = d.in_alpha_idx == 0;
-
-#define TAPS0W(M, BI, BO, AF) launch_pdl (smol_taps0w_kernel<M, BI, BO, AF>, T, grid, block, 0, stream)
-#define TAPS0W_AF(M, BO) (af ? TAPS0W (M, 4, BO, true) : TAPS0W (M, 4, BO, false))
-    if (d.mid == SMOL_MID_P16)
-        return TAPS0W_AF (BM_P16_U, 4);
-    if (d.mid == SMOL_MID_P16L)
-        return TAPS0W_AF (BM_P16L_U, 4);
-    if (d.bpp_in == 3)
-        return d.bpp_out == 3 ? TAPS0W (BM_P8L_P, 3, 3, false) : TAPS0W (BM_P8L_P, 3, 4, false);
-    if (d.in_unassoc)
-        return d.bpp_out == 3 ? TAPS0W_AF (BM_P8L_U, 3) : TAPS0W_AF (BM_P8L_U, 4);
-    return d.bpp_out == 3 ? TAPS0W_AF (BM_P8L_P, 3) : TAPS0W_AF (BM_P8L_P, 4);
+    return launch_pdl_ptr (fn, &T, grid, block, 0, stream);
 #undef TAPS0W_AF
 #undef TAPS0W
 }
