@@ -4023,7 +4023,10 @@ struct RowsLanes
         for (int i = 0; i < N; i++) r.v[i] = (p.v[i] >> n) & MASK;
         return r;
     }
-    static __device__ __forceinline__ P scale (const P &p, uint32_t mul, const RowsParams &R) { return box_scale<MODE> (p, mul, R.b.acc_fits_24 != 0); }
+    /* (always the wide form: with bilinear on one axis the lanes a box sums are not the 8- or 16-bit
+     * values box_params_init's "fits 24 bits" estimate assumes -- found by the soak: P16L lanes of
+     * 19 bits summed over a 33-row box) */
+    static __device__ __forceinline__ P scale (const P &p, uint32_t mul, const RowsParams &) { return box_scale<MODE> (p, mul, false); }
     static __device__ __forceinline__ P shfl_add (P p, uint32_t m)
     {
 #pragma unroll

@@ -68,6 +68,12 @@ REGRESSION_JOBS = [
     # which staged only half of the inverse-division table
     (cases.ABGR8_P, 62, 2, 256, cases.ARGB8_U, 31, 1, 128, 0, "saturated"),
     (cases.RGBA8_P, 16, 2, 64, cases.BGRA8_U, 8, 1, 32, 0, "alpha_edges"),
+    # found by tools/soak.py (round 2): bilinear across + box down on 19-bit (P16 linear) lanes overflowed the
+    # 24-bit shortcut of the box normalisation in the rows kernel
+    (cases.ARGB8_U, 8, 100, 32, cases.BGRA8_U, 1, 3, 16, 1, "saturated"),
+    (cases.RGBA8_U, 37, 100, 160, cases.ARGB8_U, 41, 3, 176, 1, "saturated"),
+    (cases.ABGR8_U, 300, 2000, 1200, cases.ABGR8_U, 200, 9, 800, 1, "saturated"),
+    (cases.ABGR8_U, 300, 2000, 1200, cases.RGBA8_U, 200, 9, 800, 0, "saturated"),
 ]
 
 
