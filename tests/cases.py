@@ -68,6 +68,12 @@ AXIS_PAIRS = [
     (100, 3), (300, 1), (520, 2), (1000, 111), (90, 10), (2048, 8), (2041, 8),
 ]
 
+# more ratio classes (the soak tool's list): long box spans next to mild bilinear ratios, so that random pairs
+# of them mix box and bilinear axes with large accumulations
+SOAK_AXIS_PAIRS = AXIS_PAIRS + [(640, 200), (641, 97), (333, 777), (1000, 3), (4000, 15), (12, 700), (255, 1), (256, 1),
+                                (257, 1), (2040, 8), (2041, 8), (96, 12), (100, 50), (77, 154), (200, 15), (255, 16),
+                                (1500, 100), (3000, 230), (1300, 87), (160, 640), (33, 1000)]
+
 BIG_AXIS_PAIRS = [(9000, 1), (16400, 2), (65535, 1), (65535, 65534), (65534, 65535), (1, 65535), (2, 65535)]
 
 

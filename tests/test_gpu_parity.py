@@ -61,6 +61,22 @@ def test_random_matrix_vs_oracle(sb, restatement, forced):
         sb.force_kernel(0)
 
 
+@pytest.mark.parametrize("forced", [0, 9], ids=["auto", "rows"])
+def test_random_matrix_mixed_axes(sb, restatement, forced):
+    """A second random matrix over the soak tool's ratio classes (long box spans on one axis, mild bilinear
+    ratios on the other, saturated images): the mixed filter pairs with large accumulations."""
+    sb.force_kernel(forced)
+    try:
+        for idx, job in enumerate(cases.job_matrix(977, 500, axis_pairs=cases.SOAK_AXIS_PAIRS, max_pixels=400000)):
+            ti, wi, hi, si, to, wo, ho, so, srgb, mode = job
+            src = cases.make_image(ti, wi, hi, si, mode, seed=idx)
+            want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
+            got = cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, srgb)
+            assert np.array_equal(got, want), (job, describe(got, want))
+    finally:
+        sb.force_kernel(0)
+
+
 REGRESSION_JOBS = [
     # found by tools/soak.py: dynamic + static shared memory just above the 48 KB default limit
     (cases.BGR8, 77, 37, 240, cases.RGBA8_U, 154, 41, 624, 0, "saturated"),
