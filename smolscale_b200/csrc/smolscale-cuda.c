@@ -19,6 +19,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#if defined (__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <cuda_runtime_api.h>
 
@@ -1150,6 +1153,48 @@ typedef struct
 }
 RowCopy;
 
+/* Bounce copies move tens of megabytes that the copying core never looks at again (the next
+ * reader is the DMA engine, or the caller much later), in tasks too small for memcpy's own
+ * non-temporal threshold: stream the stores past the cache so the destination lines are not read
+ * first (2 instead of 3 bytes of memory traffic per byte copied).  SMOL_CUDA_BOUNCE_NT=0: memcpy. */
+static int g_bounce_nt = 1;
+
+#if defined (__SSE2__)
+static void
+copy_streaming (char *dst, const char *src, size_t n)
+{
+    size_t head;
+
+    if (!g_bounce_nt || n < 1024)
+    {
+        memcpy (dst, src, n);
+        return;
+    }
+    head = (16 - ((uintptr_t) dst & 15)) & 15;
+    if (head)
+    {
+        memcpy (dst, src, head);
+        dst += head; src += head; n -= head;
+    }
+    for (; n >= 64; n -= 64, src += 64, dst += 64)
+    {
+        const __m128i a = _mm_loadu_si128 ((const __m128i *) src), b = _mm_loadu_si128 ((const __m128i *) (src + 16));
+        const __m128i c = _mm_loadu_si128 ((const __m128i *) (src + 32)), d = _mm_loadu_si128 ((const __m128i *) (src + 48));
+
+        _mm_stream_si128 ((__m128i *) dst, a);
+        _mm_stream_si128 ((__m128i *) (dst + 16), b);
+        _mm_stream_si128 ((__m128i *) (dst + 32), c);
+        _mm_stream_si128 ((__m128i *) (dst + 48), d);
+    }
+    if (n)
+        memcpy (dst, src, n);
+}
+#define copy_streaming_fence() _mm_sfence ()
+#else
+#define copy_streaming(dst, src, n) memcpy (dst, src, n)
+#define copy_streaming_fence() ((void) 0)
+#endif
+
 static void
 row_copy_task (void *arg)
 {
@@ -1157,10 +1202,11 @@ row_copy_task (void *arg)
     size_t r;
 
     if (c->dpitch == c->width_bytes && c->spitch == c->width_bytes)
-        memcpy (c->dst, c->src, c->width_bytes * c->n_rows);
+        copy_streaming (c->dst, c->src, c->width_bytes * c->n_rows);
     else
         for (r = 0; r < c->n_rows; r++)
-            memcpy (c->dst + r * c->dpitch, c->src + r * c->spitch, c->width_bytes);
+            copy_streaming (c->dst + r * c->dpitch, c->src + r * c->spitch, c->width_bytes);
+    copy_streaming_fence ();
 }
 
 static long
@@ -1188,6 +1234,7 @@ bounce_config (void)
         g_bounce_band = 65536;
     if (g_bounce_task < 16384)
         g_bounce_task = 16384;
+    g_bounce_nt = env_long ("SMOL_CUDA_BOUNCE_NT", 1) != 0;
     __atomic_store_n (&g_bounce, env_long ("SMOL_CUDA_BOUNCE", 1) != 0, __ATOMIC_RELEASE);
 }
 
