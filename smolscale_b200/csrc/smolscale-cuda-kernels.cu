@@ -2206,9 +2206,10 @@ smol_magb_kernel (const MagbParams M)
      * upper row is this run's lower row, so the two register sets swap roles from run to run
      * (X on top, then Y on top) and only one row is fetched and expanded per run.
      * FULL: the column's 16 bytes all lie inside the row (everything but a ragged last column). */
-    auto stage3 = [&] (auto full_tag)
+    auto stage3 = [&] (auto full_tag, auto a16_tag)
     {
         constexpr bool FULL = decltype (full_tag)::value;
+        constexpr bool A16 = decltype (a16_tag)::value;     /* destination rows on 16-byte boundaries (else: 4-byte) */
         uint32_t X[8], Y[8], hx = 0xffffffffu, hy = 0xffffffffu;
         auto fetch_row = [&] (uint32_t (&R)[8], uint32_t r)
         {
@@ -2238,8 +2239,14 @@ smol_magb_kernel (const MagbParams M)
                     for (int j = 0; j < 4; j++)
                         o[j] = __byte_perm (half_unpremul<AF> (o[j], sm_inv), 0, P.prmt_sel);
                 }
-                if constexpr (FULL)
+                if constexpr (FULL && A16)
                     *reinterpret_cast<uint4 *> (out) = make_uint4 (o[0], o[1], o[2], o[3]);
+                else if constexpr (FULL)
+                {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        reinterpret_cast<uint32_t *> (out)[k] = o[k];
+                }
                 else
                 {
 #pragma unroll
@@ -2271,10 +2278,12 @@ smol_magb_kernel (const MagbParams M)
             }
         }
     };
-    if (n_valid == 16)
-        stage3 (std::true_type {});
+    if (n_valid != 16)
+        stage3 (std::false_type {}, std::false_type {});
+    else if (((reinterpret_cast<uintptr_t> (dst_img) | P.dst_pitch) & 15) == 0)
+        stage3 (std::true_type {}, std::true_type {});
     else
-        stage3 (std::false_type {});
+        stage3 (std::true_type {}, std::false_type {});
 }
 
 /* ------------------------------------------------------------------------------------------ *
@@ -4420,7 +4429,8 @@ mag_eligible (const SmolLaunch &L)
 static bool
 magb_eligible (const SmolLaunch &L)
 {
-    /* byte-granular vertical stage with 16-byte stores; SMOL_MAGB_ALL=1 (measurements) sends every
+    /* byte-granular vertical stage with 16-byte stores (four 4-byte stores when the destination rows
+     * sit on word boundaries only); SMOL_MAGB_ALL=1 (measurements) sends every
      * bilinear job without halvings here, not just vertical magnifications */
     static int all = -1;
     if (all < 0)
@@ -4429,7 +4439,7 @@ magb_eligible (const SmolLaunch &L)
         all = e ? atoi (e) : 0;
     }
     const bool shape_ok = all ? (taps_eligible (L) && L.d.h_halvings == 0 && L.d.v_halvings == 0) : mag_eligible (L);
-    return shape_ok && aligned16 (L.dst) && (L.dst_pitch & 15) == 0 && (L.dst_image_stride & 15) == 0;
+    return shape_ok && aligned4 (L.dst) && (L.dst_pitch & 3) == 0 && (L.dst_image_stride & 3) == 0;
 }
 
 static bool

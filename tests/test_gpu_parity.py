@@ -202,6 +202,35 @@ def test_magb_kernel_family(sb, restatement):
     assert sb.kernel_launches()["magb"] == 1
 
 
+def test_magb_word_aligned_destinations(sb, restatement):
+    """The byte-granular kernel on destination rows that sit on 4-byte but not 16-byte boundaries (a
+    sub-rectangle of a larger RGB canvas, or a padded pitch): four word stores per column instead of
+    one 16-byte store; padding and the bytes around the image stay untouched."""
+    import torch
+    rng = np.random.default_rng(21)
+    for wi, hi, wo, ho in [(64, 48, 256, 192), (37, 21, 141, 57), (100, 7, 260, 29), (1024, 40, 4096, 161), (3, 2, 11, 9)]:
+        for ti, to in [(cases.RGB8, cases.BGR8), (cases.BGR8, cases.RGB8), (cases.RGBA8_P, cases.RGB8), (cases.RGB8, cases.BGRA8_P)]:
+            si = wi * cases.bpp(ti)
+            so = (wo * cases.bpp(to) + 3) // 4 * 4 + 4 * int(rng.integers(0, 4))
+            off = 4 * int(rng.integers(0, 4))
+            src = cases.make_image(ti, wi, hi, si, "random", seed=wo)
+            want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, 0)
+            d_in = torch.from_numpy(src).cuda()
+            d_out = torch.full((want.size + 32,), 0xCD, dtype=torch.uint8, device="cuda")
+            sb.reset_stats()
+            sb.force_kernel(8)
+            try:
+                sb.scale_simple(d_in, ti, wi, hi, si, d_out.data_ptr() + off, to, wo, ho, so, 0)
+            finally:
+                sb.force_kernel(0)
+            torch.cuda.synchronize()
+            assert sb.kernel_launches()["magb"] == 1, sb.kernel_launches()
+            got = d_out.cpu().numpy()
+            body = got[off:off + want.size]
+            assert np.array_equal(body, want), ((ti, wi, hi, si, to, wo, ho, so, off), describe(body, want))
+            assert (got[:off] == 0xCD).all() and (got[off + want.size:] == 0xCD).all(), (ti, wo, so, off)
+
+
 def test_unaligned_host_pointers(sb, restatement):
     """Odd base addresses and odd pitches on both sides (verify.c uses pitch 3 and 4)."""
     for off_in, off_out, ti, to in [(1, 3, cases.RGBA8_P, cases.ARGB8_U), (2, 1, cases.RGB8, cases.BGR8),
