@@ -1762,6 +1762,212 @@ smol_tapsn_kernel (const Taps0Params T, uint32_t vh)
     }
 }
 
+#ifndef SMOL_TAPS11_MINBLOCKS
+#define SMOL_TAPS11_MINBLOCKS 4
+#endif
+/* Bilinear with ONE halving on both axes (reference BILINEAR_1H x BILINEAR_1H: every reduction
+ * between 2:1 and 4:1 that is not exactly 2:1 -- 4K -> 720p, 1080p -> 480p ...; the commonest
+ * non-trivial downscale), 8-bit premultiplied intermediate.  smol_tapsn_kernel with everything it
+ * decides at run time resolved: a thread owns one output column and a STRIP of output rows, reads
+ * the column's two horizontal taps as a four-pixel window at constant offsets from one row pointer
+ * and walks the strip with straight-line code -- an output pixel is the mean of two vertical
+ * samples, each a tap between two horizontally filtered rows; which of those rows coincide (the
+ * second sample usually starts on the first one's lower row, the next pixel often on this one's last
+ * row) depends on the row only, so every branch is uniform across the CTA.  Less than half of the
+ * general kernel's instructions per output pixel. */
+template <int BI, int BO, bool IU, bool OU, bool AF>
+__global__ void __launch_bounds__ (256, SMOL_TAPS11_MINBLOCKS)
+smol_taps11_kernel (const Taps0Params T)
+{
+    __shared__ uint32_t sm_inv[OU ? 256 : 1];
+    const TapsParams &P = T.t;
+
+    pdl_launch_dependents ();
+    if constexpr (OU)
+    {
+        for (uint32_t i = threadIdx.y * blockDim.x + threadIdx.x; i < 256; i += blockDim.x * blockDim.y)
+            sm_inv[i] = __ldg (&P.inv_div_p8[i]) << 3;
+        __syncthreads ();
+    }
+
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t yl0 = (blockIdx.y * blockDim.y + threadIdx.y) * P.rows_per_thread;
+    if (x >= P.w_out || yl0 >= P.n_rows)
+        return;
+    const uint32_t yl1 = min (yl0 + P.rows_per_thread, P.n_rows);
+    const uint32_t *ty = P.tab_y + ((P.first_row + yl0) << 1);
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
+    const uint32_t h_last = P.h_in - 1, pitch = P.src_pitch;
+
+    const uint32_t e0 = __ldg (&P.tab_x[2 * x]), e1 = __ldg (&P.tab_x[2 * x + 1]);
+    const uint32_t F0 = SMOL_TAB_F (e0), G0 = 256u - F0, F1 = SMOL_TAB_F (e1), G1 = 256u - F1;
+    /* The two taps read pixels p0, p0 + 1 and p1, p1 + 1 with p1 = p0 + 1 or p0 + 2 (the samples are
+     * ratio / 2 = 1 .. 2 pixels apart): a window of four pixels at constant offsets from ONE row
+     * pointer, the second tap's pair picked by two selects.  Columns whose window would cross the
+     * row's end (the last one or two) address every pixel on its own. */
+    const uint32_t p0 = SMOL_TAB_OFS (e0), p1 = SMOL_TAB_OFS (e1);
+    const bool near = p1 == p0 + 1, window = (near || p1 == p0 + 2) && p0 + 3 < P.w_in;
+    const uint8_t *col = src + (size_t) p0 * BI;
+    const uint32_t oq0 = (min (p0 + 1, P.w_in - 1) - p0) * BI, op1 = (p1 - p0) * BI, oq1 = (min (p1 + 1, P.w_in - 1) - p0) * BI;
+
+    if (in_first_wave (T.prefetch) && (threadIdx.x & 3) == 0)
+    {
+        /* the source rows of the strip's first output pixel (four lanes share a prefetch) */
+        const uint32_t ra = SMOL_TAB_OFS (__ldg (&ty[0])), rb = min (SMOL_TAB_OFS (__ldg (&ty[1])) + 1, h_last);
+#pragma unroll 1
+        for (uint32_t r = ra; r <= rb; r++)
+            prefetch_l2 (col + (size_t) r * pitch);
+    }
+    pdl_wait ();
+
+    auto load_raw = [&] (const uint8_t *p) -> uint32_t
+    {
+        if constexpr (BI == 4)
+            return __ldg (reinterpret_cast<const uint32_t *> (p));
+        else
+            return (uint32_t) __ldg (p) | ((uint32_t) __ldg (p + 1) << 8) | ((uint32_t) __ldg (p + 2) << 16) | 0xff000000u;
+    };
+    auto unpack = [&] (uint32_t raw) -> Px16
+    {
+        Px16 r;
+        r.a = raw & 0x00ff00ffu;
+        r.b = __byte_perm (raw, 0, 0x4341);
+        if constexpr (IU)
+        {
+            /* premultiply: ((c + 1) * (alpha + 1) - 1) >> 8, alpha lane untouched (generic:238-244) */
+            if constexpr (AF)
+            {
+                const uint32_t alpha = raw & 0xff, m = alpha + 1;
+                r.a = (((((r.a & 0x00ff0000u) + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff0000u) | alpha;
+                r.b = (((r.b + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff00ffu;
+            }
+            else
+            {
+                const uint32_t alpha = raw >> 24, m = alpha + 1;
+                r.a = (((r.a + 0x00010001u) * m - 0x00010001u) >> 8) & 0x00ff00ffu;
+                r.b = (((((r.b & 0x000000ffu) + 0x00010001u) * m - 0x00010001u) >> 8) & 0x000000ffu) | (alpha << 16);
+            }
+        }
+        return r;
+    };
+    uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl0 * P.dst_pitch + (size_t) x * BO;
+
+    /* WINDOW resolved at compile time: the body exists twice, the few boundary columns take the second copy */
+    auto strip = [&] (auto window_tag)
+    {
+    constexpr bool WINDOW = decltype (window_tag)::value;
+    /* A source row at this column: its four raw pixels (load_row), then the mean of the two taps
+     * (hfilter).  Split so that ALL rows of an output pixel are requested before the first one is
+     * used: one memory round trip per output pixel instead of one per row -- the kernel is bound by
+     * load latency, not by issue slots. */
+    struct Raw4 { uint32_t w[4]; };
+    auto load_row = [&] (uint32_t r) -> Raw4
+    {
+        const uint8_t *row = col + (size_t) r * pitch;
+        Raw4 v;
+        v.w[0] = load_raw (row);
+        if constexpr (WINDOW)
+        {
+            v.w[1] = load_raw (row + BI);
+            v.w[2] = load_raw (row + 2 * BI);
+            v.w[3] = load_raw (row + 3 * BI);       /* (only used when the taps are two pixels apart; a neighbouring lane reads it anyway) */
+        }
+        else
+        {
+            v.w[1] = load_raw (row + oq0);
+            v.w[2] = load_raw (row + op1);
+            v.w[3] = load_raw (row + oq1);
+        }
+        return v;
+    };
+    auto hfilter = [&] (const Raw4 &v) -> Px16
+    {
+        const uint32_t w2 = WINDOW && near ? v.w[1] : v.w[2], w3 = WINDOW && near ? v.w[2] : v.w[3];
+        const Px16 a0 = unpack (v.w[0]), b0 = unpack (v.w[1]), a1 = unpack (w2), b1 = unpack (w3);
+        Px16 h;
+        h.a = ((__byte_perm (a0.a * F0 + b0.a * G0, 0, 0x4341) + __byte_perm (a1.a * F1 + b1.a * G1, 0, 0x4341)) >> 1) & 0x00ff00ffu;
+        h.b = ((__byte_perm (a0.b * F0 + b0.b * G0, 0, 0x4341) + __byte_perm (a1.b * F1 + b1.b * G1, 0, 0x4341)) >> 1) & 0x00ff00ffu;
+        return h;
+    };
+
+    Px16 last;                      /* the most recently filtered source row: often the next pixel's first */
+    uint32_t last_idx = 0xffffffffu;
+    last.a = last.b = 0;
+
+    uint32_t ea = __ldg (&ty[0]), eb = __ldg (&ty[1]);
+#pragma unroll 1
+    for (uint32_t yl = yl0; yl < yl1; yl++, ty += 2, dst += P.dst_pitch)
+    {
+        const uint32_t a0 = SMOL_TAB_OFS (ea), a1 = min (a0 + 1, h_last), Fa = SMOL_TAB_F (ea), Ga = 256u - Fa;
+        const uint32_t b0 = SMOL_TAB_OFS (eb), b1 = min (b0 + 1, h_last), Fb = SMOL_TAB_F (eb), Gb = 256u - Fb;
+
+        if (yl + 1 < yl1)
+        {
+            /* the next pixel's rows on their way while this one is computed */
+            ea = __ldg (&ty[2]);
+            eb = __ldg (&ty[3]);
+            if (T.row_ahead && (threadIdx.x & 3) == 0)
+            {
+                /* at most three rows are new: b1 + 1 .. the next second sample's lower row */
+                const uint32_t nb = min (SMOL_TAB_OFS (eb) + 1, h_last), n0 = max (SMOL_TAB_OFS (ea), b1 + 1);
+                const uint8_t *pr = col + (size_t) n0 * pitch;
+                if (n0 <= nb)
+                    prefetch_l2 (pr);
+                if (n0 + 1 <= nb)
+                    prefetch_l2 (pr + pitch);
+                if (n0 + 2 <= nb)
+                    prefetch_l2 (pr + 2 * (size_t) pitch);
+            }
+        }
+
+        /* rows a0, a1 for the first sample, b0, b1 for the second; usually b0 == a1, and a0 is often
+         * the previous pixel's b1.  All of this depends on the row only: uniform branches. */
+        const bool have_a0 = a0 == last_idx, chained = b0 == a1;
+        Raw4 ra, rb, rc, rd;
+        if (!have_a0)
+            ra = load_row (a0);
+        rb = load_row (a1);
+        rc = load_row (chained ? b1 : b0);
+        if (!chained)
+            rd = load_row (b1);
+
+        Px16 X, Y, Z, W;
+        if (have_a0) X = last; else X = hfilter (ra);
+        Y = hfilter (rb);
+        if (chained)
+        {
+            Z = Y;
+            W = hfilter (rc);
+        }
+        else
+        {
+            Z = hfilter (rc);
+            W = hfilter (rd);
+        }
+        last = W;
+        last_idx = b1;
+
+        const uint32_t acc_a = __byte_perm (X.a * Fa + Y.a * Ga, 0, 0x4341) + __byte_perm (Z.a * Fb + W.a * Gb, 0, 0x4341);
+        const uint32_t acc_b = __byte_perm (X.b * Fa + Y.b * Ga, 0, 0x4341) + __byte_perm (Z.b * Fb + W.b * Gb, 0, 0x4341);
+        uint32_t v = __byte_perm (acc_a >> 1, acc_b >> 1, 0x6240);             /* source byte order */
+        if constexpr (OU)
+            v = half_unpremul<AF> (v, sm_inv);
+        v = __byte_perm (v, 0, P.prmt_sel);
+
+        if constexpr (BO == 4)
+            *reinterpret_cast<uint32_t *> (dst) = v;
+        else
+        {
+            dst[0] = (uint8_t) v; dst[1] = (uint8_t) (v >> 8); dst[2] = (uint8_t) (v >> 16);
+        }
+    }
+    };
+    if (window)
+        strip (std::true_type {});
+    else
+        strip (std::false_type {});
+}
+
 /* ------------------------------------------------------------------------------------------ *
  * "mag" kernel: vertical magnification (h_out > h_in; BASELINE config 4), bilinear / copy / one *
  * horizontally, 8-bit premultiplied intermediate.                                              *
@@ -5129,6 +5335,58 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
             dim3 ngrid ((d.w_out + nbx - 1) / nbx, (nstrips + nby - 1) / nby, L.n_images);
             const bool af = d.in_alpha_idx == 0;
             const uint32_t hh = d.h_halvings, vh = d.v_halvings;
+            static int taps11_on = -1, taps11_rpt = 0, taps11_ahead = 1;
+            if (taps11_on < 0)
+            {
+                const char *e = getenv ("SMOL_TAPS11"), *r = getenv ("SMOL_TAPS11_RPT"), *a = getenv ("SMOL_TAPS11_AHEAD");
+                taps11_rpt = r ? atoi (r) : 0;
+                taps11_ahead = a ? atoi (a) : 1;
+                taps11_on = e ? atoi (e) : 1;
+            }
+            if (hh == 1 && vh == 1 && taps11_on)
+            {
+                /* one halving on both axes: the straight-line strip kernel.  Strip length: longer
+                 * strips amortise the per-thread set-up and reuse the last filtered row, but the grid
+                 * must keep about two waves of CTAs or load latency shows (measured, 4K -> 720p, us per
+                 * frame at 1 / 2 / 3 / 5 / 7 rows: 12.4 / 10.9 / 10.9 / 11.6 / 12.7; 4K -> 900p 5 rows
+                 * 14.3, 2 rows 15.6): the longest strip of up to 6 rows that leaves 1.9 waves. */
+                uint32_t best_r = 1;
+                const double slots = (double) num_sms () * SMOL_TAPS11_MINBLOCKS;
+                for (uint32_t r = 2; r <= 6 && r <= L.n_rows; r++)
+                {
+                    const uint32_t strips = (L.n_rows + r - 1) / r;
+                    const uint32_t by = 256 / nbx < strips ? 256 / nbx : strips;
+                    const double ctas = (double) ((d.w_out + nbx - 1) / nbx) * ((strips + by - 1) / by) * L.n_images;
+                    if (ctas >= 1.9 * slots)
+                        best_r = r;
+                }
+                if (taps11_rpt > 0)
+                    best_r = (uint32_t) taps11_rpt;
+                T.t.rows_per_thread = best_r;
+                T.row_ahead = (uint32_t) taps11_ahead;
+                const uint32_t strips = (L.n_rows + best_r - 1) / best_r;
+                const uint32_t by = 256 / nbx < strips ? 256 / nbx : strips;
+                const dim3 block11 (nbx, by), grid11 ((d.w_out + nbx - 1) / nbx, (strips + by - 1) / by, L.n_images);
+#define TAPS11(BI, BO, IU, OU, AF) launch_pdl (smol_taps11_kernel<BI, BO, IU, OU, AF>, T, grid11, block11, 0, stream)
+                if (d.bpp_in == 3)
+                {
+                    if (d.bpp_out == 3)     return TAPS11 (3, 3, false, false, false);
+                    if (d.out_unassoc)      return TAPS11 (3, 4, false, true, false);
+                    return TAPS11 (3, 4, false, false, false);
+                }
+                if (d.in_unassoc)
+                {
+                    if (d.bpp_out == 3)
+                        return af ? TAPS11 (4, 3, true, false, true) : TAPS11 (4, 3, true, false, false);
+                    return af ? TAPS11 (4, 4, true, false, true) : TAPS11 (4, 4, true, false, false);
+                }
+                if (d.bpp_out == 3)
+                    return TAPS11 (4, 3, false, false, false);
+                if (d.out_unassoc)
+                    return af ? TAPS11 (4, 4, false, true, true) : TAPS11 (4, 4, false, true, false);
+                return TAPS11 (4, 4, false, false, false);
+#undef TAPS11
+            }
 #define TAPSN(BI, BO, IU, OU, AF) (hh == 0 ? launch_pdl_args (smol_tapsn_kernel<BI, BO, IU, OU, AF, 0>, ngrid, nblock, 0, stream, T, vh) \
                                    : hh == 1 ? launch_pdl_args (smol_tapsn_kernel<BI, BO, IU, OU, AF, 1>, ngrid, nblock, 0, stream, T, vh) \
                                              : launch_pdl_args (smol_tapsn_kernel<BI, BO, IU, OU, AF, 2>, ngrid, nblock, 0, stream, T, vh))

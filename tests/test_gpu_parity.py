@@ -202,6 +202,52 @@ def test_magb_kernel_family(sb, restatement):
     assert sb.kernel_launches()["magb"] == 1
 
 
+TAPS11_GEOMETRIES = [(100, 100, 33, 33), (1280, 90, 427, 30), (37, 29, 13, 11), (640, 480, 213, 160), (9, 9, 3, 4), (255, 7, 100, 3),
+                     (5, 5, 2, 2), (7, 300, 3, 101), (4000, 21, 1001, 9), (131, 67, 64, 17), (3840, 2160, 1280, 720), (2560, 1440, 1000, 563)]
+
+
+def test_one_halving_strip_kernel(sb, restatement):
+    """Reductions between 2:1 and 4:1 on both axes (one halving each: the straight-line strip kernel
+    inside the taps_direct family): every source type x random destination types, widths whose last
+    columns clamp at the row's end, device buffers with word-aligned padded pitches, row bands that
+    start and end inside a strip; the two large jobs make the launcher pick strips of several rows."""
+    import torch
+    rng = np.random.default_rng(31)
+    sb.reset_stats()
+    n = 0
+    for gi, (wi, hi, wo, ho) in enumerate(TAPS11_GEOMETRIES):
+        big = wi * hi > 1000000
+        for ti in (cases.ALL_TYPES if not big else [cases.BGRA8_P, cases.RGBA8_U, cases.RGB8]):
+            to = cases.ALL_TYPES[int(rng.integers(len(cases.ALL_TYPES)))]
+            if 4 <= ti <= 7 and 4 <= to <= 7:
+                to = cases.RGBA8_P                                  # (unassociated -> unassociated takes the 128bpp intermediate)
+            si = (wi * cases.bpp(ti) + 3) // 4 * 4 + 4 * int(rng.integers(0, 3))
+            so = (wo * cases.bpp(to) + 3) // 4 * 4 + 4 * int(rng.integers(0, 3))
+            src = cases.make_image(ti, wi, hi, si, "random", seed=gi)
+            want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, 0)
+            d_in = torch.from_numpy(src).cuda()
+            d_out = torch.full((want.size + 16,), 0xCD, dtype=torch.uint8, device="cuda")
+            sb.scale_simple(d_in.data_ptr(), ti, wi, hi, si, d_out.data_ptr(), to, wo, ho, so, 0)
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy()
+            assert np.array_equal(got[:want.size], want), ((ti, wi, hi, si, to, wo, ho, so), describe(got[:want.size], want))
+            assert (got[want.size:] == 0xCD).all()
+            n += 1
+            # a row band through the batch API
+            y0 = int(rng.integers(0, ho))
+            nr = int(rng.integers(1, ho - y0 + 1))
+            d_out.fill_(0xCD)
+            ctx = sb.ScaleCtx(d_in.data_ptr(), ti, wi, hi, si, None, to, wo, ho, so, 0)
+            ctx.batch_full(d_out.data_ptr(), y0, nr)
+            ctx.destroy()
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy()
+            m = so * (nr - 1) + wo * cases.bpp(to)
+            assert np.array_equal(got[:m], want[y0 * so: y0 * so + m]), (ti, to, wi, hi, wo, ho, y0, nr)
+            n += 1
+    assert sb.kernel_launches()["taps_direct"] == n, sb.kernel_launches()
+
+
 def test_magb_word_aligned_destinations(sb, restatement):
     """The byte-granular kernel on destination rows that sit on 4-byte but not 16-byte boundaries (a
     sub-rectangle of a larger RGB canvas, or a padded pitch): four word stores per column instead of
