@@ -5343,7 +5343,7 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
                 taps11_ahead = a ? atoi (a) : 1;
                 taps11_on = e ? atoi (e) : 1;
             }
-            if (hh == 1 && vh == 1 && taps11_on)
+            if (hh == 1 && vh == 1 && taps11_on && d.bpp_in == 4)     /* (24bpp sources, three byte loads per pixel: measured slower than the general kernel) */
             {
                 /* one halving on both axes: the straight-line strip kernel.  Strip length: longer
                  * strips amortise the per-thread set-up and reuse the last filtered row, but the grid
@@ -5368,12 +5368,6 @@ launch_taps (const SmolLaunch &L, cudaStream_t stream)
                 const uint32_t by = 256 / nbx < strips ? 256 / nbx : strips;
                 const dim3 block11 (nbx, by), grid11 ((d.w_out + nbx - 1) / nbx, (strips + by - 1) / by, L.n_images);
 #define TAPS11(BI, BO, IU, OU, AF) launch_pdl (smol_taps11_kernel<BI, BO, IU, OU, AF>, T, grid11, block11, 0, stream)
-                if (d.bpp_in == 3)
-                {
-                    if (d.bpp_out == 3)     return TAPS11 (3, 3, false, false, false);
-                    if (d.out_unassoc)      return TAPS11 (3, 4, false, true, false);
-                    return TAPS11 (3, 4, false, false, false);
-                }
                 if (d.in_unassoc)
                 {
                     if (d.bpp_out == 3)
