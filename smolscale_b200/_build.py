@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libsmolscale_cuda.so")
+PNG_LIB_PATH = os.path.join(HERE, "libsmolpng.so")
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -69,6 +70,25 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+def build_png(force=False):
+    """libsmolpng.so: the PNG file I/O either side of the path (include/smol-png.h).  Plain C over
+    zlib, no CUDA; kept out of libsmolscale_cuda.so so that library's dependencies do not grow."""
+    srcs = [os.path.join(CSRC, "smol-png.c"), os.path.join(INCLUDE, "smol-png.h")]
+    if not force and os.path.exists(PNG_LIB_PATH) and \
+            all(os.path.getmtime(s) <= os.path.getmtime(PNG_LIB_PATH) for s in srcs):
+        return PNG_LIB_PATH
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-g", "-Wall", "-Wextra", "-fPIC", "-fvisibility=hidden", "-shared",
+           "-I", INCLUDE, "-o", PNG_LIB_PATH, srcs[0], "-lz"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        print(" ".join(cmd))
+        print(r.stdout)
+        print(r.stderr)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+    return PNG_LIB_PATH
+
+
 if __name__ == "__main__":
     import sys
     print(build(force=True, verbose="-v" in sys.argv))
+    print(build_png(force=True))
