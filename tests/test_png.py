@@ -26,7 +26,7 @@ def png():
     return mod
 
 
-def _rng_image(w, h, seed, opaque_rows=True):
+def _rng_image(w, h, seed):
     rng = np.random.default_rng(seed)
     # smooth gradients + noise, so the filter heuristic picks different filters on different rows
     y, x = np.mgrid[0:h, 0:w]
