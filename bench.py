@@ -284,7 +284,7 @@ def cpu_baseline_sample(cfg, src, budget_s=12.0):
             h.scale_threaded(src[n % n_src], ti, wi, hi, wi * bpp(ti), out, to, wo, ho, wo * bpp(to), srgb, cores, 1)
             n += 1
             el = time.perf_counter() - t0
-            if el * cores > budget_s or n >= 400:
+            if el * cores > budget_s or n >= 4000:      # ~12 s of CPU work (core-seconds), bounded
                 break
         h.close()
         return {"value": round(n * wo * ho / 1e6 / el, 2), "unit": "Mpix/s", "cores": cores, "kind": "reference",
