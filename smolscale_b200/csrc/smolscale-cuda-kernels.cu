@@ -3591,8 +3591,15 @@ pack128_fast (const uint32_t lane[4], const SmolJobDesc &d, const SmolDeviceLuts
  * shared memory as 32 lane-private copies so the gathers are conflict-free.                       *
  * ------------------------------------------------------------------------------------------ */
 
-template <int MODE, int BI>
-__global__ void __launch_bounds__ (1024, 1)
+/* Two instances.  A job with enough items to fill every SM's 32 warps is issue-bound: 32 warps of 64
+ * registers.  A smaller job is bound by each thread's chain of dependent loads: 16 warps of 128
+ * registers, which lets a thread request every source pixel of up to four taps in two rows (16 loads)
+ * before it unpacks the first (B200, 256x256 -> 32x32 linear light 23.6 -> 12.5 us with two taps per
+ * batch at 80 registers; 4K -> 720p 34.5 -> 30.5 us with the 64-register instance). */
+#define SMOL_TAPS128_WARPS(SMALL) ((SMALL) ? 16 : 32)
+
+template <int MODE, int BI, bool SMALL>
+__global__ void __launch_bounds__ (SMOL_TAPS128_WARPS (SMALL) * 32, 1)
 smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u32_ok, uint32_t rows_per_item)
 {
     extern __shared__ __align__ (16) uint8_t sm_dyn[];
@@ -3652,7 +3659,7 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
     const uint32_t *tx = P.tab_x + (x << hh);
     const uint8_t *src = P.src + (size_t) tz * P.src_image_stride;
 
-    auto fetch = [&] (const uint8_t *row, uint32_t j) -> BoxPx<MODE>
+    auto load_raw = [&] (const uint8_t *row, uint32_t j) -> uint32_t
     {
         const uint8_t *p = row + (size_t) j * BI;
         uint32_t raw;
@@ -3663,6 +3670,11 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
             raw = (uint32_t) __ldg (p) | ((uint32_t) __ldg (p + 1) << 8) | ((uint32_t) __ldg (p + 2) << 16);
             raw |= BI == 4 ? ((uint32_t) __ldg (p + 3) << 24) : 0xff000000u;
         }
+        return raw;
+    };
+
+    auto unpack = [&] (uint32_t raw) -> BoxPx<MODE>
+    {
         if constexpr (NEED_FROM)
         {
             BoxPx<MODE> r;
@@ -3675,26 +3687,63 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
             return box_unpack<MODE, 0> (raw, P, nullptr, nullptr, nullptr);
     };
 
-    auto hval = [&] (uint32_t r) -> BoxPx<MODE>
+    /* Horizontally filtered pixel of NR source rows at once.  A thread walks its output pixel's
+     * taps alone, so what bounds a small job is the length of its dependent load chain, not the
+     * arithmetic: the table entries of a batch of taps are requested together, then every source
+     * pixel the batch needs in all NR rows (HB taps x 2 pixels x NR rows), and only then does the
+     * unpack chain start. */
+    constexpr int HB = SMALL ? 4 : 2;
+    auto hrows = [&] (auto nr_c, const uint32_t *rs, BoxPx<MODE> *out)
     {
-        const uint8_t *row = src + (size_t) r * P.src_pitch;
-        BoxPx<MODE> acc;
+        constexpr int NR = decltype (nr_c)::value;
+        const uint8_t *row[NR];
 #pragma unroll
-        for (int i = 0; i < 4; i++) acc.v[i] = 0;
-#pragma unroll 1
-        for (uint32_t k = 0; k < n_h; k++)
+        for (int j = 0; j < NR; j++)
         {
-            const uint32_t e = __ldg (&tx[k]);
-            const uint32_t ofs = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e), G = 256u - F;
-            const BoxPx<MODE> p = fetch (row, ofs);
-            const BoxPx<MODE> q = fetch (row, min (ofs + 1, d.w_in - 1));
+            row[j] = src + (size_t) rs[j] * P.src_pitch;
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                acc.v[i] += ((p.v[i] * F + q.v[i] * G) >> 8) & 0x00ffffffu;
+            for (int i = 0; i < 4; i++) out[j].v[i] = 0;
+        }
+#pragma unroll 1
+        for (uint32_t k0 = 0; k0 < n_h; k0 += HB)
+        {
+            uint32_t e[HB], rp[NR][HB], rq[NR][HB];
+#pragma unroll
+            for (int b = 0; b < HB; b++)
+                e[b] = __ldg (&tx[min (k0 + b, n_h - 1)]);
+#pragma unroll
+            for (int b = 0; b < HB; b++)
+            {
+                const uint32_t ofs = SMOL_TAB_OFS (e[b]), ofs1 = min (ofs + 1, d.w_in - 1);
+#pragma unroll
+                for (int j = 0; j < NR; j++)
+                {
+                    rp[j][b] = load_raw (row[j], ofs);
+                    rq[j][b] = load_raw (row[j], ofs1);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < HB; b++)
+            {
+                if (k0 + b < n_h)
+                {
+                    const uint32_t F = SMOL_TAB_F (e[b]), G = 256u - F;
+#pragma unroll
+                    for (int j = 0; j < NR; j++)
+                    {
+                        const BoxPx<MODE> p = unpack (rp[j][b]);
+                        const BoxPx<MODE> q = unpack (rq[j][b]);
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            out[j].v[i] += ((p.v[i] * F + q.v[i] * G) >> 8) & 0x00ffffffu;
+                    }
+                }
+            }
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) acc.v[i] = (acc.v[i] >> hh) & 0x00ffffffu;
-        return acc;
+        for (int j = 0; j < NR; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) out[j].v[i] = (out[j].v[i] >> hh) & 0x00ffffffu;
     };
 
     uint32_t idx0 = 0xffffffffu, idx1 = 0xffffffffu;
@@ -3709,14 +3758,22 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
     BoxPx<MODE> acc;
 #pragma unroll
     for (int i = 0; i < 4; i++) acc.v[i] = 0;
+    /* the row's vertical taps (at most four) in one go, off the dependent chain of the loop below */
+    uint32_t ey[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        ey[k] = __ldg (&ty[min ((uint32_t) k, n_v - 1)]);
 
 #pragma unroll 1
     for (uint32_t kv = 0; kv < n_v; kv++)
     {
-        const uint32_t e = __ldg (&ty[kv]);
+        const uint32_t e = kv == 0 ? ey[0] : kv == 1 ? ey[1] : kv == 2 ? ey[2] : ey[3];
         const uint32_t r0 = SMOL_TAB_OFS (e), F = SMOL_TAB_F (e), G = 256u - F;
         const uint32_t r1 = min (r0 + 1, d.h_in - 1);
+        bool new0 = false;
 
+        /* the reference's two-row cache (generic:1648-1682); which rows are new is the same for
+         * the whole warp (one output row per item) */
         if (r0 != idx0)
         {
             if (r0 == idx1)
@@ -3725,14 +3782,22 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
                 idx1 = idx0;
             }
             else
-                c0 = hval (r0);
+                new0 = true;
             idx0 = r0;
         }
-        if (r1 != idx1)
+        const bool new1 = r1 != idx1;
+        idx1 = r1;
+        if (new0 && new1)
         {
-            c1 = hval (r1);
-            idx1 = r1;
+            const uint32_t rs[2] = { r0, r1 };
+            BoxPx<MODE> o[2];
+            hrows (std::integral_constant<int, 2> (), rs, o);
+            c0 = o[0]; c1 = o[1];
         }
+        else if (new0)
+            hrows (std::integral_constant<int, 1> (), &r0, &c0);
+        else if (new1)
+            hrows (std::integral_constant<int, 1> (), &r1, &c1);
 #pragma unroll
         for (int i = 0; i < 4; i++)
             acc.v[i] += ((c0.v[i] * F + c1.v[i] * G) >> 8) & 0x00ffffffu;
@@ -6111,27 +6176,32 @@ launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
     size_t bytes;
     /* dynamic shared memory: up to the end of the tables' fixed window addresses (see box3_accum) */
     const size_t one_tab = 0x20000 - 0x400, two_tabs = 0x30000 - 0x400;
-    if (d.mid == SMOL_MID_P8L && d.in_unassoc)      { variant = 0; fn = (const void *) smol_taps128_kernel<BM_P8L_U, 4>; bytes = one_tab; }
-    else if (d.mid == SMOL_MID_P8L && d.bpp_in == 3) { variant = 1; fn = (const void *) smol_taps128_kernel<BM_P8L_P, 3>; bytes = one_tab; }
-    else if (d.mid == SMOL_MID_P8L)                 { variant = 2; fn = (const void *) smol_taps128_kernel<BM_P8L_P, 4>; bytes = two_tabs; }
-    else if (d.mid == SMOL_MID_P16)                 { variant = 3; fn = (const void *) smol_taps128_kernel<BM_P16_U, 4>; bytes = 0; }
-    else                                            { variant = 4; fn = (const void *) smol_taps128_kernel<BM_P16L_U, 4>; bytes = one_tab; }
+    /* small: one round of items at 16 warps per SM covers the job (see the kernel) */
+    const bool small = n_items <= (uint64_t) num_sms () * SMOL_TAPS128_WARPS (true);
+    const uint32_t w_max = SMOL_TAPS128_WARPS (small);
+#define T128_FN(M, B) (small ? (const void *) smol_taps128_kernel<M, B, true> : (const void *) smol_taps128_kernel<M, B, false>)
+    if (d.mid == SMOL_MID_P8L && d.in_unassoc)      { variant = 0; fn = T128_FN (BM_P8L_U, 4); bytes = one_tab; }
+    else if (d.mid == SMOL_MID_P8L && d.bpp_in == 3) { variant = 1; fn = T128_FN (BM_P8L_P, 3); bytes = one_tab; }
+    else if (d.mid == SMOL_MID_P8L)                 { variant = 2; fn = T128_FN (BM_P8L_P, 4); bytes = two_tabs; }
+    else if (d.mid == SMOL_MID_P16)                 { variant = 3; fn = T128_FN (BM_P16_U, 4); bytes = 0; }
+    else                                            { variant = 4; fn = T128_FN (BM_P16L_U, 4); bytes = one_tab; }
+#undef T128_FN
 
-    /* resident CTAs per SM by device, variant and warps per CTA (0: not asked yet) */
-    static int occ_cache[SMOL_KERNELS_MAX_DEVICES][5][33];
-    const int dev = current_device ();
-    uint32_t best_w = 32, best_occ = 1;
+    /* resident CTAs per SM by device, instance and warps per CTA (0: not asked yet) */
+    static int occ_cache[SMOL_KERNELS_MAX_DEVICES][10][33];
+    const int dev = current_device (), inst = variant * 2 + (small ? 1 : 0);
+    uint32_t best_w = w_max, best_occ = 1;
     smem_optin (fn, 200 * 1024);
     {
         double best_eff = 0.0;
-        for (uint32_t w = 32; w >= 20; w--)
+        for (uint32_t w = w_max; w >= w_max * 5 / 8; w--)
         {
-            int occ = __atomic_load_n (&occ_cache[dev][variant][w], __ATOMIC_RELAXED);
+            int occ = __atomic_load_n (&occ_cache[dev][inst][w], __ATOMIC_RELAXED);
             if (occ == 0)
             {
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, fn, (int) w * 32, bytes) != cudaSuccess || occ < 1)
                     occ = 1;
-                __atomic_store_n (&occ_cache[dev][variant][w], occ, __ATOMIC_RELAXED);
+                __atomic_store_n (&occ_cache[dev][inst][w], occ, __ATOMIC_RELAXED);
             }
             const uint64_t slots = (uint64_t) num_sms () * occ * w;
             const uint64_t rounds = (n_items + slots - 1) / slots;
@@ -6148,7 +6218,8 @@ launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
     const uint64_t ctas = (n_items + best_w - 1) / best_w, resident = (uint64_t) num_sms () * best_occ;
     dim3 block (best_w * 32), grid ((unsigned) (ctas < resident ? ctas : resident));
 
-#define T128(M, B) launch_pdl_args (smol_taps128_kernel<M, B>, grid, block, bytes, stream, P, hh, vh, src_u32_ok, rpi)
+#define T128(M, B) (small ? launch_pdl_args (smol_taps128_kernel<M, B, true>, grid, block, bytes, stream, P, hh, vh, src_u32_ok, rpi) \
+                          : launch_pdl_args (smol_taps128_kernel<M, B, false>, grid, block, bytes, stream, P, hh, vh, src_u32_ok, rpi))
     switch (variant)
     {
         case 0:  return T128 (BM_P8L_U, 4);
