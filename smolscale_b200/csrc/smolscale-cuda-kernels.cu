@@ -3646,10 +3646,26 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
     const uint32_t items_per_image = items_x * strips;
     const uint32_t n_items = items_per_image * P.n_images;
     const uint32_t warps = nthr >> 5;
+    /* item -> (image, strip, column tile) by multiply-high with a reciprocal computed once per thread
+     * (floor (2^32 / d) gives a quotient at most one too small: one correction step) */
+    const uint32_t rcp_x = items_x == 1 ? 0xffffffffu : (uint32_t) (0x100000000ull / items_x);
+    const uint32_t rcp_img = items_per_image == 1 ? 0xffffffffu : (uint32_t) (0x100000000ull / items_per_image);
+    auto div_by = [] (uint32_t t, uint32_t dv, uint32_t rcp) -> uint32_t
+    {
+        uint32_t q = __umulhi (t, rcp);
+        if (t - q * dv >= dv)
+            q++;
+        return q;
+    };
+    /* 32bpp source pixels as one word or as four bytes: decided once, outside the item loop (inside, the
+     * compiler turned the choice into predicated code and every pixel paid for both forms) */
+    auto walk = [&] (auto u32_tag)
+    {
+    constexpr bool U32 = decltype (u32_tag)::value;
     for (uint32_t item = blockIdx.x * warps + (tid >> 5); item < n_items; item += gridDim.x * warps)
     {
-    const uint32_t tz = item / items_per_image, trem = item - tz * items_per_image;
-    const uint32_t strip = trem / items_x;
+    const uint32_t tz = P.n_images == 1 ? 0u : div_by (item, items_per_image, rcp_img), trem = item - tz * items_per_image;
+    const uint32_t strip = div_by (trem, items_x, rcp_x);
     const uint32_t yl0 = strip * rows_per_item, yl1 = min (yl0 + rows_per_item, P.n_rows);
     const uint32_t x = (trem - strip * items_x) * 32 + (tid & 31);
     if (x >= d.w_out)
@@ -3663,7 +3679,7 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
     {
         const uint8_t *p = row + (size_t) j * BI;
         uint32_t raw;
-        if (BI == 4 && src_u32_ok)
+        if constexpr (U32)
             raw = __ldg (reinterpret_cast<const uint32_t *> (p));
         else
         {
@@ -3811,6 +3827,16 @@ smol_taps128_kernel (const BoxParams P, uint32_t hh, uint32_t vh, uint32_t src_u
     store_raw_px (o8, packed, d.bpp_out);
     }
     }
+    };
+    if constexpr (BI == 4)
+    {
+        if (src_u32_ok)
+            walk (std::true_type {});
+        else
+            walk (std::false_type {});
+    }
+    else
+        walk (std::false_type {});
 }
 
 /* ------------------------------------------------------------------------------------------ *
@@ -6164,9 +6190,20 @@ launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
         const char *e = getenv ("SMOL_TAPS128_RPI");
         tune_rpi = e ? atoi (e) : 0;
     }
-    /* rows per item: with halvings the row cache rarely carries over (one row); without, strips */
-    const uint32_t rpi = tune_rpi > 0 ? (uint32_t) tune_rpi
-                         : (hh == 0 && vh == 0 ? ((uint64_t) d.h_in * 4 < (uint64_t) d.h_out * 5 ? 8u : 4u) : 1u);
+    /* rows per item: with vertical halvings the row cache rarely carries over (one row); without, strips
+     * share half of every output row's source rows with the row above (4K -> 1279x2160 linear light
+     * 52.7 -> 43.7 us) -- as long as the strips still make at least two rounds of items for every warp
+     * slot of the GPU (a small job is bound by the length of each warp's chain, and strips lengthen it) */
+    uint32_t rpi = 1;
+    if (vh == 0)
+    {
+        rpi = (uint64_t) d.h_in * 4 < (uint64_t) d.h_out * 5 ? 8u : 4u;
+        while (rpi > 1 && (uint64_t) ((d.w_out + 31) / 32) * ((L.n_rows + rpi - 1) / rpi) * L.n_images
+                          < 2 * (uint64_t) num_sms () * SMOL_TAPS128_WARPS (false))
+            rpi /= 2;
+    }
+    if (tune_rpi > 0)
+        rpi = (uint32_t) tune_rpi;
     const uint64_t n_items = (uint64_t) ((d.w_out + 31) / 32) * ((L.n_rows + rpi - 1) / rpi) * L.n_images;
     if (n_items > 0x7fffffffull)
         return cudaErrorInvalidValue;
