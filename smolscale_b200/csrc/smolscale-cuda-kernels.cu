@@ -3597,6 +3597,11 @@ pack128_fast (const uint32_t lane[4], const SmolJobDesc &d, const SmolDeviceLuts
  * before it unpacks the first (B200, 256x256 -> 32x32 linear light 23.6 -> 12.5 us with two taps per
  * batch at 80 registers; 4K -> 720p 34.5 -> 30.5 us with the 64-register instance). */
 #define SMOL_TAPS128_WARPS(SMALL) ((SMALL) ? 16 : 32)
+/* output pixels of a call up to which the tile kernel (smol_tile128h_kernel) takes over: measured 2.5x
+ * faster at 1,024 pixels, 10 % slower at 19,200 */
+#ifndef SMOL_TILE128H_MAX_PIXELS
+#define SMOL_TILE128H_MAX_PIXELS 4096ull
+#endif
 
 template <int MODE, int BI, bool SMALL>
 __global__ void __launch_bounds__ (SMOL_TAPS128_WARPS (SMALL) * 32, 1)
@@ -4233,6 +4238,219 @@ smol_tile128_kernel (const Tile128Params M)
             e = sm_ty[min (ry, th - 1)];
         }
         while (ry < ry_end && SMOL_TAB_OFS (e) == ofs);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ *
+ * "tile128h" kernel: bilinear WITH halvings on either axis (2:1 < ratio <= 8:1) on a 128bpp       *
+ * intermediate, for TINY jobs (icons: 256x256 -> 32x32 in linear light) -- the tile kernel's       *
+ * three phases with 2^h taps per output pixel.  taps128 gives every output pixel to one thread,     *
+ * which walks all its taps alone: with a few hundred output pixels that is a few warps, each        *
+ * working through 64 source pixels one dependent chain after the other (11 us).  Here a 512-thread  *
+ * CTA owns a tile of output pixels and spreads the tile's whole source window over its threads:    *
+ *   1a. the window is loaded (coalesced, eight pixels in flight per thread) and unpacked ONCE      *
+ *       per source pixel;                                                                          *
+ *   1b. per (source row, output column): the 2^hh horizontal taps, summed and halved;              *
+ *   2.  per output pixel: the 2^vh vertical taps between filtered rows, halved, repacked.          *
+ * Same lane arithmetic as taps128 (bit-identical results; 60-job sweep with SMOL_TILE128H=1).      *
+ * 256x256 -> 32x32 linear light: 11.0 -> 4.4 us.  Measured and REJECTED for larger jobs: a tile's   *
+ * life is a chain of dependent latencies (tables, window bounds, window, three barriers) that two   *
+ * or three resident CTAs per SM do not hide -- 4K -> 720p 62 us against taps128's 29, and neither   *
+ * more loads in flight nor larger tiles changed that (profiles/r02_tile128h_sweep.json).           *
+ * Reported as kernel family "taps128".                                                             *
+ * ------------------------------------------------------------------------------------------ */
+
+struct Tile128hParams
+{
+    BoxParams b;
+    uint32_t hh, vh;
+    uint32_t tile_w, tile_h;            /* output tile */
+    uint32_t u_pitch, max_src_rows;     /* bound of the tile's source window (pixels, rows) */
+    uint32_t src_u32_ok;
+};
+
+template <int MODE, int BI, int BO>
+__global__ void __launch_bounds__ (512)
+smol_tile128h_kernel (const Tile128hParams M)
+{
+    extern __shared__ __align__ (16) uint8_t sm_dyn[];
+    __shared__ uint32_t sm_ty[128];
+    __shared__ uint32_t sm_inv8[256];
+    __shared__ uint32_t sm_from[256];
+    __shared__ uint8_t sm_to_srgb[2048];
+    constexpr bool NEED_INV = MODE == BM_P8L_P;
+    constexpr bool NEED_FROM = MODE == BM_P8L_P || MODE == BM_P8L_U || MODE == BM_P16L_U;
+    const BoxParams &P = M.b;
+    const SmolJobDesc &d = P.d;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t hh = M.hh, vh = M.vh, n_h = 1u << hh, n_v = 1u << vh;
+
+    pdl_launch_dependents ();
+    if (tid < 256)
+    {
+        if constexpr (NEED_FROM)
+            sm_from[tid] = P.luts->from_srgb[tid];
+        if constexpr (NEED_INV)
+            sm_inv8[tid] = P.luts->inv_div_p8[tid] << 3;
+    }
+    if constexpr (MODE != BM_P16_U)
+        reinterpret_cast<uint32_t *> (sm_to_srgb)[tid] = reinterpret_cast<const uint32_t *> (P.luts->to_srgb)[tid];
+
+    const uint32_t x0 = blockIdx.x * M.tile_w;
+    const uint32_t x1 = min (x0 + M.tile_w, d.w_out);
+    const uint32_t yl0 = blockIdx.y * M.tile_h;
+    const uint32_t yl1 = min (yl0 + M.tile_h, P.n_rows);
+    const uint32_t tw = x1 - x0, th = yl1 - yl0;
+    const uint32_t *ty = P.tab_y + ((P.first_row + yl0) << vh);
+
+    /* table offsets never decrease along an axis: the first and the last tap bound the window */
+    const uint32_t c_lo = SMOL_TAB_OFS (__ldg (&P.tab_x[x0 << hh]));
+    const uint32_t c_hi = min (SMOL_TAB_OFS (__ldg (&P.tab_x[(x1 << hh) - 1])) + 1, d.w_in - 1);
+    const uint32_t r_lo = SMOL_TAB_OFS (__ldg (&ty[0]));
+    const uint32_t r_hi = min (SMOL_TAB_OFS (__ldg (&ty[(th << vh) - 1])) + 1, d.h_in - 1);
+    const uint32_t n_cols = c_hi - c_lo + 1, n_rows = r_hi - r_lo + 1;
+    if (n_cols > M.u_pitch || n_rows > M.max_src_rows)
+        __trap ();                      /* the host's window bound is wrong: never corrupt memory quietly */
+    for (uint32_t i = tid; i < (th << vh); i += 512)
+        sm_ty[i] = __ldg (&ty[i]);
+
+    uint4 *sm_u = reinterpret_cast<uint4 *> (sm_dyn);
+    uint4 *sm_h = sm_u + (size_t) M.max_src_rows * M.u_pitch;
+
+    const uint8_t *src = P.src + (size_t) blockIdx.z * P.src_image_stride;
+    __syncthreads ();
+    pdl_wait ();
+
+    /* phase 1a: (row, column) pairs of the window flattened over the CTA's threads */
+    {
+        const uint32_t total = n_rows * n_cols;
+        const uint32_t rcp = n_cols == 1 ? 0xffffffffu : (uint32_t) (0x100000000ull / n_cols);
+        const uint8_t *win = src + (size_t) r_lo * P.src_pitch + (size_t) c_lo * BI;
+        auto fill = [&] (auto u32_tag)
+        {
+            constexpr bool U32 = decltype (u32_tag)::value;
+            /* NB source pixels per thread requested before the first is unpacked: with one or two loads in
+             * flight per thread the phase ran at the latency of a load, not at the rate of the memory system */
+            constexpr int NB = 8;
+            for (uint32_t i0 = tid; i0 < total; i0 += 512 * NB)
+            {
+                uint32_t raw[NB], at[NB];
+#pragma unroll
+                for (int b = 0; b < NB; b++)
+                {
+                    const uint32_t i = min (i0 + (uint32_t) b * 512, total - 1);
+                    uint32_t r = __umulhi (i, rcp);
+                    if (i - r * n_cols >= n_cols)
+                        r++;
+                    const uint32_t c = i - r * n_cols;
+                    const uint8_t *p = win + (size_t) r * P.src_pitch + c * BI;
+                    at[b] = r * M.u_pitch + c;
+                    if constexpr (U32)
+                        raw[b] = __ldg (reinterpret_cast<const uint32_t *> (p));
+                    else
+                    {
+                        raw[b] = (uint32_t) __ldg (p) | ((uint32_t) __ldg (p + 1) << 8) | ((uint32_t) __ldg (p + 2) << 16);
+                        raw[b] |= BI == 4 ? ((uint32_t) __ldg (p + 3) << 24) : 0xff000000u;
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < NB; b++)
+                {
+                    if (i0 + (uint32_t) b * 512 < total)
+                    {
+                        const BoxPx<MODE> u = box_unpack<MODE, 0> (raw[b], P, sm_inv8, sm_from, nullptr);
+                        sm_u[at[b]] = make_uint4 (u.v[0], u.v[1], u.v[2], u.v[3]);
+                    }
+                }
+            }
+        };
+        if constexpr (BI == 4)
+        {
+            if (M.src_u32_ok)
+                fill (std::true_type {});
+            else
+                fill (std::false_type {});
+        }
+        else
+            fill (std::false_type {});
+    }
+    __syncthreads ();
+
+    /* tile_w is a power of two: full tiles split the thread index with shifts */
+    const bool full = tw == M.tile_w;
+    const uint32_t n_runs = 512 / tw;
+    const uint32_t run = full ? tid / M.tile_w : tid / tw;
+    const uint32_t xl = tid - run * tw;
+
+    /* phase 1b */
+    if (run < n_runs)
+    {
+        uint32_t op[4], oq[4], F[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const uint32_t e = __ldg (&P.tab_x[((x0 + xl) << hh) + min ((uint32_t) k, n_h - 1)]);
+            op[k] = SMOL_TAB_OFS (e) - c_lo;
+            oq[k] = min (SMOL_TAB_OFS (e) + 1, d.w_in - 1) - c_lo;
+            F[k] = SMOL_TAB_F (e);
+        }
+        for (uint32_t r = run; r < n_rows; r += n_runs)
+        {
+            const uint4 *urow = sm_u + r * M.u_pitch;
+            uint4 h = make_uint4 (0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                if ((uint32_t) k < n_h)
+                {
+                    const uint4 p = urow[op[k]], q = urow[oq[k]];
+                    const uint32_t G = 256u - F[k];
+                    h.x += ((p.x * F[k] + q.x * G) >> 8) & 0x00ffffffu;
+                    h.y += ((p.y * F[k] + q.y * G) >> 8) & 0x00ffffffu;
+                    h.z += ((p.z * F[k] + q.z * G) >> 8) & 0x00ffffffu;
+                    h.w += ((p.w * F[k] + q.w * G) >> 8) & 0x00ffffffu;
+                }
+            }
+            h.x = (h.x >> hh) & 0x00ffffffu; h.y = (h.y >> hh) & 0x00ffffffu;
+            h.z = (h.z >> hh) & 0x00ffffffu; h.w = (h.w >> hh) & 0x00ffffffu;
+            sm_h[r * M.tile_w + xl] = h;
+        }
+    }
+    __syncthreads ();
+
+    /* phase 2 */
+    if (run >= n_runs)
+        return;
+    const uint4 *hcol = sm_h + xl;
+    uint8_t *dst = P.dst + (size_t) blockIdx.z * P.dst_image_stride + (size_t) yl0 * P.dst_pitch + (size_t) (x0 + xl) * BO;
+    for (uint32_t ry = run; ry < th; ry += n_runs)
+    {
+        uint32_t acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+        for (int kv = 0; kv < 4; kv++)
+        {
+            if ((uint32_t) kv < n_v)
+            {
+                const uint32_t e = sm_ty[(ry << vh) + kv];
+                const uint32_t ofs = SMOL_TAB_OFS (e), Fv = SMOL_TAB_F (e), Gv = 256u - Fv;
+                const uint4 t = hcol[(ofs - r_lo) * M.tile_w], b = hcol[(min (ofs + 1, d.h_in - 1) - r_lo) * M.tile_w];
+                acc[0] += ((t.x * Fv + b.x * Gv) >> 8) & 0x00ffffffu;
+                acc[1] += ((t.y * Fv + b.y * Gv) >> 8) & 0x00ffffffu;
+                acc[2] += ((t.z * Fv + b.z * Gv) >> 8) & 0x00ffffffu;
+                acc[3] += ((t.w * Fv + b.w * Gv) >> 8) & 0x00ffffffu;
+            }
+        }
+        uint32_t fin[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) fin[i] = (acc[i] >> vh) & 0x00ffffffu;
+        const uint32_t v = pack128_fast<MODE> (fin, d, P.luts, sm_to_srgb);
+        uint8_t *o = dst + (size_t) ry * P.dst_pitch;
+        if constexpr (BO == 4)
+            *reinterpret_cast<uint32_t *> (o) = v;
+        else
+        {
+            o[0] = (uint8_t) v; o[1] = (uint8_t) (v >> 8); o[2] = (uint8_t) (v >> 16);
+        }
     }
 }
 
@@ -6168,6 +6386,84 @@ launch_taps0w (const SmolLaunch &L, cudaStream_t stream)
 
 static void box_params_init (BoxParams &P, const SmolLaunch &L);
 
+/* The tile kernel for 128bpp bilinear with halvings takes the tiny jobs (see the kernel); cudaErrorNotSupported =
+ * not this kernel's job.  SMOL_TILE128H=0 never, 1 whenever possible (measurements, tests). */
+static cudaError_t
+launch_tile128h (const SmolLaunch &L, cudaStream_t stream)
+{
+    const SmolJobDesc &d = L.d;
+    static int mode = -1, tune_kb = 72;
+    if (mode < 0)
+    {
+        const char *e = getenv ("SMOL_TILE128H"), *k = getenv ("SMOL_TILE128H_KB");
+        tune_kb = k && atoi (k) > 0 ? atoi (k) : 72;
+        mode = e ? atoi (e) : 2;
+    }
+    if (mode == 0 || (d.h_halvings == 0 && d.v_halvings == 0))
+        return cudaErrorNotSupported;
+    if (d.bpp_out == 4 && !((reinterpret_cast<uintptr_t> (L.dst) & 3) == 0 && (L.dst_pitch & 3) == 0 && (L.dst_image_stride & 3) == 0))
+        return cudaErrorNotSupported;
+    if (mode == 2 && (uint64_t) d.w_out * L.n_rows * L.n_images > SMOL_TILE128H_MAX_PIXELS)
+        return cudaErrorNotSupported;
+
+    Tile128hParams M;
+    box_params_init (M.b, L);
+    M.hh = d.h_halvings;
+    M.vh = d.v_halvings;
+    M.src_u32_ok = d.bpp_in == 3 || ((reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0
+                                     && (L.src_image_stride & 3) == 0);
+    /* Tile shape: the cheapest in unpacks (window pixels per output pixel, the halo is paid again by the
+     * neighbours) plus horizontal taps (window rows per output row), among the shapes whose window fits
+     * 72 KB and whose vertical table fits sm_ty. */
+    double best = 1e300;
+    size_t smem = 0;
+    M.tile_w = 0;
+    for (uint32_t tw = 64; tw >= 8; tw /= 2)
+        for (uint32_t th = 32; th >= 1; th /= 2)
+        {
+            if ((th << M.vh) > 128)
+                continue;
+            uint64_t cols = ((uint64_t) tw * d.w_in + d.w_out - 1) / d.w_out + 5;     /* + 4 is reached (brute force over the planner) */
+            uint64_t rows = ((uint64_t) th * d.h_in + d.h_out - 1) / d.h_out + 5;
+            cols = cols < d.w_in ? cols : d.w_in;
+            rows = rows < d.h_in ? rows : d.h_in;
+            const size_t bytes = (size_t) rows * (cols + tw) * 16;
+            if (bytes > (size_t) tune_kb * 1024)
+                continue;
+            const uint32_t etw = tw < d.w_out ? tw : d.w_out, eth = th < L.n_rows ? th : L.n_rows;
+            const double cost = (double) rows * cols / ((double) etw * eth) * 34.0 + (double) rows / eth * (6.0 + 13.0 * (1 << M.hh))
+                                + 512.0 / ((double) etw * eth) * 4.0;
+            if (cost < best)
+            {
+                best = cost;
+                M.tile_w = tw; M.tile_h = th;
+                M.u_pitch = (uint32_t) cols; M.max_src_rows = (uint32_t) rows;
+                smem = bytes;
+            }
+        }
+    if (M.tile_w == 0)
+        return cudaErrorNotSupported;
+    const uint32_t tiles_y = (L.n_rows + M.tile_h - 1) / M.tile_h;
+    if (tiles_y > 65535 || L.n_images > 65535)
+        return cudaErrorNotSupported;
+    dim3 grid ((d.w_out + M.tile_w - 1) / M.tile_w, tiles_y, L.n_images);
+
+#define TILE128H_BO(MD, B, O) (smem_optin ((const void *) smol_tile128h_kernel<MD, B, O>, 100 * 1024), \
+                               launch_pdl (smol_tile128h_kernel<MD, B, O>, M, grid, dim3 (512), smem, stream))
+#define TILE128H(MD, B) (d.bpp_out == 3 ? TILE128H_BO (MD, B, 3) : TILE128H_BO (MD, B, 4))
+    if (d.mid == SMOL_MID_P8L)
+    {
+        if (d.in_unassoc)
+            return TILE128H (BM_P8L_U, 4);
+        return d.bpp_in == 3 ? TILE128H (BM_P8L_P, 3) : TILE128H (BM_P8L_P, 4);
+    }
+    if (d.mid == SMOL_MID_P16)
+        return TILE128H (BM_P16_U, 4);
+    return TILE128H (BM_P16L_U, 4);
+#undef TILE128H
+#undef TILE128H_BO
+}
+
 static cudaError_t
 launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
 {
@@ -6176,6 +6472,11 @@ launch_taps128 (const SmolLaunch &L, cudaStream_t stream)
 
     if (taps0w_eligible (L))
         return launch_taps0w (L, stream);
+    {
+        const cudaError_t e = launch_tile128h (L, stream);
+        if (e != cudaErrorNotSupported)
+            return e;
+    }
 
     box_params_init (P, L);
     const uint32_t src_u32_ok = d.bpp_in == 3 || ((reinterpret_cast<uintptr_t> (L.src) & 3) == 0 && (L.src_pitch & 3) == 0

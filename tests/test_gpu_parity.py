@@ -633,3 +633,87 @@ def test_rgb_destination_at_any_alignment(sb, restatement):
             body = got[off:off + want.size]
             assert np.array_equal(body, want), ((ti, wi, hi, si, to, wo, ho, so, srgb, off), describe(body, want))
             assert (got[:off] == 0xCD).all() and (got[off + want.size:] == 0xCD).all(), (ti, wo, so, off)
+
+
+TAPS128_GEOMETRIES = [(256, 256, 32, 32), (100, 100, 33, 33), (37, 29, 13, 11), (9, 9, 3, 4), (5, 5, 2, 2), (640, 480, 160, 120),
+                      (255, 7, 100, 3), (7, 300, 3, 101), (300, 40, 300, 11), (40, 300, 11, 300), (131, 67, 17, 64),
+                      (1920, 1080, 640, 360), (3840, 2160, 1279, 2160), (2048, 64, 256, 200), (1024, 768, 128, 96)]
+
+
+def _taps128_family_jobs():
+    """128bpp bilinear with a halving on an axis: linear light for every source type, and
+    unassociated -> unassociated without it; padded pitches; 24bpp ends of rows."""
+    rng = np.random.default_rng(77)
+    for gi, (wi, hi, wo, ho) in enumerate(TAPS128_GEOMETRIES):
+        big = wi * hi > 500000
+        for ti in (cases.ALL_TYPES if not big else [cases.BGRA8_P, cases.ARGB8_U, cases.RGB8]):
+            for srgb in (1, 0):
+                if srgb:
+                    to = cases.ALL_TYPES[int(rng.integers(len(cases.ALL_TYPES)))]
+                elif 4 <= ti <= 7:
+                    to = 4 + int(rng.integers(4))
+                else:
+                    continue
+                si = wi * cases.bpp(ti) + (0 if rng.integers(2) else 4 * int(rng.integers(1, 3)))
+                so = wo * cases.bpp(to) + (0 if rng.integers(2) else 4 * int(rng.integers(1, 3)))
+                yield gi, ti, wi, hi, si, to, wo, ho, so, srgb
+
+
+def test_taps128_family(sb, restatement):
+    """Both instances of the one-thread-per-pixel kernel (16 warps x 128 registers for jobs one round of
+    items covers, 32 x 64 otherwise), strips when the vertical axis has no halvings, the tile kernel on
+    the tiny jobs, and a row band through the batch API."""
+    import torch
+    rng = np.random.default_rng(5)
+    sb.reset_stats()
+    n = 0
+    for gi, ti, wi, hi, si, to, wo, ho, so, srgb in _taps128_family_jobs():
+        src = cases.make_image(ti, wi, hi, si, "premul" if ti < 4 else "random", seed=gi)
+        want = restatement.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
+        d_in = torch.from_numpy(src).cuda()
+        d_out = torch.full((want.size + 16,), 0xCD, dtype=torch.uint8, device="cuda")
+        sb.scale_simple(d_in.data_ptr(), ti, wi, hi, si, d_out.data_ptr(), to, wo, ho, so, srgb)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        assert np.array_equal(got[:want.size], want), ((ti, wi, hi, si, to, wo, ho, so, srgb), describe(got[:want.size], want))
+        assert (got[want.size:] == 0xCD).all()
+        n += 1
+        y0 = int(rng.integers(0, ho))
+        nr = int(rng.integers(1, ho - y0 + 1))
+        d_out.fill_(0xCD)
+        ctx = sb.ScaleCtx(d_in.data_ptr(), ti, wi, hi, si, None, to, wo, ho, so, srgb)
+        ctx.batch_full(d_out.data_ptr(), y0, nr)
+        ctx.destroy()
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        m = so * (nr - 1) + wo * cases.bpp(to)
+        assert np.array_equal(got[:m], want[y0 * so: y0 * so + m]), (ti, to, wi, hi, wo, ho, y0, nr, srgb)
+        assert (got[m:] == 0xCD).all()
+        n += 1
+    assert sb.kernel_launches()["taps128"] == n, sb.kernel_launches()
+
+
+def test_tile128h_kernel_forced():
+    """SMOL_TILE128H=1 (read once per process, hence the child process) sends every eligible job of the
+    family through the tile kernel, which the dispatcher itself only uses for tiny jobs."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, os
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import cases, oracle, test_gpu_parity as T
+import smolscale_b200 as sb
+chk = oracle.restatement()
+n = 0
+for gi, ti, wi, hi, si, to, wo, ho, so, srgb in T._taps128_family_jobs():
+    src = cases.make_image(ti, wi, hi, si, "premul" if ti < 4 else "random", seed=gi)
+    want = chk.scale_simple(src, ti, wi, hi, si, to, wo, ho, so, srgb)
+    got = T.cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, srgb)
+    assert np.array_equal(got, want), ((ti, wi, hi, si, to, wo, ho, so, srgb), T.describe(got, want))
+    n += 1
+print("ok", n)
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SMOL_TILE128H="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.stdout[-2000:], r.stderr[-4000:])
