@@ -29,6 +29,18 @@ for (wi, hi, wo, ho) in [(129, 33, 131, 35), (64, 48, 127, 96), (200, 100, 133, 
     for ti, to, srgb in [(cases.RGBA8_U, cases.ARGB8_U, 0), (cases.BGRA8_U, cases.BGRA8_U, 1), (cases.RGBA8_P, cases.RGB8, 1),
                          (cases.RGB8, cases.BGR8, 1), (cases.RGBA8_P, cases.RGB8, 0), (cases.RGB8, cases.RGB8, 0)]:
         jobs.append((ti, wi, hi, wi * cases.bpp(ti), to, wo, ho, wo * cases.bpp(to) + (1 if cases.bpp(to) == 3 else 0), srgb, "random"))
+# 128bpp bilinear with halvings (taps128's two instances, strips, the tile kernel on tiny jobs; SMOL_TILE128H=1 in the
+# environment sends all of them through the tile kernel): tight and padded pitches, 24bpp row ends
+t128 = []
+for (wi, hi, wo, ho) in [(256, 256, 32, 32), (100, 100, 33, 33), (37, 29, 13, 11), (9, 9, 3, 4), (5, 5, 2, 2), (255, 7, 100, 3),
+                         (7, 300, 3, 101), (300, 40, 300, 11), (40, 300, 11, 300), (640, 480, 160, 120), (700, 500, 233, 499)]:
+    for ti, to, srgb, extra in [(cases.RGBA8_P, cases.BGRA8_U, 1, 0), (cases.ARGB8_U, cases.ARGB8_P, 1, 4), (cases.RGB8, cases.BGR8, 1, 0),
+                                (cases.RGB8, cases.RGBA8_P, 1, 1), (cases.BGRA8_U, cases.RGBA8_U, 0, 8), (cases.ABGR8_P, cases.RGB8, 1, 0)]:
+        t128.append((ti, wi, hi, wi * cases.bpp(ti) + extra, to, wo, ho, wo * cases.bpp(to) + (extra if cases.bpp(to) == 4 else 0), srgb,
+                     "premul" if ti < 4 else "random"))
+jobs += t128
+if len(sys.argv) > 2 and sys.argv[2] == "taps128":
+    jobs = t128
 for idx, job in enumerate(jobs):
     ti, wi, hi, si, to, wo, ho, so, srgb, mode = job
     src = cases.make_image(ti, wi, hi, si, mode, seed=idx)
