@@ -6264,6 +6264,30 @@ launch_box (const SmolLaunch &L, cudaStream_t stream)
                         }
                     }
                 }
+                /* A job of fewer items than one round of warp slots: as few warps per CTA as still give
+                 * every item a warp, so that the CTAs spread over ALL the SMs instead of filling some
+                 * of them (1,950 items at 17 warps per CTA occupy 115 of 148 SMs; at 14 all of them,
+                 * with fewer warps competing for each SM's issue slots).  Table modes only: measured on
+                 * B200, linear light 400^2 -> 16^2 25.4 -> 21.0 us, 4000x3000 -> 200x150 33.8 -> 30.8, RGB8
+                 * 28.2 -> 26.0, nothing slower; without tables 1024^2 -> 64^2 went 12.6 -> 15.7, so those keep
+                 * the cost model's count (profiles/r02_box_spread_sweep.json).  SMOL_BOX_SPREAD=0: off. */
+                static int tune_spread = -1;
+                if (tune_spread < 0)
+                {
+                    const char *e = getenv ("SMOL_BOX_SPREAD");
+                    tune_spread = e ? atoi (e) : 1;
+                }
+                if (tune_spread && has_lut)
+                {
+                    const uint64_t items = (uint64_t) x_tiles * ((L.n_rows + best_k - 1) / best_k) * L.n_images;
+                    if (items <= (uint64_t) num_sms () * best_w)
+                    {
+                        uint32_t w_even = (uint32_t) ((items + num_sms () - 1) / num_sms ());
+                        w_even = w_even < 4 ? 4 : w_even;
+                        if (w_even < best_w)
+                            best_w = w_even;
+                    }
+                }
                 if (tune_wpc > 0 && (uint32_t) tune_wpc <= w_max)
                     best_w = (uint32_t) tune_wpc;
                 P.rows_per_item = best_k;
