@@ -204,3 +204,35 @@ def test_lut_headers_equal_reference_data(reference):
     # the two closed forms the survey found (ceil (2^16 / a), ceil (2^19 / a)) as an independent cross-check
     assert all(product["inv_div_p16"][a] == -(-(1 << 16) // a) for a in range(1, 256))
     assert all(product["inv_div_p16l"][a] == -(-(1 << 19) // a) for a in range(1, 256))
+
+
+def test_tile_window_bound_of_the_halving_tile_kernel(sb):
+    """launch_tile128h sizes a tile's shared-memory window as ceil (tile * dim_in / dim_out) + 5 pixels per axis
+    (smolscale-cuda-kernels.cu); the kernel traps if a tile's first and last taps span more.  Brute force over the
+    planner's own tables: every tile of every job stays inside the bound (the widest seen needs + 4)."""
+    import random
+    rnd = random.Random(1)
+    dims = []
+    for _ in range(400):
+        d_out = rnd.choice([1, 2, 3, 5, 7, 30, 31, 33, 64, 100, 127, 200, 333, 640, 1279, 1280]) if rnd.random() < 0.5 \
+            else rnd.randint(1, 2500)
+        d_in = min(65535, int(d_out * rnd.uniform(2.0, 8.0)) + rnd.randint(-2, 2))
+        if d_out * 2 < d_in <= d_out * 8:
+            dims.append((d_in, d_out))
+    assert len(dims) > 300
+    worst = -100
+    for d_in, d_out in dims:
+        p = sb.plan_query(cases.RGBA8_P, d_in, d_in, cases.RGBA8_P, d_out, d_out, 1, tables=True)
+        hh = p["halvings_h"]
+        assert p["filter_h"] == 2 and hh >= 1 and p["kernel_name"] == "taps128"
+        ofs = p["tab_x"][0::2].astype(np.int64)
+        assert (np.diff(ofs) >= 0).all()                      # the kernel takes the first and the last tap as the window's ends
+        for tile in (64, 32, 16, 8):
+            uncapped = (tile * d_in + d_out - 1) // d_out + 5
+            bound = min(uncapped, d_in)
+            t0 = np.arange(0, d_out, tile)
+            t1 = np.minimum(t0 + tile, d_out)
+            span = np.minimum(ofs[(t1 << hh) - 1] + 1, d_in - 1) - ofs[t0 << hh] + 1
+            assert (span <= bound).all(), (d_in, d_out, tile)
+            worst = max(worst, int((span - uncapped).max()))
+    assert worst <= -1                                         # a pixel of margin wherever the row itself is not the bound
