@@ -70,21 +70,28 @@ unfilter_row (uint8_t *row, const uint8_t *prev, size_t n, unsigned step, unsign
                     row [i] += prev [i];
             break;
         case 3:
-            for (i = 0; i < n; i++)
-            {
-                unsigned left = i >= step ? row [i - step] : 0;
-                unsigned up = prev ? prev [i] : 0;
-                row [i] += (left + up) >> 1;
-            }
+            /* the first pixel has no left neighbour; without a row above Average is half of Sub */
+            for (i = 0; i < step && i < n; i++)
+                row [i] += (prev ? prev [i] : 0) >> 1;
+            if (prev)
+                for (; i < n; i++)
+                    row [i] += (row [i - step] + prev [i]) >> 1;
+            else
+                for (; i < n; i++)
+                    row [i] += row [i - step] >> 1;
             break;
         case 4:
-            for (i = 0; i < n; i++)
+            /* Paeth (0, b, 0) = b on the first pixel, Paeth (a, 0, 0) = a on the first row */
+            if (!prev)
             {
-                int left = i >= step ? row [i - step] : 0;
-                int up = prev ? prev [i] : 0;
-                int ul = (prev && i >= step) ? prev [i - step] : 0;
-                row [i] += paeth (left, up, ul);
+                for (i = step; i < n; i++)
+                    row [i] += row [i - step];
+                break;
             }
+            for (i = 0; i < step && i < n; i++)
+                row [i] += prev [i];
+            for (; i < n; i++)
+                row [i] += paeth (row [i - step], prev [i], prev [i - step]);
             break;
         default:
             return SMOL_PNG_ERR_CORRUPT;
@@ -148,6 +155,21 @@ expand_row (const PngHeader *h, const uint8_t *row, uint32_t width, uint8_t *des
     const unsigned depth = h->info.bit_depth;
     const unsigned sample_bytes = depth == 16 ? 2 : 1;
     uint32_t x;
+
+    /* the two layouts nearly every file has */
+    if (depth == 8 && dx == 1 && h->info.color_type == 6)
+    {
+        memcpy (dest, row, (size_t) width * 4);
+        return;
+    }
+    if (depth == 8 && dx == 1 && h->info.color_type == 2 && !h->info.has_trns)
+    {
+        for (x = 0; x < width; x++, row += 3, dest += 4)
+        {
+            dest [0] = row [0]; dest [1] = row [1]; dest [2] = row [2]; dest [3] = 255;
+        }
+        return;
+    }
 
     for (x = 0; x < width; x++, dest += dx * 4)
     {
