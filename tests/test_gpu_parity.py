@@ -712,6 +712,25 @@ for gi, ti, wi, hi, si, to, wo, ho, so, srgb in T._taps128_family_jobs():
     got = T.cuda_scale(sb, src, ti, wi, hi, si, to, wo, ho, so, srgb)
     assert np.array_equal(got, want), ((ti, wi, hi, si, to, wo, ho, so, srgb), T.describe(got, want))
     n += 1
+# several images in one launch (grid.z), device buffers, image strides with padding
+import torch
+for ti, wi, hi, to, wo, ho, srgb in [(cases.RGBA8_P, 100, 100, cases.BGRA8_U, 33, 33, 1), (cases.ARGB8_U, 64, 48, cases.RGBA8_U, 9, 17, 0),
+                                     (cases.RGB8, 90, 70, cases.RGB8, 30, 11, 1)]:
+    si, so, k = wi * cases.bpp(ti), wo * cases.bpp(to), 5
+    stride_in, stride_out = si * hi + 32, so * ho + 48
+    srcs = [cases.make_image(ti, wi, hi, si, "premul" if ti < 4 else "random", seed=40 + i) for i in range(k)]
+    d_in = torch.zeros(stride_in * k, dtype=torch.uint8, device="cuda")
+    for i, s_ in enumerate(srcs):
+        d_in[i * stride_in: i * stride_in + s_.size] = torch.from_numpy(s_).cuda()
+    d_out = torch.full((stride_out * k,), 0xCD, dtype=torch.uint8, device="cuda")
+    sb.scale_images(d_in, stride_in, ti, wi, hi, si, d_out, stride_out, to, wo, ho, so, srgb, k)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    for i, s_ in enumerate(srcs):
+        want = chk.scale_simple(s_, ti, wi, hi, si, to, wo, ho, so, srgb)
+        assert np.array_equal(got[i * stride_out: i * stride_out + want.size], want), ("images", ti, to, i)
+        assert (got[i * stride_out + want.size: (i + 1) * stride_out] == 0xCD).all()
+    n += 1
 print("ok", n)
 """ % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, SMOL_TILE128H="1")
