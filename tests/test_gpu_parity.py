@@ -637,7 +637,9 @@ def test_rgb_destination_at_any_alignment(sb, restatement):
 
 TAPS128_GEOMETRIES = [(256, 256, 32, 32), (100, 100, 33, 33), (37, 29, 13, 11), (9, 9, 3, 4), (5, 5, 2, 2), (640, 480, 160, 120),
                       (255, 7, 100, 3), (7, 300, 3, 101), (300, 40, 300, 11), (40, 300, 11, 300), (131, 67, 17, 64),
-                      (1920, 1080, 640, 360), (3840, 2160, 1279, 2160), (2048, 64, 256, 200), (1024, 768, 128, 96)]
+                      (1920, 1080, 640, 360), (3840, 2160, 1279, 2160), (2048, 64, 256, 200), (1024, 768, 128, 96),
+                      # a halving on one axis with an upscale, a copy or a one-pixel dimension on the other
+                      (40, 300, 100, 100), (300, 37, 97, 90), (64, 200, 64, 50), (1, 100, 1, 30), (100, 1, 30, 1), (2, 9, 1, 3)]
 
 
 def _taps128_family_jobs():
